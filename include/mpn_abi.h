@@ -1,0 +1,212 @@
+/* ============================================================================
+ * mpn_abi.h — C ABI of libmpn_b200.so: the drop-in boundary for the
+ * multipathnet detection forward hot path on B200 (sm_100a).
+ *
+ * Plain C declarations only (no macros in prototypes, no torch/TH types) so the
+ * block between MPN_CDEF_BEGIN/END can be pasted verbatim into LuaJIT
+ * `ffi.cdef` (lua/mpn_ffi.lua does exactly that) and is what Python loads via
+ * ctypes (multipathnet_b200/_lib.py). Every entry point names the reference
+ * interface it replaces (paths relative to facebookresearch/multipathnet).
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; text via mpn_last_error.
+ *    Nothing exits, throws, or longjmps across the boundary.
+ *  - `*_dev` pointers are device pointers on the ctx's device; others are host
+ *    pointers. The caller owns all I/O buffers; the library owns ctx/model only.
+ *  - calls run on the ctx's stream; entry points taking/returning HOST buffers
+ *    are synchronous (like the reference's blocking :float()/:cuda() copies),
+ *    `_dev` entry points are stream-ordered and asynchronous.
+ *  - boxes are 1-based pixel coordinates [x1,y1,x2,y2]; ROI rows are
+ *    [batch_idx(1-based), x1, y1, x2, y2] (ImageDetect.lua:66-70).
+ *  - no global mutable state: one mpn_ctx per (thread, device)
+ *    (test_runner.lua:55-66 runs one replica per thread/GPU).
+ * ==========================================================================*/
+#ifndef MPN_ABI_H
+#define MPN_ABI_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* MPN_CDEF_BEGIN */
+
+typedef struct mpn_ctx mpn_ctx;
+typedef struct mpn_model mpn_model;
+
+/* ---- context ------------------------------------------------------------- */
+/* device: CUDA ordinal. cuda_stream: a cudaStream_t, or NULL for the legacy
+ * default stream (what cutorch uses unless cutorch.setStream was called).   */
+int mpn_ctx_create(int device, void *cuda_stream, mpn_ctx **out);
+void mpn_ctx_destroy(mpn_ctx *ctx);
+const char *mpn_last_error(const mpn_ctx *ctx);   /* ctx may be NULL: last create error */
+int mpn_ctx_synchronize(mpn_ctx *ctx);
+/* number of kernels THIS library launched on ctx since creation (bench.py's gpu_launches) */
+int64_t mpn_ctx_launch_count(const mpn_ctx *ctx);
+const char *mpn_version(void);
+
+/* ---- NMS: replaces utils.nms -> nms.c:NMS (utils.lua:29-33, nms.c:59-108) --
+ * scored_boxes: N x 5 [x1,y1,x2,y2,score]. Writes the kept ROW INDICES
+ * (0-based, selection order = the order nms.c emits its kept rows) into
+ * keep_idx (capacity N) and the count into *n_keep. Bit-exact vs nms.c,
+ * including its tie behaviour. Host buffers, synchronous.                   */
+int mpn_nms(mpn_ctx *ctx, const float *scored_boxes, int64_t N, float thr,
+            int32_t *keep_idx, int64_t *n_keep);
+/* Batched form (one launch set for all classes of an image, Tester_FRCNN.lua:106-117):
+ * segment s covers rows [seg_offsets[s], seg_offsets[s+1]) of scored_boxes;
+ * keep_idx is written at the same offsets (indices local to the segment),
+ * keep_counts[s] = number kept. Host buffers, synchronous.                  */
+int mpn_nms_batched(mpn_ctx *ctx, const float *scored_boxes, const int64_t *seg_offsets,
+                    int64_t nseg, float thr, int32_t *keep_idx, int64_t *keep_counts);
+/* Same, device buffers, stream-ordered (seg_offsets stays on the host).     */
+int mpn_nms_batched_dev(mpn_ctx *ctx, const float *scored_boxes_dev, const int64_t *seg_offsets,
+                        int64_t nseg, float thr, int32_t *keep_idx_dev, int32_t *keep_counts_dev);
+/* replaces utils.nms_dense (utils.lua:402-462, used by demo.lua:85): 0-based
+ * original indices in descending-score order; ties broken by ascending index. */
+int mpn_nms_dense(mpn_ctx *ctx, const float *scored_boxes, int64_t N, float thr,
+                  int32_t *pick_idx, int64_t *n_pick);
+/* replaces utils.bbox_vote -> nms.c:bbox_vote (utils.lua:35-39, nms.c:110-142) */
+int mpn_bbox_vote(mpn_ctx *ctx, const float *nms_boxes, int64_t K, const float *scored_boxes,
+                  int64_t N, float thr, float *res);
+
+/* ---- region modules ------------------------------------------------------ */
+/* nn.Foveal:updateOutput (modules/Foveal.lua:15-44): R x 5 -> 4R x 5, the four
+ * regions of ROI i consecutive; fp64 arithmetic rounded once to fp32.       */
+int mpn_foveal(mpn_ctx *ctx, const float *rois, int64_t R, float *out);
+/* nn.ContextRegion(scale):updateOutput (modules/ContextRegion.lua:14-32)     */
+int mpn_context_region(mpn_ctx *ctx, const float *rois, int64_t R, float scale, float *out);
+/* nn.BBoxNorm:updateOutput, evaluate mode (modules/BBoxNorm.lua:18-32): in place */
+int mpn_bbox_norm(mpn_ctx *ctx, float *deltas, int64_t R, int64_t C4, const float *mean4,
+                  const float *std4);
+/* utils.convertFrom tensor branch applied per class block of 4
+ * (ImageDetect.lua:183-185, utils.lua:226-246): deltas R x 4C, boxes R x 4.   */
+int mpn_bbox_decode(mpn_ctx *ctx, const float *deltas, const float *boxes, int64_t R, int64_t C,
+                    float *out);
+
+/* ---- inn.ROIPooling(W,H,scale):updateOutput {data, rois} ------------------
+ * (call sites vgg.lua:28, alexnet.lua:23, resnet.lua:48, model_utils.lua:215)
+ * fmap N x C x H x W fp32 (NCHW as Torch holds it), rois R x 5, out
+ * R x C x PH x PW, argmax (R*C*PH*PW int32, flat h*W+w or -1) may be NULL.
+ * variant: 1 = Caffe port (end inclusive), 2 = imagine-nn v2 (default).     */
+int mpn_roi_pool(mpn_ctx *ctx, const float *fmap, int64_t N, int64_t C, int64_t H, int64_t W,
+                 const float *rois, int64_t R, int32_t PW, int32_t PH, float spatial_scale,
+                 int32_t variant, float *out, int32_t *argmax);
+int mpn_roi_pool_dev(mpn_ctx *ctx, const float *fmap_dev, int64_t N, int64_t C, int64_t H,
+                     int64_t W, const float *rois_dev, int64_t R, int32_t PW, int32_t PH,
+                     float spatial_scale, int32_t variant, float *out_dev, int32_t *argmax_dev);
+
+/* ---- model: the nn.Sequential graphs of models/{vgg,multipathnet,resnet}.lua
+ * described as data. Layers operate on numbered tensor slots; slot 0 of the
+ * trunk is the input image (1 x 3 x H x W fp32, post-transformer).          */
+enum {
+  MPN_LAYER_CONV = 1,       /* conv kh x kw, stride, pad, + bias [+ residual] [+ ReLU]; a Linear is a 1x1 conv on a 1x1 map */
+  MPN_LAYER_MAXPOOL = 2,    /* k x k, stride, pad, ceil_mode */
+  MPN_LAYER_AVGPOOL = 3,    /* global average over H x W (ResNet avgpool 7) */
+  MPN_LAYER_FLATTEN = 4     /* (H,W,C) -> 1 x 1 x (H*W*C); reference order (c,ph,pw) is honoured by permuting the next weight */
+};
+typedef struct mpn_layer {
+  int32_t kind;
+  int32_t in_slot, out_slot;
+  int32_t cin, cout, kh, kw, stride, pad;
+  int32_t relu;             /* 1: ReLU fused after bias(+residual) */
+  int32_t residual_slot;    /* slot added before ReLU, or -1 */
+  int32_t ceil_mode;        /* pooling only */
+  int32_t weight, bias;     /* indices into weights[], -1 = none; conv weight is Cout x Cin x kh x kw (Torch layout) */
+} mpn_layer;
+
+typedef struct mpn_tower {   /* one region tower of multipathnet.lua:73-113, or THE head of vgg/resnet */
+  int32_t region;           /* 0 = the ROI itself, 1..3 = Foveal regions x1.5, x2, x4 (Foveal.lua:36-39) */
+  int32_t n_levels;         /* 1..3 pooled trunk taps, channel-concat order (model_utils.lua:229-235) */
+  int32_t level_slot[3];    /* trunk slot of each level */
+  float   level_scale[3];   /* spatial scale of each level (1/16, 1/8, 1/4) */
+  int32_t pooled_w, pooled_h;
+  int32_t normalize;        /* 1: L2-normalise each level then x1000 (model_utils.lua:217-220,240) */
+  int32_t n_layers;         /* per-ROI layers applied to the pooled R x PH x PW x C tensor (slot 0) */
+  int32_t first_layer;      /* index into the model's tower_layers[] array */
+  int32_t out_slot;         /* tower-local slot holding the R x 1 x 1 x F result */
+} mpn_tower;
+
+typedef struct mpn_head {    /* Linear over a column range of the towers' concat (multipathnet.lua:115-117) */
+  int32_t col_begin, col_len;
+  int32_t cout;
+  int32_t weight, bias;
+} mpn_head;
+
+typedef struct mpn_model_desc {
+  int32_t n_trunk_layers;  const mpn_layer *trunk_layers;
+  int32_t n_towers;        const mpn_tower *towers;
+  int32_t n_tower_layers;  const mpn_layer *tower_layers;
+  int32_t n_cls_heads;     const mpn_head *cls_heads;   /* >1: integral head, eval = mean of softmaxes (model_utils.lua:296-313) */
+  mpn_head bbox_head;
+  int32_t num_classes;     /* C incl. background */
+  int32_t roi_variant;     /* 1 or 2, see mpn_roi_pool */
+  int32_t no_softmax;      /* model.noSoftMax (ImageDetect.lua:189): scores are already probabilities */
+  int32_t has_bbox_norm;   /* nn.BBoxNorm appended (model_utils.lua:176-182) */
+  float bbox_mean[4], bbox_std[4];
+  int32_t max_rois;        /* capacity to allocate for */
+  int32_t max_h, max_w;    /* largest scaled image */
+} mpn_model_desc;
+
+/* weights[i] are HOST fp32 arrays in Torch layout with n_elem[i] elements; they are
+ * copied/re-laid-out at create, nothing is retained.                         */
+int mpn_model_create(mpn_ctx *ctx, const mpn_model_desc *desc, const float *const *weights,
+                     const int64_t *n_elem, int32_t n_weights, mpn_model **out);
+void mpn_model_destroy(mpn_model *m);
+
+/* model:get(1):forward — the conv trunk, once per image (ImageDetect.lua:107-108).
+ * image: 3 x H x W fp32 host (or device with _dev), already transformed+scaled. */
+int mpn_model_trunk(mpn_model *m, const float *image, int32_t H, int32_t W);
+int mpn_model_trunk_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W);
+/* modules 2..n on cached trunk features (recompute_features=false path,
+ * ImageDetect.lua:109-124): rois R x 5 in scaled-image coords. Outputs are the
+ * RAW network outputs: cls R x C (logits, or probabilities if no_softmax) and
+ * bbox R x 4C (after BBoxNorm if present) = what model:forward returns.      */
+int mpn_model_heads(mpn_model *m, const float *rois, int64_t R, float *cls_out, float *bbox_out);
+int mpn_model_heads_dev(mpn_model *m, const float *rois_dev, int64_t R, float *cls_out_dev,
+                        float *bbox_out_dev);
+
+/* ImageDetect:detect (ImageDetect.lua:156-193) after getImages: trunk (if
+ * recompute_features) + heads + convertFrom per class with the ORIGINAL boxes +
+ * softmax unless no_softmax. boxes R x 4 original-image coords, im_scale from
+ * getImages. scores R x C, bboxes R x 4C (host, synchronous).                */
+int mpn_model_detect(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes,
+                     int64_t R, float im_scale, int32_t recompute_features, float *scores,
+                     float *bboxes);
+/* detect + Tester_FRCNN:testOne post-processing (Tester_FRCNN.lua:75-78,106-117)
+ * in one stream-ordered pass: clamp to [1,W0]x[1,H0], per foreground class
+ * gather [box,score] rows with score > score_thresh, NMS at nms_thr.
+ * keep_idx: (C-1) x R int32 (row indices into the R proposals, selection order),
+ * keep_counts: C-1. scores/bboxes as mpn_model_detect but bboxes are clamped.
+ * All pointers host; any of scores/bboxes may be NULL to skip that copy.     */
+int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W,
+                         const float *boxes, int64_t R, float im_scale, float W0, float H0,
+                         float score_thresh, float nms_thr, float *scores, float *bboxes,
+                         int32_t *keep_idx, int32_t *keep_counts);
+/* Same with every buffer resident on the device, fully asynchronous (the
+ * throughput path: bench.py `value`). */
+int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W,
+                             const float *boxes_dev, int64_t R, float im_scale, float W0, float H0,
+                             float score_thresh, float nms_thr, float *scores_dev,
+                             float *bboxes_dev, int32_t *keep_idx_dev, int32_t *keep_counts_dev);
+
+/* introspection for tests/profiling: copy a trunk slot to host as N x C x H x W fp32 */
+int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_t capacity,
+                             int32_t *C, int32_t *H, int32_t *W);
+/* select conv/GEMM implementation: 0 = tcgen05 tensor-core path (default, product),
+ * 1 = plain fp32 CUDA-core check kernel (debug/verification only, very slow). */
+int mpn_model_set_conv_impl(mpn_model *m, int32_t impl);
+/* algorithmic FLOPs of the last trunk / heads call (SURVEY 8d definition)    */
+int mpn_model_last_flops(const mpn_model *m, double *trunk_flops, double *head_flops);
+
+/* standalone GEMM check entry (tests): C[M,N] = A[M,K] * B[N,K]^T + bias, fp32 host
+ * buffers, computed with the same split-bf16 tcgen05 kernel the model uses.  */
+int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bias, int64_t M,
+                   int64_t N, int64_t K, int32_t relu, int32_t impl, float *C);
+/* standalone conv check entry (tests): x N x Cin x H x W, w Cout x Cin x kh x kw (Torch layouts) */
+int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t H, int64_t W,
+                   const float *w, const float *bias, int64_t Cout, int32_t kh, int32_t kw,
+                   int32_t stride, int32_t pad, int32_t relu, int32_t impl, float *y);
+
+/* MPN_CDEF_END */
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPN_ABI_H */

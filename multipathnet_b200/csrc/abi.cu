@@ -1,0 +1,369 @@
+// abi.cu — context management and the host-buffer entry points of include/mpn_abi.h.
+// Host-pointer calls stage through ctx-owned device scratch, run on the ctx stream and
+// synchronise before returning (the reference's :cuda()/:float() copies block the same way).
+#include "conv_gemm.cuh"
+#include "roi.cuh"
+#include <algorithm>
+#include <mutex>
+
+int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
+int mpn_nms_dense_launch(mpn_ctx *, const float *, int, float, int32_t *, int32_t *);
+int mpn_bbox_vote_launch(mpn_ctx *, const float *, int, const float *, int, float, float *);
+int mpn_foveal_launch(mpn_ctx *, const float *, int64_t, float *);
+int mpn_context_region_launch(mpn_ctx *, const float *, int64_t, float, float *);
+int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
+int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
+int mpn_split_rows_launch(mpn_ctx *, const float *, int64_t, int64_t, int64_t, __nv_bfloat16 *, __nv_bfloat16 *, int64_t);
+int mpn_nchw_to_nhwc_split_launch(mpn_ctx *, const float *, int, int, int, int, DTensor &);
+int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
+int mpn_weight_permute_split_launch(mpn_ctx *, const float *, int64_t, int, int, int, __nv_bfloat16 *, __nv_bfloat16 *);
+
+static std::string g_create_err;
+static std::mutex g_create_mu;
+
+static int grow(mpn_ctx *ctx, void **p, size_t *have, size_t bytes, void **out) {
+  if (bytes > *have) {
+    if (*p) { cudaStreamSynchronize(ctx->stream); cudaFree(*p); *p = nullptr; *have = 0; }
+    size_t want = std::max(bytes, (size_t)1 << 20);
+    MPN_CUDA(ctx, cudaMalloc(p, want));
+    *have = want;
+  }
+  *out = *p;
+  return MPN_OK;
+}
+int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes, out); }
+int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, bytes, out); }
+
+// bump allocator over scratch slot 1 for the host-wrapper calls
+struct Arena {
+  mpn_ctx *ctx; size_t off = 0; char *base = nullptr; size_t cap = 0;
+  std::vector<size_t> sizes;
+  size_t reserve(size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; }
+  int commit() { void *p; MPN_TRY(mpn_scratch(ctx, off + 256, &p)); base = (char *)p; cap = off; return MPN_OK; }
+  template <class T> T *at(size_t o) { return reinterpret_cast<T *>(base + o); }
+};
+
+extern "C" {
+
+const char *mpn_version(void) { return "mpn_b200 0.1 (sm_100a; tcgen05 bf16x3 engine)"; }
+
+int mpn_ctx_create(int device, void *cuda_stream, mpn_ctx **out) {
+  if (!out) return MPN_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || device < 0 || device >= count) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = e != cudaSuccess ? std::string("no CUDA device: ") + cudaGetErrorString(e)
+                                    : "device ordinal out of range";
+    cudaGetLastError();
+    return MPN_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = std::string("cudaSetDevice/GetDeviceProperties failed: ") + cudaGetErrorString(e);
+    return MPN_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    std::lock_guard<std::mutex> lk(g_create_mu);
+    g_create_err = "libmpn_b200 is built for sm_100a (Blackwell B200) only; found sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor) + ". There is no fallback path.";
+    return MPN_ERR_STATE;
+  }
+  mpn_ctx *c = new mpn_ctx();
+  c->device = device; c->stream = (cudaStream_t)cuda_stream; c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return MPN_OK;
+}
+
+void mpn_ctx_destroy(mpn_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->scratch2) cudaFree(ctx->scratch2);
+  delete ctx;
+}
+
+const char *mpn_last_error(const mpn_ctx *ctx) {
+  if (!ctx) return g_create_err.c_str();
+  return ctx->err.c_str();
+}
+
+int mpn_ctx_synchronize(mpn_ctx *ctx) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+// ------------------------------------------------------------------ NMS family
+int mpn_nms_batched_dev(mpn_ctx *ctx, const float *scored_boxes_dev, const int64_t *seg_offsets, int64_t nseg,
+                        float thr, int32_t *keep_idx_dev, int32_t *keep_counts_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, seg_offsets && nseg >= 0, "seg_offsets missing");
+  if (nseg == 0) return MPN_OK;
+  // device form requires uniform segments (the pipeline's layout: nseg x cap x 5)
+  const int64_t cap = seg_offsets[1] - seg_offsets[0];
+  for (int64_t s = 0; s < nseg; ++s)
+    MPN_CHECK_ARG(ctx, seg_offsets[s + 1] - seg_offsets[s] == cap && seg_offsets[s] == s * cap,
+                  "mpn_nms_batched_dev needs uniform contiguous segments");
+  if (cap == 0) { MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream)); return MPN_OK; }
+  return mpn_nms_launch(ctx, scored_boxes_dev, (int)cap, (int)nseg, nullptr, nullptr, thr, keep_idx_dev, keep_counts_dev);
+}
+
+int mpn_nms_batched(mpn_ctx *ctx, const float *scored_boxes, const int64_t *seg_offsets, int64_t nseg, float thr,
+                    int32_t *keep_idx, int64_t *keep_counts) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, seg_offsets && keep_counts && nseg >= 0, "bad arguments");
+  if (nseg == 0) return MPN_OK;
+  int64_t cap = 0;
+  for (int64_t s = 0; s < nseg; ++s) {
+    MPN_CHECK_ARG(ctx, seg_offsets[s + 1] >= seg_offsets[s], "seg_offsets must be non-decreasing");
+    cap = std::max(cap, seg_offsets[s + 1] - seg_offsets[s]);
+  }
+  for (int64_t s = 0; s < nseg; ++s) keep_counts[s] = 0;
+  if (cap == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, scored_boxes && keep_idx, "buffers missing");
+  MPN_CHECK_ARG(ctx, cap <= 0x7fffffff / 8, "segment too large");
+  // repack ragged segments into the uniform-capacity device layout
+  std::vector<float> packed((size_t)nseg * cap * 5, 0.f);
+  std::vector<int32_t> counts(nseg);
+  for (int64_t s = 0; s < nseg; ++s) {
+    const int64_t n = seg_offsets[s + 1] - seg_offsets[s];
+    counts[s] = (int32_t)n;
+    if (n) memcpy(&packed[(size_t)s * cap * 5], scored_boxes + seg_offsets[s] * 5, sizeof(float) * 5 * (size_t)n);
+  }
+  Arena a{ctx};
+  size_t o_sb = a.reserve(sizeof(float) * packed.size()), o_cnt = a.reserve(sizeof(int32_t) * nseg),
+         o_keep = a.reserve(sizeof(int32_t) * (size_t)nseg * cap), o_kc = a.reserve(sizeof(int32_t) * nseg);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_sb), packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<int32_t>(o_cnt), counts.data(), sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_nms_launch(ctx, a.at<float>(o_sb), (int)cap, (int)nseg, a.at<int32_t>(o_cnt), nullptr, thr,
+                         a.at<int32_t>(o_keep), a.at<int32_t>(o_kc)));
+  std::vector<int32_t> hk((size_t)nseg * cap), hc(nseg);
+  MPN_CUDA(ctx, cudaMemcpyAsync(hk.data(), a.at<int32_t>(o_keep), sizeof(int32_t) * hk.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(hc.data(), a.at<int32_t>(o_kc), sizeof(int32_t) * nseg, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t s = 0; s < nseg; ++s) {
+    keep_counts[s] = hc[s];
+    if (hc[s]) memcpy(keep_idx + seg_offsets[s], &hk[(size_t)s * cap], sizeof(int32_t) * (size_t)hc[s]);
+  }
+  return MPN_OK;
+}
+
+int mpn_nms(mpn_ctx *ctx, const float *scored_boxes, int64_t N, float thr, int32_t *keep_idx, int64_t *n_keep) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CHECK_ARG(ctx, n_keep && N >= 0, "bad arguments");
+  int64_t offs[2] = {0, N};
+  return mpn_nms_batched(ctx, scored_boxes, offs, 1, thr, keep_idx, n_keep);
+}
+
+int mpn_nms_dense(mpn_ctx *ctx, const float *scored_boxes, int64_t N, float thr, int32_t *pick_idx, int64_t *n_pick) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, n_pick && N >= 0, "bad arguments");
+  *n_pick = 0;
+  if (N == 0) return MPN_OK;     // utils.lua:405-407 returns an empty LongTensor
+  MPN_CHECK_ARG(ctx, scored_boxes && pick_idx, "buffers missing");
+  Arena a{ctx};
+  size_t o_sb = a.reserve(sizeof(float) * 5 * (size_t)N), o_pick = a.reserve(sizeof(int32_t) * (size_t)N), o_cnt = a.reserve(16);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_sb), scored_boxes, sizeof(float) * 5 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_nms_dense_launch(ctx, a.at<float>(o_sb), (int)N, thr, a.at<int32_t>(o_pick), a.at<int32_t>(o_cnt)));
+  int32_t cnt = 0;
+  MPN_CUDA(ctx, cudaMemcpyAsync(&cnt, a.at<int32_t>(o_cnt), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cnt) MPN_CUDA(ctx, cudaMemcpy(pick_idx, a.at<int32_t>(o_pick), sizeof(int32_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  *n_pick = cnt;
+  return MPN_OK;
+}
+
+int mpn_bbox_vote(mpn_ctx *ctx, const float *nms_boxes, int64_t K, const float *scored_boxes, int64_t N, float thr,
+                  float *res) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, K >= 0 && N >= 0, "bad arguments");
+  if (K == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, nms_boxes && res && (N == 0 || scored_boxes), "buffers missing");
+  Arena a{ctx};
+  size_t o_n = a.reserve(sizeof(float) * 5 * (size_t)K), o_s = a.reserve(sizeof(float) * 5 * (size_t)std::max<int64_t>(N, 1)),
+         o_r = a.reserve(sizeof(float) * 5 * (size_t)K);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_n), nms_boxes, sizeof(float) * 5 * (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
+  if (N) MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_s), scored_boxes, sizeof(float) * 5 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_bbox_vote_launch(ctx, a.at<float>(o_n), (int)K, a.at<float>(o_s), (int)N, thr, a.at<float>(o_r)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(res, a.at<float>(o_r), sizeof(float) * 5 * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------ region modules
+static int unary_rois(mpn_ctx *ctx, const float *in, int64_t R, int64_t out_rows_per_in, float *out,
+                      int (*launch)(mpn_ctx *, const float *, int64_t, float, float *), float param) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0, "bad R");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, in && out, "buffers missing");
+  Arena a{ctx};
+  size_t o_i = a.reserve(sizeof(float) * 5 * (size_t)R), o_o = a.reserve(sizeof(float) * 5 * (size_t)(R * out_rows_per_in));
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_i), in, sizeof(float) * 5 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(launch(ctx, a.at<float>(o_i), R, param, a.at<float>(o_o)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, a.at<float>(o_o), sizeof(float) * 5 * (size_t)(R * out_rows_per_in), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+static int foveal_adapter(mpn_ctx *c, const float *i, int64_t R, float, float *o) { return mpn_foveal_launch(c, i, R, o); }
+
+int mpn_foveal(mpn_ctx *ctx, const float *rois, int64_t R, float *out) { return unary_rois(ctx, rois, R, 4, out, foveal_adapter, 0.f); }
+int mpn_context_region(mpn_ctx *ctx, const float *rois, int64_t R, float scale, float *out) {
+  return unary_rois(ctx, rois, R, 1, out, mpn_context_region_launch, scale);
+}
+
+int mpn_bbox_norm(mpn_ctx *ctx, float *deltas, int64_t R, int64_t C4, const float *mean4, const float *std4) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0 && C4 > 0 && C4 % 4 == 0, "BBoxNorm: input:size(2) % 4 == 0 required (BBoxNorm.lua:19)");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, deltas && mean4 && std4, "buffers missing");
+  Arena a{ctx};
+  size_t o = a.reserve(sizeof(float) * (size_t)(R * C4));
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o), deltas, sizeof(float) * (size_t)(R * C4), cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_bbox_norm_launch(ctx, a.at<float>(o), R, C4, mean4, std4));
+  MPN_CUDA(ctx, cudaMemcpyAsync(deltas, a.at<float>(o), sizeof(float) * (size_t)(R * C4), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_bbox_decode(mpn_ctx *ctx, const float *deltas, const float *boxes, int64_t R, int64_t C, float *out) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0 && C > 0, "bad arguments");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, deltas && boxes && out, "buffers missing");
+  Arena a{ctx};
+  size_t o_d = a.reserve(sizeof(float) * 4 * (size_t)(R * C)), o_b = a.reserve(sizeof(float) * 4 * (size_t)R),
+         o_o = a.reserve(sizeof(float) * 4 * (size_t)(R * C));
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_d), deltas, sizeof(float) * 4 * (size_t)(R * C), cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_b), boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_bbox_decode_launch(ctx, a.at<float>(o_d), a.at<float>(o_b), R, (int)C, 0, 0.f, 0.f, a.at<float>(o_o)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, a.at<float>(o_o), sizeof(float) * 4 * (size_t)(R * C), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------ inn.ROIPooling
+int mpn_roi_pool_dev(mpn_ctx *ctx, const float *fmap_dev, int64_t N, int64_t C, int64_t H, int64_t W,
+                     const float *rois_dev, int64_t R, int32_t PW, int32_t PH, float spatial_scale, int32_t variant,
+                     float *out_dev, int32_t *argmax_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && PW > 0 && PH > 0, "bad geometry");
+  MPN_CHECK_ARG(ctx, variant == 1 || variant == 2, "variant must be 1 or 2");
+  return mpn_roi_pool_nchw_launch(ctx, fmap_dev, N, C, H, W, rois_dev, R, PW, PH, spatial_scale, variant, out_dev, argmax_dev);
+}
+
+int mpn_roi_pool(mpn_ctx *ctx, const float *fmap, int64_t N, int64_t C, int64_t H, int64_t W, const float *rois,
+                 int64_t R, int32_t PW, int32_t PH, float spatial_scale, int32_t variant, float *out, int32_t *argmax) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, N > 0 && C > 0 && H > 0 && W > 0 && R >= 0 && PW > 0 && PH > 0, "bad geometry");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, fmap && rois && out, "buffers missing");
+  for (int64_t r = 0; r < R; ++r) {
+    const float b = rois[5 * r];
+    MPN_CHECK_ARG(ctx, b >= 1.f && b <= (float)N, "ROI batch index out of range (1-based, ImageDetect.lua:69)");
+  }
+  const size_t nf = (size_t)(N * C * H * W), no = (size_t)(R * C * PH * PW);
+  Arena a{ctx};
+  size_t o_f = a.reserve(sizeof(float) * nf), o_r = a.reserve(sizeof(float) * 5 * (size_t)R), o_o = a.reserve(sizeof(float) * no),
+         o_a = a.reserve(sizeof(int32_t) * no);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_f), fmap, sizeof(float) * nf, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_r), rois, sizeof(float) * 5 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_roi_pool_dev(ctx, a.at<float>(o_f), N, C, H, W, a.at<float>(o_r), R, PW, PH, spatial_scale, variant,
+                           a.at<float>(o_o), argmax ? a.at<int32_t>(o_a) : nullptr));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, a.at<float>(o_o), sizeof(float) * no, cudaMemcpyDeviceToHost, ctx->stream));
+  if (argmax) MPN_CUDA(ctx, cudaMemcpyAsync(argmax, a.at<int32_t>(o_a), sizeof(int32_t) * no, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------ engine check entries
+int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t H, int64_t W, const float *w,
+                   const float *bias, int64_t Cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad, int32_t relu,
+                   int32_t impl, float *y) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, x && w && y && N > 0 && Cin > 0 && Cout > 0 && H > 0 && W > 0, "bad arguments");
+  const int64_t Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  MPN_CHECK_ARG(ctx, Ho > 0 && Wo > 0, "empty output");
+  const size_t nx = (size_t)(N * Cin * H * W), nw = (size_t)(Cout * Cin * kh * kw), ny = (size_t)(N * Cout * Ho * Wo);
+  Arena a{ctx};
+  size_t o_x = a.reserve(4 * nx), o_w = a.reserve(4 * nw), o_b = a.reserve(4 * (size_t)Cout), o_y = a.reserve(4 * ny),
+         o_xh = a.reserve(2 * nx), o_xl = a.reserve(2 * nx), o_wh = a.reserve(2 * nw), o_wl = a.reserve(2 * nw),
+         o_yh = a.reserve(2 * ny), o_yl = a.reserve(2 * ny);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_x), x, 4 * nx, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_w), w, 4 * nw, cudaMemcpyHostToDevice, ctx->stream));
+  if (bias) MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_b), bias, 4 * (size_t)Cout, cudaMemcpyHostToDevice, ctx->stream));
+  DTensor ty; ty.hi = a.at<__nv_bfloat16>(o_yh); ty.lo = a.at<__nv_bfloat16>(o_yl); ty.N = N; ty.H = Ho; ty.W = Wo; ty.C = Cout; ty.ld = Cout;
+  if (impl == 2) {       // CUDA-core direct conv straight from the NCHW fp32 input (first-layer kernel)
+    MPN_TRY(conv_direct_nchw_launch(ctx, a.at<float>(o_x), (int)N, (int)Cin, (int)H, (int)W, a.at<float>(o_w),
+                                    bias ? a.at<float>(o_b) : nullptr, (int)Cout, kh, kw, stride, pad, relu, ty));
+  } else {
+    DTensor tx; tx.hi = a.at<__nv_bfloat16>(o_xh); tx.lo = a.at<__nv_bfloat16>(o_xl); tx.N = N; tx.H = H; tx.W = W; tx.C = Cin; tx.ld = Cin;
+    MPN_TRY(mpn_nchw_to_nhwc_split_launch(ctx, a.at<float>(o_x), (int)N, (int)Cin, (int)H, (int)W, tx));
+    MPN_TRY(mpn_weight_permute_split_launch(ctx, a.at<float>(o_w), Cout, (int)Cin, kh, kw, a.at<__nv_bfloat16>(o_wh), a.at<__nv_bfloat16>(o_wl)));
+    ConvProblem p; p.x = tx; p.w_hi = a.at<__nv_bfloat16>(o_wh); p.w_lo = a.at<__nv_bfloat16>(o_wl);
+    p.bias = bias ? a.at<float>(o_b) : nullptr; p.Cout = (int)Cout; p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.relu = relu;
+    p.y = ty;
+    if (impl == 1) { MPN_TRY(conv_ref_launch(ctx, p)); }
+    else { ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl)); }
+  }
+  MPN_TRY(mpn_nhwc_split_to_nchw_launch(ctx, ty, a.at<float>(o_y)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(y, a.at<float>(o_y), 4 * ny, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bias, int64_t M, int64_t N, int64_t K,
+                   int32_t relu, int32_t impl, float *C) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
+  const size_t na = (size_t)(M * K), nb = (size_t)(N * K), nc = (size_t)(M * N);
+  Arena a{ctx};
+  size_t o_a = a.reserve(4 * na), o_b = a.reserve(4 * nb), o_bias = a.reserve(4 * (size_t)N), o_c = a.reserve(4 * nc),
+         o_ah = a.reserve(2 * na), o_al = a.reserve(2 * na), o_bh = a.reserve(2 * nb), o_bl = a.reserve(2 * nb);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_a), A, 4 * na, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_b), B, 4 * nb, cudaMemcpyHostToDevice, ctx->stream));
+  if (bias) MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_bias), bias, 4 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_split_rows_launch(ctx, a.at<float>(o_a), M, K, K, a.at<__nv_bfloat16>(o_ah), a.at<__nv_bfloat16>(o_al), K));
+  MPN_TRY(mpn_split_rows_launch(ctx, a.at<float>(o_b), N, K, K, a.at<__nv_bfloat16>(o_bh), a.at<__nv_bfloat16>(o_bl), K));
+  ConvProblem p;
+  p.x.hi = a.at<__nv_bfloat16>(o_ah); p.x.lo = a.at<__nv_bfloat16>(o_al); p.x.N = M; p.x.H = 1; p.x.W = 1; p.x.C = K; p.x.ld = K;
+  p.w_hi = a.at<__nv_bfloat16>(o_bh); p.w_lo = a.at<__nv_bfloat16>(o_bl); p.bias = bias ? a.at<float>(o_bias) : nullptr;
+  p.Cout = (int)N; p.relu = relu;
+  p.y.f32 = a.at<float>(o_c); p.y.N = M; p.y.H = 1; p.y.W = 1; p.y.C = N; p.y.ld = N; p.y_f32_ld = N;
+  if (impl == 1) { MPN_TRY(conv_ref_launch(ctx, p)); }
+  else { ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl)); }
+  MPN_CUDA(ctx, cudaMemcpyAsync(C, a.at<float>(o_c), 4 * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+}  // extern "C"

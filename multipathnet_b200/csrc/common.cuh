@@ -1,0 +1,96 @@
+// common.cuh — context, error plumbing and small device helpers shared by all TUs
+// of libmpn_b200.so. sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/mpn_abi.h"
+
+struct mpn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string err;
+  int64_t launches = 0;
+  // scratch owned by the ctx (grown on demand, never shrunk)
+  void *scratch = nullptr; size_t scratch_bytes = 0;
+  void *scratch2 = nullptr; size_t scratch2_bytes = 0;
+};
+
+#define MPN_OK 0
+#define MPN_ERR_ARG (-1)
+#define MPN_ERR_CUDA (-2)
+#define MPN_ERR_STATE (-3)
+
+inline int mpn_fail(mpn_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define MPN_CUDA(ctx, expr)                                                         \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      char b__[512];                                                                \
+      snprintf(b__, sizeof b__, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), \
+               __FILE__, __LINE__, cudaGetErrorString(e__));                        \
+      cudaGetLastError();                                                           \
+      return mpn_fail((ctx), MPN_ERR_CUDA, b__);                                    \
+    }                                                                               \
+  } while (0)
+
+#define MPN_CHECK_ARG(ctx, cond, msg)                                   \
+  do {                                                                  \
+    if (!(cond)) return mpn_fail((ctx), MPN_ERR_ARG, std::string(msg)); \
+  } while (0)
+
+#define MPN_TRY(expr)           \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != MPN_OK) return r__; \
+  } while (0)
+
+// count + check a kernel launch
+#define MPN_LAUNCHED(ctx)                 \
+  do {                                    \
+    (ctx)->launches++;                    \
+    MPN_CUDA((ctx), cudaGetLastError());  \
+  } while (0)
+
+int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out);    // slot 1
+int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out);   // slot 2
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- split-bf16 representation ------------------------------------------------
+// Every activation / weight that feeds the tensor cores is stored as two bf16
+// planes: hi = bf16_rn(x), lo = bf16_rn(x - hi). hi + lo reproduces x to ~2^-17
+// relative; the GEMMs issue hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
+  return __bfloat162float(hi) + __bfloat162float(lo);
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b16) { return __uint_as_float(b16 << 16); }
+// unpack a uint32 holding two bf16 (low = element 0)
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// A device tensor in the library's internal layout: NHWC, either split-bf16 planes
+// (hi, lo) or fp32, with a pixel stride `ld` (elements) so channel slices alias.
+struct DTensor {
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  float *f32 = nullptr;
+  int64_t N = 0, H = 0, W = 0, C = 0, ld = 0;
+  int64_t pixels() const { return N * H * W; }
+};

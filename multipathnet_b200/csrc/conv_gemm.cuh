@@ -1,0 +1,37 @@
+// conv_gemm.cuh — shared declarations for the convolution / GEMM engines.
+#pragma once
+#include "common.cuh"
+#include <cuda.h>   // CUtensorMap type only; the encode entry point is fetched at run time
+
+// One convolution (or Linear = 1x1 conv on a 1x1 map) in the internal NHWC split-bf16
+// representation. y[n,ho,wo,co] = sum_{kh,kw,ci} x[n, ho*s+kh-p, wo*s+kw-p, ci] * w[co,(kh,kw,ci)]
+//                                 + bias[co] (+ residual) (ReLU)
+struct ConvProblem {
+  DTensor x;                       // input  (split planes)
+  const __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;   // [Cout][kh*kw*Cin], K order (kh,kw,ci)
+  const float *bias = nullptr;     // [Cout] or null
+  int Cout = 0, kh = 1, kw = 1, stride = 1, pad = 0;
+  int relu = 0;
+  DTensor res;                     // optional residual (split planes), same geometry as y
+  DTensor y;                       // output: split planes (hi/lo) and/or f32; y.ld / f32_ld = pixel strides
+  int64_t y_f32_ld = 0;
+};
+
+// Plan = tile decomposition + TMA descriptors for one ConvProblem on the tcgen05 path.
+struct ConvPlan {
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  int BN = 0;                      // 64 / 128 / 256
+  int tn = 0, th = 0, tw = 0;      // 128 output pixels per M tile = tn*th*tw
+  int tiles_img = 0, tiles_h = 0, tiles_w = 0, tiles_n = 0;
+  int flat = 0;                    // 1: 1x1/s1/p0 => pixels treated as one flat axis
+  int valid = 0;
+};
+
+int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &plan);
+int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &plan);
+int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p);           // CUDA-core fp32 check kernel
+// first-layer direct conv: x is NCHW fp32 (N x Cin x H x W), w fp32 [Cout][Cin][kh][kw] (Torch layout)
+int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
+                            const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu,
+                            DTensor &y);
+double conv_flops(const ConvProblem &p);

@@ -1,0 +1,133 @@
+// conv_simt.cu — CUDA-core convolution kernels (sm_100a).
+//  * conv_direct_nchw_kernel: the FIRST trunk layer (Cin=3: VGG conv1_1 K=27, ResNet conv1
+//    7x7/s2 K=147). K is too small for a 64-wide tensor-core K block, the layer is ~0.6 % of
+//    the trunk FLOPs and HBM-write-bound; it reads the NCHW fp32 image exactly as
+//    ImageDetect hands it over (ImageDetect.lua:167-169) and emits NHWC split-bf16 planes.
+//  * conv_ref_kernel: a deliberately plain one-thread-per-output fp32 kernel over the same
+//    split-bf16 operands as the tcgen05 engine. Verification/debug only (mpn_model_set_conv_impl
+//    = 1, mpn_*_check impl=1): it lets tests separate "tensor-core engine bug" from "graph bug".
+#include "conv_gemm.cuh"
+
+namespace {
+
+constexpr int DC_CO = 16;   // output channels per thread
+
+__global__ void __launch_bounds__(256)
+conv_direct_nchw_kernel(const float *__restrict__ x, int N, int Cin, int H, int W, const float *__restrict__ w,
+                        const float *__restrict__ bias, int Cout, int kh, int kw, int stride, int pad, int relu,
+                        int Ho, int Wo, __nv_bfloat16 *__restrict__ oh, __nv_bfloat16 *__restrict__ ol,
+                        long long ld) {
+  extern __shared__ float s_w[];   // [DC_CO][Cin*kh*kw] for this block's channel group
+  const int K = Cin * kh * kw;
+  const int co0 = blockIdx.y * DC_CO;
+  for (int i = threadIdx.x; i < DC_CO * K; i += blockDim.x) {
+    int co = co0 + i / K;
+    s_w[i] = (co < Cout) ? w[(size_t)co * K + (i % K)] : 0.f;
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * Ho * Wo) return;
+  const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+  float acc[DC_CO];
+#pragma unroll
+  for (int c = 0; c < DC_CO; ++c) acc[c] = 0.f;
+  for (int ci = 0; ci < Cin; ++ci)
+    for (int r = 0; r < kh; ++r) {
+      const int hi = ho * stride + r - pad;
+      if (hi < 0 || hi >= H) continue;
+      for (int q = 0; q < kw; ++q) {
+        const int wi = wo * stride + q - pad;
+        if (wi < 0 || wi >= W) continue;
+        const float v = __ldg(x + (((size_t)n * Cin + ci) * H + hi) * W + wi);
+        const int kidx = (ci * kh + r) * kw + q;
+#pragma unroll
+        for (int c = 0; c < DC_CO; ++c) acc[c] = fmaf(v, s_w[c * K + kidx], acc[c]);
+      }
+    }
+#pragma unroll
+  for (int g = 0; g < DC_CO / 8; ++g) {
+    const int c = co0 + g * 8;
+    if (c >= Cout) break;
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float f0 = acc[g * 8 + 2 * t] + (bias ? __ldg(bias + c + 2 * t) : 0.f);
+      float f1 = acc[g * 8 + 2 * t + 1] + (bias ? __ldg(bias + c + 2 * t + 1) : 0.f);
+      if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(f0, h0, l0); split_bf16(f1, h1, l1);
+      ph[t] = pack_bf16x2(h0, h1); pl[t] = pack_bf16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4 *>(oh + pix * ld + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4 *>(ol + pix * ld + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+struct RefParams {
+  const __nv_bfloat16 *xh, *xl; long long xld; int N, H, W, Cin;
+  const __nv_bfloat16 *wh, *wl;
+  const float *bias; int Cout, kh, kw, stride, pad, relu, Ho, Wo;
+  const __nv_bfloat16 *rh, *rl; long long rld;
+  __nv_bfloat16 *oh, *ol; long long old_;
+  float *of; long long ofld;
+};
+
+__global__ void __launch_bounds__(256) conv_ref_kernel(const RefParams p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  if (idx >= total) return;
+  const int co = (int)(idx % p.Cout); const long long pix = idx / p.Cout;
+  const int wo = (int)(pix % p.Wo), ho = (int)((pix / p.Wo) % p.Ho), n = (int)(pix / ((long long)p.Wo * p.Ho));
+  float acc = 0.f;
+  const long long Ktot = (long long)p.kh * p.kw * p.Cin;
+  for (int r = 0; r < p.kh; ++r) {
+    const int hi = ho * p.stride + r - p.pad;
+    if (hi < 0 || hi >= p.H) continue;
+    for (int q = 0; q < p.kw; ++q) {
+      const int wi = wo * p.stride + q - p.pad;
+      if (wi < 0 || wi >= p.W) continue;
+      const long long xo = (((long long)n * p.H + hi) * p.W + wi) * p.xld;
+      const long long wo_ = (long long)co * Ktot + (long long)(r * p.kw + q) * p.Cin;
+      for (int ci = 0; ci < p.Cin; ++ci) {
+        const float a = join_bf16(p.xh[xo + ci], p.xl[xo + ci]);
+        const float b = join_bf16(p.wh[wo_ + ci], p.wl[wo_ + ci]);
+        acc = fmaf(a, b, acc);
+      }
+    }
+  }
+  if (p.bias) acc += p.bias[co];
+  if (p.rh) acc += join_bf16(p.rh[pix * p.rld + co], p.rl[pix * p.rld + co]);
+  if (p.relu) acc = fmaxf(acc, 0.f);
+  if (p.oh) { __nv_bfloat16 h, l; split_bf16(acc, h, l); p.oh[pix * p.old_ + co] = h; p.ol[pix * p.old_ + co] = l; }
+  if (p.of) p.of[pix * p.ofld + co] = acc;
+}
+
+}  // namespace
+
+int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
+                            const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu, DTensor &y) {
+  MPN_CHECK_ARG(ctx, Cout % 8 == 0, "conv_direct: Cout must be a multiple of 8");
+  const long long pixels = (long long)N * y.H * y.W;
+  if (pixels <= 0) return MPN_OK;
+  const size_t smem = sizeof(float) * DC_CO * Cin * kh * kw;
+  MPN_CHECK_ARG(ctx, smem <= 48 * 1024, "conv_direct: filter too large");
+  dim3 grid((unsigned)((pixels + 255) / 256), (unsigned)((Cout + DC_CO - 1) / DC_CO));
+  conv_direct_nchw_kernel<<<grid, 256, smem, ctx->stream>>>(x_nchw, N, Cin, H, W, w, bias, Cout, kh, kw, stride, pad,
+                                                          relu, (int)y.H, (int)y.W, y.hi, y.lo, y.ld);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
+int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p) {
+  RefParams r;
+  r.xh = p.x.hi; r.xl = p.x.lo; r.xld = p.x.ld; r.N = (int)p.x.N; r.H = (int)p.x.H; r.W = (int)p.x.W; r.Cin = (int)p.x.C;
+  r.wh = p.w_hi; r.wl = p.w_lo; r.bias = p.bias; r.Cout = p.Cout; r.kh = p.kh; r.kw = p.kw; r.stride = p.stride;
+  r.pad = p.pad; r.relu = p.relu; r.Ho = (int)p.y.H; r.Wo = (int)p.y.W;
+  r.rh = p.res.hi; r.rl = p.res.lo; r.rld = p.res.ld;
+  r.oh = p.y.hi; r.ol = p.y.lo; r.old_ = p.y.ld; r.of = p.y.f32; r.ofld = p.y_f32_ld;
+  const long long total = (long long)r.N * r.Ho * r.Wo * r.Cout;
+  if (total <= 0) return MPN_OK;
+  conv_ref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(r);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}

@@ -1,0 +1,444 @@
+// gemm_tc.cu — the tensor-core engine: implicit-GEMM convolution / Linear on tcgen05
+// (5th-gen tensor cores) with TMEM accumulators, operands staged by TMA. sm_100a only.
+//
+// Replaces cudnn.SpatialConvolution and nn.Linear (cuBLAS SGEMM) on the reference hot path
+// (trunks of models/{vgg,multipathnet,resnet}.lua, fc6/fc7/cls/bbox of
+// model_utils.lua:105-119, 1x1 conv_mix of model_utils.lua:242).
+//
+// Numerics: fp32-faithful "bf16x3" — every operand is held as two bf16 planes
+// (hi = rn(x), lo = rn(x-hi)); each K step issues hi*hi + lo*hi + hi*lo into one fp32 TMEM
+// accumulator (the dropped lo*lo term is ~2^-18 relative). Result error ~1e-5 relative,
+// well inside the 1e-3 parity bar that single-pass TF32 (10-bit mantissa) misses over
+// 13 convs + 2 fcs, at 3 bf16 MMAs per step = 1.5x the cost of one TF32 pass.
+//
+// Kernel shape (persistent, warp-specialised, one CTA per SM):
+//   warp 0      : TMA producer  — per K block: A tile (128 pixels x 64 ch, hi+lo) by a 4-D
+//                 tiled tensor map over the NHWC activation whose box is a tn x th x tw pixel
+//                 patch shifted by the filter tap (zero OOB fill = conv padding, elementStrides
+//                 = conv stride), B tile (BN x 64, hi+lo) from the [Cout][kh*kw*Cin] weights.
+//   warp 1      : MMA issuer    — one elected lane issues 12 tcgen05.mma (3 products x 4 k16)
+//                 per K block into a double-buffered TMEM accumulator; tcgen05.commit frees the
+//                 smem stage / publishes the accumulator.
+//   warps 2..5  : epilogue      — tcgen05.ld 32 columns at a time, + bias (+ residual) (ReLU),
+//                 re-split to bf16 hi/lo (NHWC, next layer's A operand) and/or fp32.
+// All 128B-swizzled K-major smem tiles; mbarrier pipelines (full/empty per stage,
+// tmem_full/tmem_empty per accumulator buffer).
+#include "conv_gemm.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M (pixels per tile)
+constexpr int BK = 64;           // bf16 elements per K block = one 128B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;  // 6 warps
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB per plane
+
+__host__ __device__ constexpr int stage_bytes(int BN) { return 2 * A_TILE_BYTES + 2 * BN * BK * 2; }
+__host__ __device__ constexpr int num_stages(int BN) { return BN == 256 ? 2 : (BN == 128 ? 3 : 4); }
+__host__ __device__ constexpr int tmem_cols(int BN) { return BN == 256 ? 512 : (BN == 128 ? 256 : 128); }
+
+struct TcParams {
+  int N, Ho, Wo, Cout;           // output geometry (flat mode: N=1, Ho=1, Wo=pixels)
+  int kh, kw, stride, pad;
+  int cblocks;                   // Cin / 64
+  int tn, th, tw;                // tile decomposition (powers of two)
+  int tiles_img, tiles_h, tiles_w, tiles_n;
+  const float *bias;
+  const __nv_bfloat16 *res_hi, *res_lo; long long res_ld;
+  __nv_bfloat16 *out_hi, *out_lo; long long out_ld;
+  float *out_f32; long long out_f32_ld;
+  int relu;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled smem tile descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major; 1) | SBO>>4 [32,46) = 1024B/16
+// (stride between 8-row groups) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6) | a_format BF16=1 [7,10) | b_format BF16=1 [10,13) |
+// a_major K=0 [15] | b_major K=0 [16] | N>>3 [17,23) | M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const TcParams p) {
+  constexpr int S = num_stages(BN);
+  constexpr int STAGE = stage_bytes(BN);
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr uint32_t IDESC = make_idesc(BM, BN);
+  extern __shared__ uint8_t smem_raw[];
+  // 1024B alignment for SWIZZLE_128B tiles
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = p.tiles_img * p.tiles_h * p.tiles_w;
+  const int total_tiles = tiles_m * p.tiles_n;
+  const int num_kb = p.kh * p.kw * p.cblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+        const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+        const int w_in0 = twi * p.tw * p.stride - p.pad, h_in0 = thi * p.th * p.stride - p.pad, n0 = tni * p.tn;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % S; const uint32_t ph = (it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+          const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+          mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
+          tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+          tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+          tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, nt * BN);
+          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
+      mbar_wait(tempty_bar(a), aph ^ 1u);        // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % S; const uint32_t ph = (it / S) & 1u;
+        mbar_wait(full_bar(s), ph);                // TMA bytes landed
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + (uint32_t)s * STAGE;
+          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
+          const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
+            tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+            tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+          }
+          tc_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+          if (kb == num_kb - 1) tc_commit(tfull_bar(a));   // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;               // accumulator row = pixel within the tile
+    const int wl = row & (p.tw - 1), hl = (row / p.tw) & (p.th - 1), nl = row / (p.tw * p.th);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
+      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+      const int wo = twi * p.tw + wl, ho = thi * p.th + hl, n = tni * p.tn + nl;
+      const bool row_ok = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
+      const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
+      mbar_wait(tfull_bar(a), aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
+        tc_wait_ld();
+        const int col0 = nt * BN + ch * 32;
+        if (row_ok && col0 < p.Cout) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {             // 8 output channels per group
+            const int c = col0 + g * 8;
+            if (c >= p.Cout) break;
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+            const bool full8 = (c + 8 <= p.Cout);
+            if (p.bias) {
+              if (full8) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + c));
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + c + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              } else {
+                for (int e = 0; e < 8 && c + e < p.Cout; ++e) f[e] += __ldg(p.bias + c + e);
+              }
+            }
+            if (p.res_hi && full8) {
+              const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + c);
+              const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + c);
+              const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 x = bf16x2_to_float2(hh[t]), y = bf16x2_to_float2(ll[t]);
+                f[2 * t] += x.x + y.x; f[2 * t + 1] += x.y + y.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            if (p.out_hi && full8) {
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(f[2 * t], h0, l0); split_bf16(f[2 * t + 1], h1, l1);
+                oh[t] = pack_bf16x2(h0, h1); ol[t] = pack_bf16x2(l0, l1);
+              }
+              *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            }
+            if (p.out_f32) {
+              float *o = p.out_f32 + pix * p.out_f32_ld + c;
+              if (full8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                reinterpret_cast<float4 *>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+                reinterpret_cast<float4 *>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+              } else {
+                for (int e = 0; e < 8 && c + e < p.Cout; ++e) o[e] = f[e];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));   // 4 arrivals (one per epilogue warp) free the buffer
+    }
+  }
+
+  // ---- teardown: everyone done with TMEM before the allocating warp frees it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host: TMA descriptors
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void *p = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int encode_map(mpn_ctx *ctx, CUtensorMap *tm, const void *base, int rank, const cuuint64_t *dims,
+               const cuuint64_t *strides_bytes /* rank-1 */, const cuuint32_t *box, const cuuint32_t *estr) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return mpn_fail(ctx, MPN_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu box %u %u", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return mpn_fail(ctx, MPN_ERR_CUDA, b);
+  }
+  return MPN_OK;
+}
+
+template <int BN>
+int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
+  const int smem = num_stages(BN) * stage_bytes(BN) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int total = pl.tiles_img * pl.tiles_h * pl.tiles_w * pl.tiles_n;
+  const int grid = std::min(total, ctx->sm_count);
+  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, ctx->stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
+}  // namespace
+
+double conv_flops(const ConvProblem &p) {
+  const double Ho = (double)p.y.H, Wo = (double)p.y.W;
+  return 2.0 * (double)p.x.C * p.Cout * p.kh * p.kw * Ho * Wo * (double)p.y.N;
+}
+
+int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
+  pl.valid = 0;
+  MPN_CHECK_ARG(ctx, p.x.hi && p.x.lo && p.w_hi && p.w_lo, "conv_tc: operands must be split-bf16");
+  MPN_CHECK_ARG(ctx, p.x.C % BK == 0, "conv_tc: Cin must be a multiple of 64");
+  MPN_CHECK_ARG(ctx, p.x.ld % 8 == 0, "conv_tc: input pixel stride must be a multiple of 8 elements");
+  MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
+  const int Ho = (int)p.y.H, Wo = (int)p.y.W, N = (int)p.y.N;
+  pl.BN = p.Cout >= 256 ? 256 : (p.Cout >= 128 ? 128 : 64);
+  pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
+  pl.flat = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0) ? 1 : 0;
+  cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];
+  if (pl.flat) {
+    const long long P = (long long)p.x.N * p.x.H * p.x.W;
+    pl.tn = 1; pl.th = 1; pl.tw = BM;
+    pl.tiles_img = 1; pl.tiles_h = 1; pl.tiles_w = (int)((P + BM - 1) / BM);
+    dims[0] = (cuuint64_t)p.x.C; dims[1] = (cuuint64_t)P; dims[2] = 1; dims[3] = 1;
+    strides[0] = (cuuint64_t)p.x.ld * 2; strides[1] = (cuuint64_t)P * p.x.ld * 2; strides[2] = strides[1];
+    box[0] = BK; box[1] = BM; box[2] = 1; box[3] = 1;
+    estr[0] = estr[1] = estr[2] = estr[3] = 1;
+  } else {
+    // choose the power-of-two patch tn x th x tw (=128) that wastes the fewest MMA rows
+    double best = -1.0; int btn = 1, bth = 1, btw = 128;
+    for (int tw = 1; tw <= 128; tw <<= 1)
+      for (int th = 1; th * tw <= 128; th <<= 1) {
+        const int tn = 128 / (tw * th);
+        if (tw * p.stride > 256 || th * p.stride > 256) continue;
+        const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+        const double util = (double)N * Ho * Wo / (double)(tiles * 128) + 1e-6 * tw;   // tie-break: wider rows
+        if (util > best) { best = util; btn = tn; bth = th; btw = tw; }
+      }
+    pl.tn = btn; pl.th = bth; pl.tw = btw;
+    pl.tiles_w = (Wo + btw - 1) / btw; pl.tiles_h = (Ho + bth - 1) / bth; pl.tiles_img = (N + btn - 1) / btn;
+    dims[0] = (cuuint64_t)p.x.C; dims[1] = (cuuint64_t)p.x.W; dims[2] = (cuuint64_t)p.x.H; dims[3] = (cuuint64_t)p.x.N;
+    strides[0] = (cuuint64_t)p.x.ld * 2; strides[1] = (cuuint64_t)p.x.W * p.x.ld * 2;
+    strides[2] = (cuuint64_t)p.x.H * p.x.W * p.x.ld * 2;
+    box[0] = BK; box[1] = (cuuint32_t)(btw * p.stride); box[2] = (cuuint32_t)(bth * p.stride); box[3] = (cuuint32_t)btn;
+    estr[0] = 1; estr[1] = (cuuint32_t)p.stride; estr[2] = (cuuint32_t)p.stride; estr[3] = 1;
+  }
+  MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
+  MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));
+  const long long Ktot = (long long)p.kh * p.kw * p.x.C;
+  cuuint64_t bd[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout}, bs[1] = {(cuuint64_t)Ktot * 2};
+  cuuint32_t bb[2] = {BK, (cuuint32_t)pl.BN}, be[2] = {1, 1};
+  MPN_TRY(encode_map(ctx, &pl.tmB_hi, p.w_hi, 2, bd, bs, bb, be));
+  MPN_TRY(encode_map(ctx, &pl.tmB_lo, p.w_lo, 2, bd, bs, bb, be));
+  pl.valid = 1;
+  return MPN_OK;
+}
+
+int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
+  MPN_CHECK_ARG(ctx, pl.valid, "conv_tc_launch: invalid plan");
+  TcParams tp;
+  if (pl.flat) { tp.N = 1; tp.Ho = 1; tp.Wo = (int)(p.y.N * p.y.H * p.y.W); }
+  else { tp.N = (int)p.y.N; tp.Ho = (int)p.y.H; tp.Wo = (int)p.y.W; }
+  tp.Cout = p.Cout; tp.kh = p.kh; tp.kw = p.kw; tp.stride = p.stride; tp.pad = p.pad;
+  tp.cblocks = (int)(p.x.C / BK);
+  tp.tn = pl.tn; tp.th = pl.th; tp.tw = pl.tw;
+  tp.tiles_img = pl.tiles_img; tp.tiles_h = pl.tiles_h; tp.tiles_w = pl.tiles_w; tp.tiles_n = pl.tiles_n;
+  tp.bias = p.bias;
+  tp.res_hi = p.res.hi; tp.res_lo = p.res.lo; tp.res_ld = p.res.ld;
+  tp.out_hi = p.y.hi; tp.out_lo = p.y.lo; tp.out_ld = p.y.ld;
+  tp.out_f32 = p.y.f32; tp.out_f32_ld = p.y_f32_ld;
+  tp.relu = p.relu;
+  if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
+  switch (pl.BN) {
+    case 256: return launch_bn<256>(ctx, pl, tp);
+    case 128: return launch_bn<128>(ctx, pl, tp);
+    default: return launch_bn<64>(ctx, pl, tp);
+  }
+}

@@ -1,0 +1,645 @@
+// model.cu — executor for the detection graphs of models/{vgg,multipathnet,resnet}.lua,
+// described as data (mpn_model_desc). Mirrors the reference's own trunk / heads split:
+//   mpn_model_trunk  == model:get(1):forward            (ImageDetect.lua:107-108)
+//   mpn_model_heads  == modules 2..n on cached features  (ImageDetect.lua:114-124)
+//   mpn_model_detect == ImageDetect:detect tail          (ImageDetect.lua:176-192)
+//   mpn_model_detect_nms adds Tester_FRCNN:testOne's clamp / per-class gather / NMS
+//   (Tester_FRCNN.lua:75-78,106-117) so one stream-ordered pass produces final keep lists.
+// All activations live in HBM as NHWC split-bf16 planes; every conv / Linear runs on the
+// tcgen05 engine (gemm_tc.cu) except the Cin=3 first layer (conv_simt.cu).
+#include "conv_gemm.cuh"
+#include "roi.cuh"
+#include <algorithm>
+#include <map>
+#include <memory>
+
+// launchers defined in the other TUs
+int mpn_maxpool_launch(mpn_ctx *, const DTensor &, int, int, int, DTensor &);
+int mpn_avgpool_launch(mpn_ctx *, const DTensor &, DTensor &);
+int mpn_weight_permute_split_launch(mpn_ctx *, const float *, int64_t, int, int, int, __nv_bfloat16 *, __nv_bfloat16 *);
+int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
+int mpn_project_rois_launch(mpn_ctx *, const float *, int64_t, float, float *);
+int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
+int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
+int mpn_softmax_mean_launch(mpn_ctx *, const float *, int64_t, int, int, int, float *);
+int mpn_gather_scored_launch(mpn_ctx *, const float *, const float *, int, int, float, float *, int32_t *, int32_t *);
+int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
+
+namespace {
+
+struct DevBuf {           // owning device allocation
+  void *p = nullptr; size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int ensure(mpn_ctx *ctx, size_t n) {
+    if (n <= bytes) return MPN_OK;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    MPN_CUDA(ctx, cudaMalloc(&p, n));
+    bytes = n;
+    return MPN_OK;
+  }
+};
+
+struct SplitBuf {         // owning hi/lo planes
+  DevBuf hi, lo;
+  int ensure(mpn_ctx *ctx, size_t elems) {
+    MPN_TRY(hi.ensure(ctx, elems * 2 + 256));
+    return lo.ensure(ctx, elems * 2 + 256);
+  }
+};
+
+struct WeightDev {
+  DevBuf hi, lo;          // split [Cout][K] for tensor-core convs
+  DevBuf f32;             // raw fp32 (Torch layout) for the direct first layer / biases
+  int64_t n = 0;
+};
+
+struct LayerExec {
+  mpn_layer L;
+  ConvProblem prob;
+  ConvPlan plan;
+  bool is_direct = false;  // Cin not a multiple of 64: CUDA-core direct conv from the NCHW fp32 image
+  DTensor in, out;
+};
+
+int pool_out(int in, int k, int s, int p, int ceil_mode) {
+  int o = ceil_mode ? (in + 2 * p - k + s - 1) / s + 1 : (in + 2 * p - k) / s + 1;
+  if (ceil_mode && (o - 1) * s >= in + p) --o;
+  return o;
+}
+
+}  // namespace
+
+struct mpn_model {
+  mpn_ctx *ctx = nullptr;
+  mpn_model_desc d;
+  std::vector<mpn_layer> trunk_layers, tower_layers;
+  std::vector<mpn_tower> towers;
+  std::vector<mpn_head> cls_heads;
+  std::vector<std::unique_ptr<WeightDev>> weights;
+  std::vector<int64_t> w_elems;
+  std::vector<int> w_prepared;     // 0 = raw only, 1 = split prepared with (Cin,kh,kw) below
+  int conv_impl = 0;
+
+  // ---- trunk state
+  int tH = 0, tW = 0; bool trunk_valid = false;
+  std::vector<LayerExec> trunk_exec;
+  std::map<int, DTensor> trunk_slots; std::map<int, std::unique_ptr<SplitBuf>> trunk_bufs;
+  DevBuf image_dev;
+  double trunk_flops = 0, head_flops = 0;
+
+  // ---- heads state
+  int64_t hR = 0; bool heads_planned = false;
+  struct TowerExec {
+    std::unique_ptr<SplitBuf> pooled_buf; DTensor pooled; int ctot = 0;
+    std::vector<LayerExec> layers; std::map<int, DTensor> slots; std::map<int, std::unique_ptr<SplitBuf>> bufs;
+    int out_features = 0, col_off = 0;
+  };
+  std::vector<TowerExec> tex;
+  SplitBuf concat_buf; int concat_width = 0;
+  std::vector<LayerExec> head_exec;     // cls heads then bbox head
+  DevBuf rois_dev, boxes_dev, cls_logits, bbox_raw, scores_dev, bboxes_dev;
+  DevBuf sb_dev, src_idx_dev, counts_dev, keep_idx_dev, keep_counts_dev;
+  RoiJobs jobs;
+};
+
+namespace {
+
+int upload_weight_raw(mpn_model *m, int idx, const float *host, int64_t n) {
+  WeightDev &w = *m->weights[idx];
+  w.n = n;
+  MPN_TRY(w.f32.ensure(m->ctx, sizeof(float) * (size_t)std::max<int64_t>(n, 1)));
+  MPN_CUDA(m->ctx, cudaMemcpyAsync(w.f32.p, host, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, m->ctx->stream));
+  return MPN_OK;
+}
+
+// Torch [Cout][Cin][kh][kw] -> split [Cout][kh][kw][Cin]; raw fp32 copy is then released.
+int prepare_conv_weight(mpn_model *m, int idx, int Cout, int Cin, int kh, int kw) {
+  mpn_ctx *ctx = m->ctx;
+  MPN_CHECK_ARG(ctx, idx >= 0 && idx < (int)m->weights.size(), "layer weight index out of range");
+  WeightDev &w = *m->weights[idx];
+  MPN_CHECK_ARG(ctx, w.n == (int64_t)Cout * Cin * kh * kw, "weight element count does not match layer geometry");
+  if (m->w_prepared[idx]) return MPN_OK;
+  const size_t elems = (size_t)w.n;
+  MPN_TRY(w.hi.ensure(ctx, elems * 2 + 256));
+  MPN_TRY(w.lo.ensure(ctx, elems * 2 + 256));
+  MPN_TRY(mpn_weight_permute_split_launch(ctx, (const float *)w.f32.p, Cout, Cin, kh, kw, (__nv_bfloat16 *)w.hi.p,
+                                          (__nv_bfloat16 *)w.lo.p));
+  m->w_prepared[idx] = 1;
+  // the fp32 staging copy is no longer needed (cudaFree synchronises with the split kernel)
+  cudaFree(w.f32.p); w.f32.p = nullptr; w.f32.bytes = 0;
+  return MPN_OK;
+}
+
+DTensor make_split_view(SplitBuf &b, int64_t N, int64_t H, int64_t W, int64_t C) {
+  DTensor t; t.hi = (__nv_bfloat16 *)b.hi.p; t.lo = (__nv_bfloat16 *)b.lo.p; t.N = N; t.H = H; t.W = W; t.C = C; t.ld = C;
+  return t;
+}
+
+// Build the executable form of one CONV layer (weights prepared, problem + plan filled).
+// flat_from: if the layer consumes a FLATTENed (h,w,c) tensor, its Linear weight [Cout][c*h*w]
+// in (c,h,w) order is re-laid as a (kh=h,kw=w,Cin=c) conv weight => (h,w,c) K order.
+int build_conv(mpn_model *m, LayerExec &e, const DTensor &in, DTensor out, int fh, int fw, int fc) {
+  mpn_ctx *ctx = m->ctx;
+  const mpn_layer &L = e.L;
+  e.in = in; e.out = out;
+  ConvProblem &p = e.prob;
+  p = ConvProblem();
+  p.x = in; p.Cout = L.cout; p.kh = L.kh; p.kw = L.kw; p.stride = L.stride; p.pad = L.pad; p.relu = L.relu;
+  p.y = out; p.y_f32_ld = out.ld;
+  MPN_CHECK_ARG(ctx, L.weight >= 0, "conv layer without weight");
+  if (fc > 0) { MPN_TRY(prepare_conv_weight(m, L.weight, L.cout, fc, fh, fw)); }
+  else { MPN_TRY(prepare_conv_weight(m, L.weight, L.cout, L.cin, L.kh, L.kw)); }
+  WeightDev &w = *m->weights[L.weight];
+  p.w_hi = (const __nv_bfloat16 *)w.hi.p; p.w_lo = (const __nv_bfloat16 *)w.lo.p;
+  if (L.bias >= 0) {
+    MPN_CHECK_ARG(ctx, L.bias < (int)m->weights.size() && m->weights[L.bias]->n == L.cout, "bias size mismatch");
+    p.bias = (const float *)m->weights[L.bias]->f32.p;
+  }
+  MPN_TRY(conv_tc_plan(ctx, p, e.plan));
+  return MPN_OK;
+}
+
+int run_conv(mpn_model *m, LayerExec &e) {
+  if (m->conv_impl == 1) return conv_ref_launch(m->ctx, e.prob);
+  return conv_tc_launch(m->ctx, e.prob, e.plan);
+}
+
+// ------------------------------------------------------------------ trunk planning
+int plan_trunk(mpn_model *m, int H, int W) {
+  mpn_ctx *ctx = m->ctx;
+  m->trunk_exec.clear(); m->trunk_slots.clear();
+  m->trunk_flops = 0;
+  DTensor img; img.N = 1; img.H = H; img.W = W; img.C = 3; img.ld = 3;   // slot 0: NCHW fp32 image (special)
+  m->trunk_slots[0] = img;
+  for (const mpn_layer &L : m->trunk_layers) {
+    MPN_CHECK_ARG(ctx, m->trunk_slots.count(L.in_slot), "trunk layer reads an undefined slot");
+    const DTensor in = m->trunk_slots[L.in_slot];
+    LayerExec e; e.L = L;
+    DTensor out; out.N = in.N;
+    if (L.kind == MPN_LAYER_CONV) {
+      MPN_CHECK_ARG(ctx, L.cin == in.C, "trunk conv cin does not match its input");
+      out.H = (in.H + 2 * L.pad - L.kh) / L.stride + 1; out.W = (in.W + 2 * L.pad - L.kw) / L.stride + 1; out.C = L.cout;
+    } else if (L.kind == MPN_LAYER_MAXPOOL) {
+      out.H = pool_out((int)in.H, L.kh, L.stride, L.pad, L.ceil_mode);
+      out.W = pool_out((int)in.W, L.kw, L.stride, L.pad, L.ceil_mode); out.C = in.C;
+    } else {
+      return mpn_fail(ctx, MPN_ERR_ARG, "unsupported trunk layer kind");
+    }
+    MPN_CHECK_ARG(ctx, out.H > 0 && out.W > 0, "trunk layer output is empty");
+    MPN_CHECK_ARG(ctx, L.out_slot > 0, "trunk layers may not write slot 0");
+    auto &buf = m->trunk_bufs[L.out_slot];
+    if (!buf) buf.reset(new SplitBuf());
+    MPN_TRY(buf->ensure(ctx, (size_t)(out.N * out.H * out.W * out.C)));
+    out = make_split_view(*buf, out.N, out.H, out.W, out.C);
+    if (L.kind == MPN_LAYER_CONV) {
+      if (L.in_slot == 0) {
+        e.is_direct = true; e.in = in; e.out = out;
+        MPN_CHECK_ARG(ctx, L.weight >= 0 && m->weights[L.weight]->n == (int64_t)L.cout * L.cin * L.kh * L.kw,
+                      "first-layer weight size mismatch");
+      } else {
+        DTensor o2 = out;
+        MPN_TRY(build_conv(m, e, in, o2, 0, 0, 0));
+        if (L.residual_slot >= 0) {
+          MPN_CHECK_ARG(ctx, m->trunk_slots.count(L.residual_slot), "residual slot undefined");
+          e.prob.res = m->trunk_slots[L.residual_slot];
+        }
+      }
+      m->trunk_flops += 2.0 * L.cin * L.cout * L.kh * L.kw * (double)out.H * out.W * out.N;
+    } else {
+      e.in = in; e.out = out;
+    }
+    m->trunk_slots[L.out_slot] = out;
+    m->trunk_exec.push_back(e);
+  }
+  m->tH = H; m->tW = W; m->trunk_valid = false; m->heads_planned = false;
+  return MPN_OK;
+}
+
+int run_trunk(mpn_model *m, const float *image_dev) {
+  mpn_ctx *ctx = m->ctx;
+  for (LayerExec &e : m->trunk_exec) {
+    const mpn_layer &L = e.L;
+    if (L.kind == MPN_LAYER_CONV) {
+      if (e.is_direct) {
+        const float *bias = L.bias >= 0 ? (const float *)m->weights[L.bias]->f32.p : nullptr;
+        MPN_TRY(conv_direct_nchw_launch(ctx, image_dev, 1, L.cin, (int)e.in.H, (int)e.in.W,
+                                        (const float *)m->weights[L.weight]->f32.p, bias, L.cout, L.kh, L.kw, L.stride,
+                                        L.pad, L.relu, e.out));
+      } else {
+        MPN_TRY(run_conv(m, e));
+      }
+    } else {
+      MPN_TRY(mpn_maxpool_launch(ctx, e.in, L.kh, L.stride, L.pad, e.out));
+    }
+  }
+  m->trunk_valid = true;
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------ heads planning
+int plan_heads(mpn_model *m, int64_t R) {
+  mpn_ctx *ctx = m->ctx;
+  const int C = m->d.num_classes;
+  m->head_flops = 0;
+  m->tex.clear(); m->tex.resize(m->towers.size());
+  m->jobs.n = 0;
+  // concat width = sum of tower output features
+  int width = 0;
+  std::vector<int> feat(m->towers.size(), 0);
+  for (size_t t = 0; t < m->towers.size(); ++t) {
+    const mpn_tower &T = m->towers[t];
+    // find the producing layer of out_slot to learn its feature count
+    int f = -1;
+    for (int i = 0; i < T.n_layers; ++i) {
+      const mpn_layer &L = m->tower_layers[T.first_layer + i];
+      if (L.out_slot == T.out_slot) f = (L.kind == MPN_LAYER_CONV) ? L.cout : -2;
+    }
+    MPN_CHECK_ARG(ctx, f != -1, "tower out_slot is never written");
+    feat[t] = f;   // -2: resolved below (avgpool/flatten output)
+  }
+  // first pass to resolve shapes and features
+  for (size_t t = 0; t < m->towers.size(); ++t) {
+    const mpn_tower &T = m->towers[t];
+    mpn_model::TowerExec &X = m->tex[t];
+    X.ctot = 0;
+    for (int l = 0; l < T.n_levels; ++l) {
+      MPN_CHECK_ARG(ctx, m->trunk_slots.count(T.level_slot[l]) && T.level_slot[l] > 0, "tower level reads an undefined trunk slot");
+      X.ctot += (int)m->trunk_slots[T.level_slot[l]].C;
+    }
+    X.pooled_buf.reset(new SplitBuf());
+    MPN_TRY(X.pooled_buf->ensure(ctx, (size_t)R * T.pooled_h * T.pooled_w * X.ctot));
+    X.pooled = make_split_view(*X.pooled_buf, R, T.pooled_h, T.pooled_w, X.ctot);
+    // ROI jobs
+    int ch_off = 0;
+    for (int l = 0; l < T.n_levels; ++l) {
+      MPN_CHECK_ARG(ctx, m->jobs.n < MAX_ROI_JOBS, "too many (tower, level) ROI jobs");
+      const DTensor &f = m->trunk_slots[T.level_slot[l]];
+      RoiJob &j = m->jobs.j[m->jobs.n++];
+      j.hi = f.hi; j.lo = f.lo; j.H = (int)f.H; j.W = (int)f.W; j.C = (int)f.C; j.ld = f.ld; j.scale = T.level_scale[l];
+      j.region = T.region; j.out_hi = X.pooled.hi; j.out_lo = X.pooled.lo; j.out_ld = X.ctot; j.out_ch_off = ch_off;
+      j.normalize = T.normalize;
+      ch_off += (int)f.C;
+    }
+    // shape walk
+    std::map<int, DTensor> shp; shp[0] = X.pooled;
+    for (int i = 0; i < T.n_layers; ++i) {
+      const mpn_layer &L = m->tower_layers[T.first_layer + i];
+      MPN_CHECK_ARG(ctx, shp.count(L.in_slot), "tower layer reads an undefined slot");
+      const DTensor in = shp[L.in_slot]; DTensor out; out.N = R;
+      if (L.kind == MPN_LAYER_CONV) {
+        MPN_CHECK_ARG(ctx, L.cin == in.C, "tower conv cin does not match its input");
+        out.H = (in.H + 2 * L.pad - L.kh) / L.stride + 1; out.W = (in.W + 2 * L.pad - L.kw) / L.stride + 1; out.C = L.cout;
+      } else if (L.kind == MPN_LAYER_FLATTEN) { out.H = 1; out.W = 1; out.C = in.H * in.W * in.C; }
+      else if (L.kind == MPN_LAYER_AVGPOOL) { out.H = 1; out.W = 1; out.C = in.C; }
+      else if (L.kind == MPN_LAYER_MAXPOOL) {
+        out.H = pool_out((int)in.H, L.kh, L.stride, L.pad, L.ceil_mode); out.W = pool_out((int)in.W, L.kw, L.stride, L.pad, L.ceil_mode);
+        out.C = in.C;
+      } else return mpn_fail(ctx, MPN_ERR_ARG, "unsupported tower layer kind");
+      shp[L.out_slot] = out;
+    }
+    MPN_CHECK_ARG(ctx, shp.count(T.out_slot), "tower out_slot undefined");
+    const DTensor o = shp[T.out_slot];
+    MPN_CHECK_ARG(ctx, o.H == 1 && o.W == 1, "tower output must be R x 1 x 1 x F");
+    X.out_features = (int)o.C; X.col_off = width; width += (int)o.C;
+  }
+  m->concat_width = width;
+  MPN_CHECK_ARG(ctx, width % 8 == 0, "concat width must be a multiple of 8");
+  MPN_TRY(m->concat_buf.ensure(ctx, (size_t)R * width));
+  // second pass: allocate + build
+  for (size_t t = 0; t < m->towers.size(); ++t) {
+    const mpn_tower &T = m->towers[t];
+    mpn_model::TowerExec &X = m->tex[t];
+    X.slots.clear(); X.slots[0] = X.pooled; X.layers.clear();
+    int flat_h = 0, flat_w = 0, flat_c = 0; int flat_slot = -1;
+    for (int i = 0; i < T.n_layers; ++i) {
+      const mpn_layer &L = m->tower_layers[T.first_layer + i];
+      const DTensor in = X.slots[L.in_slot];
+      LayerExec e; e.L = L;
+      DTensor out; out.N = R;
+      if (L.kind == MPN_LAYER_FLATTEN) {
+        MPN_CHECK_ARG(ctx, in.ld == in.C, "flatten needs a dense input");
+        out = in; out.H = 1; out.W = 1; out.C = in.H * in.W * in.C; out.ld = out.C;
+        flat_h = (int)in.H; flat_w = (int)in.W; flat_c = (int)in.C; flat_slot = L.out_slot;
+        X.slots[L.out_slot] = out; e.in = in; e.out = out; X.layers.push_back(e);
+        continue;
+      }
+      if (L.kind == MPN_LAYER_CONV) {
+        out.H = (in.H + 2 * L.pad - L.kh) / L.stride + 1; out.W = (in.W + 2 * L.pad - L.kw) / L.stride + 1; out.C = L.cout;
+      } else if (L.kind == MPN_LAYER_AVGPOOL) { out.H = 1; out.W = 1; out.C = in.C; }
+      else { out.H = pool_out((int)in.H, L.kh, L.stride, L.pad, L.ceil_mode); out.W = pool_out((int)in.W, L.kw, L.stride, L.pad, L.ceil_mode); out.C = in.C; }
+      if (L.out_slot == T.out_slot) {      // write straight into this tower's column slice of the concat
+        out.hi = (__nv_bfloat16 *)m->concat_buf.hi.p + X.col_off; out.lo = (__nv_bfloat16 *)m->concat_buf.lo.p + X.col_off;
+        out.ld = width;
+      } else {
+        auto &buf = X.bufs[L.out_slot];
+        if (!buf) buf.reset(new SplitBuf());
+        MPN_TRY(buf->ensure(ctx, (size_t)(out.N * out.H * out.W * out.C)));
+        DTensor v = make_split_view(*buf, out.N, out.H, out.W, out.C); out = v;
+      }
+      if (L.kind == MPN_LAYER_CONV) {
+        const bool from_flat = (L.in_slot == flat_slot) && L.kh == 1 && L.kw == 1;
+        MPN_TRY(build_conv(m, e, in, out, from_flat ? flat_h : 0, from_flat ? flat_w : 0, from_flat ? flat_c : 0));
+        if (L.residual_slot >= 0) {
+          MPN_CHECK_ARG(ctx, X.slots.count(L.residual_slot), "tower residual slot undefined");
+          e.prob.res = X.slots[L.residual_slot];
+        }
+        m->head_flops += 2.0 * (double)L.cin * L.cout * L.kh * L.kw * (double)out.H * out.W * (double)R;
+      } else { e.in = in; e.out = out; }
+      X.slots[L.out_slot] = out;
+      X.layers.push_back(e);
+    }
+  }
+  // heads: cls (K of them) then bbox, fp32 outputs
+  const int K = (int)m->cls_heads.size();
+  MPN_TRY(m->cls_logits.ensure(ctx, sizeof(float) * (size_t)K * R * C + 256));
+  MPN_TRY(m->bbox_raw.ensure(ctx, sizeof(float) * (size_t)R * 4 * C + 256));
+  MPN_TRY(m->scores_dev.ensure(ctx, sizeof(float) * (size_t)R * C + 256));
+  MPN_TRY(m->bboxes_dev.ensure(ctx, sizeof(float) * (size_t)R * 4 * C + 256));
+  m->head_exec.clear();
+  auto add_head = [&](const mpn_head &h, float *out_ptr) -> int {
+    MPN_CHECK_ARG(ctx, h.col_begin % 8 == 0 && h.col_begin + h.col_len <= width && h.col_len % 64 == 0, "head column range invalid");
+    LayerExec e; mpn_layer L; memset(&L, 0, sizeof L);
+    L.kind = MPN_LAYER_CONV; L.cin = h.col_len; L.cout = h.cout; L.kh = L.kw = 1; L.stride = 1; L.pad = 0; L.relu = 0;
+    L.residual_slot = -1; L.weight = h.weight; L.bias = h.bias;
+    e.L = L;
+    DTensor in; in.hi = (__nv_bfloat16 *)m->concat_buf.hi.p + h.col_begin; in.lo = (__nv_bfloat16 *)m->concat_buf.lo.p + h.col_begin;
+    in.N = R; in.H = 1; in.W = 1; in.C = h.col_len; in.ld = width;
+    DTensor out; out.f32 = out_ptr; out.N = R; out.H = 1; out.W = 1; out.C = h.cout; out.ld = h.cout;
+    MPN_TRY(build_conv(m, e, in, out, 0, 0, 0));
+    m->head_flops += 2.0 * (double)h.col_len * h.cout * (double)R;
+    m->head_exec.push_back(e);
+    return MPN_OK;
+  };
+  for (int k = 0; k < K; ++k) {
+    MPN_CHECK_ARG(ctx, m->cls_heads[k].cout == C, "cls head width must equal num_classes");
+    MPN_TRY(add_head(m->cls_heads[k], (float *)m->cls_logits.p + (size_t)k * R * C));
+  }
+  MPN_CHECK_ARG(ctx, m->d.bbox_head.cout == 4 * C, "bbox head width must be 4*num_classes");
+  MPN_TRY(add_head(m->d.bbox_head, (float *)m->bbox_raw.p));
+  // post-processing buffers
+  MPN_TRY(m->sb_dev.ensure(ctx, sizeof(float) * (size_t)(C - 1) * R * 5 + 256));
+  MPN_TRY(m->src_idx_dev.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * R + 256));
+  MPN_TRY(m->counts_dev.ensure(ctx, sizeof(int32_t) * (size_t)C + 256));
+  MPN_TRY(m->keep_idx_dev.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * R + 256));
+  MPN_TRY(m->keep_counts_dev.ensure(ctx, sizeof(int32_t) * (size_t)C + 256));
+  m->hR = R; m->heads_planned = true;
+  return MPN_OK;
+}
+
+int run_heads(mpn_model *m, const float *rois_dev, int64_t R) {
+  mpn_ctx *ctx = m->ctx;
+  const mpn_tower &T0 = m->towers[0];
+  MPN_TRY(mpn_roi_pool_fused_launch(ctx, m->jobs, rois_dev, R, T0.pooled_w, T0.pooled_h, m->d.roi_variant));
+  for (size_t t = 0; t < m->towers.size(); ++t) {
+    for (LayerExec &e : m->tex[t].layers) {
+      switch (e.L.kind) {
+        case MPN_LAYER_CONV: MPN_TRY(run_conv(m, e)); break;
+        case MPN_LAYER_FLATTEN: break;
+        case MPN_LAYER_AVGPOOL: MPN_TRY(mpn_avgpool_launch(ctx, e.in, e.out)); break;
+        case MPN_LAYER_MAXPOOL: MPN_TRY(mpn_maxpool_launch(ctx, e.in, e.L.kh, e.L.stride, e.L.pad, e.out)); break;
+        default: return mpn_fail(ctx, MPN_ERR_ARG, "bad tower layer");
+      }
+    }
+  }
+  for (LayerExec &e : m->head_exec) MPN_TRY(run_conv(m, e));
+  if (m->d.has_bbox_norm)
+    MPN_TRY(mpn_bbox_norm_launch(ctx, (float *)m->bbox_raw.p, R, 4 * m->d.num_classes, m->d.bbox_mean, m->d.bbox_std));
+  return MPN_OK;
+}
+
+int ensure_trunk(mpn_model *m, int H, int W) {
+  if (m->trunk_exec.empty() || m->tH != H || m->tW != W) MPN_TRY(plan_trunk(m, H, W));
+  return MPN_OK;
+}
+int ensure_heads(mpn_model *m, int64_t R) {
+  mpn_ctx *ctx = m->ctx;
+  MPN_CHECK_ARG(ctx, !m->trunk_exec.empty(), "heads called before any trunk forward (ImageDetect.lua:95 asserts the same)");
+  MPN_CHECK_ARG(ctx, R > 0 && R <= m->d.max_rois, "R out of range (0 < R <= max_rois)");
+  if (!m->heads_planned || m->hR != R) MPN_TRY(plan_heads(m, R));
+  return MPN_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI
+extern "C" {
+
+int mpn_model_create(mpn_ctx *ctx, const mpn_model_desc *desc, const float *const *weights, const int64_t *n_elem,
+                     int32_t n_weights, mpn_model **out) {
+  if (!ctx || !desc || !out) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, desc->n_towers >= 1 && desc->n_trunk_layers >= 1 && desc->n_cls_heads >= 1, "empty model description");
+  MPN_CHECK_ARG(ctx, desc->num_classes >= 2, "num_classes must be >= 2");
+  MPN_CHECK_ARG(ctx, desc->roi_variant == 1 || desc->roi_variant == 2, "roi_variant must be 1 or 2");
+  mpn_model *m = new mpn_model();
+  m->ctx = ctx; m->d = *desc;
+  m->trunk_layers.assign(desc->trunk_layers, desc->trunk_layers + desc->n_trunk_layers);
+  m->tower_layers.assign(desc->tower_layers, desc->tower_layers + desc->n_tower_layers);
+  m->towers.assign(desc->towers, desc->towers + desc->n_towers);
+  m->cls_heads.assign(desc->cls_heads, desc->cls_heads + desc->n_cls_heads);
+  m->d.trunk_layers = nullptr; m->d.tower_layers = nullptr; m->d.towers = nullptr; m->d.cls_heads = nullptr;
+  for (size_t t = 1; t < m->towers.size(); ++t) {
+    if (m->towers[t].pooled_w != m->towers[0].pooled_w || m->towers[t].pooled_h != m->towers[0].pooled_h) {
+      delete m; return mpn_fail(ctx, MPN_ERR_ARG, "all towers must share the pooled size");
+    }
+  }
+  m->weights.resize(n_weights); m->w_elems.assign(n_elem, n_elem + n_weights); m->w_prepared.assign(n_weights, 0);
+  for (int i = 0; i < n_weights; ++i) {
+    m->weights[i].reset(new WeightDev());
+    int r = upload_weight_raw(m, i, weights[i], n_elem[i]);
+    if (r != MPN_OK) { delete m; return r; }
+  }
+  // the host arrays may be freed by the caller once we return
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) { delete m; return mpn_fail(ctx, MPN_ERR_CUDA, cudaGetErrorString(e)); }
+  *out = m;
+  return MPN_OK;
+}
+
+void mpn_model_destroy(mpn_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  delete m;
+}
+
+int mpn_model_set_conv_impl(mpn_model *m, int32_t impl) {
+  if (!m) return MPN_ERR_ARG;
+  MPN_CHECK_ARG(m->ctx, impl == 0 || impl == 1, "impl must be 0 (tcgen05) or 1 (fp32 check kernel)");
+  m->conv_impl = impl;
+  return MPN_OK;
+}
+
+int mpn_model_last_flops(const mpn_model *m, double *trunk_flops, double *head_flops) {
+  if (!m) return MPN_ERR_ARG;
+  if (trunk_flops) *trunk_flops = m->trunk_flops;
+  if (head_flops) *head_flops = m->head_flops;
+  return MPN_OK;
+}
+
+int mpn_model_trunk_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image_dev && H > 0 && W > 0 && H <= m->d.max_h && W <= m->d.max_w, "image missing or larger than max_h x max_w");
+  MPN_TRY(ensure_trunk(m, H, W));
+  return run_trunk(m, image_dev);
+}
+
+int mpn_model_trunk(mpn_model *m, const float *image, int32_t H, int32_t W) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image && H > 0 && W > 0, "image missing");
+  const size_t bytes = sizeof(float) * 3 * (size_t)H * W;
+  MPN_TRY(m->image_dev.ensure(ctx, bytes));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->image_dev.p, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, H, W));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_heads_dev(mpn_model *m, const float *rois_dev, int64_t R, float *cls_out_dev, float *bbox_out_dev) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, m->trunk_valid, "heads called before a trunk forward");
+  MPN_TRY(ensure_heads(m, R));
+  MPN_TRY(run_heads(m, rois_dev, R));
+  const int C = m->d.num_classes, K = (int)m->cls_heads.size();
+  if (cls_out_dev) {
+    if (K == 1 && !m->d.no_softmax) {
+      MPN_CUDA(ctx, cudaMemcpyAsync(cls_out_dev, m->cls_logits.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {   // integral head: the model's own output is the mean of K softmaxes
+      MPN_TRY(mpn_softmax_mean_launch(ctx, (const float *)m->cls_logits.p, R, C, K, 1, cls_out_dev));
+    }
+  }
+  if (bbox_out_dev)
+    MPN_CUDA(ctx, cudaMemcpyAsync(bbox_out_dev, m->bbox_raw.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_heads(mpn_model *m, const float *rois, int64_t R, float *cls_out, float *bbox_out) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, rois && R > 0, "rois missing");
+  const int C = m->d.num_classes;
+  MPN_TRY(m->rois_dev.ensure(ctx, sizeof(float) * 5 * (size_t)R));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->rois_dev.p, rois, sizeof(float) * 5 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(ensure_heads(m, R));
+  MPN_TRY(mpn_model_heads_dev(m, (const float *)m->rois_dev.p, R, (float *)m->scores_dev.p, nullptr));
+  if (cls_out) MPN_CUDA(ctx, cudaMemcpyAsync(cls_out, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bbox_out) MPN_CUDA(ctx, cudaMemcpyAsync(bbox_out, m->bbox_raw.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+// shared tail: heads -> scores (softmax / integral mean) -> decode (+clamp) [-> gather -> NMS]
+static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, float im_scale, int do_nms, float W0,
+                           float H0, float score_thresh, float nms_thr) {
+  mpn_ctx *ctx = m->ctx;
+  const int C = m->d.num_classes, K = (int)m->cls_heads.size();
+  MPN_TRY(ensure_heads(m, R));
+  MPN_TRY(m->rois_dev.ensure(ctx, sizeof(float) * 5 * (size_t)R));
+  MPN_TRY(mpn_project_rois_launch(ctx, boxes_dev, R, im_scale, (float *)m->rois_dev.p));
+  MPN_TRY(run_heads(m, (const float *)m->rois_dev.p, R));
+  // class_values: softmax unless model.noSoftMax; an integral head IS its mean of softmaxes (noSoftMax=true)
+  const int do_softmax = (K > 1) ? 1 : (m->d.no_softmax ? 0 : 1);
+  MPN_TRY(mpn_softmax_mean_launch(ctx, (const float *)m->cls_logits.p, R, C, K, do_softmax, (float *)m->scores_dev.p));
+  MPN_TRY(mpn_bbox_decode_launch(ctx, (const float *)m->bbox_raw.p, boxes_dev, R, C, do_nms, W0, H0, (float *)m->bboxes_dev.p));
+  if (do_nms) {
+    MPN_TRY(mpn_gather_scored_launch(ctx, (const float *)m->scores_dev.p, (const float *)m->bboxes_dev.p, (int)R, C,
+                                     score_thresh, (float *)m->sb_dev.p, (int32_t *)m->src_idx_dev.p, (int32_t *)m->counts_dev.p));
+    MPN_TRY(mpn_nms_launch(ctx, (const float *)m->sb_dev.p, (int)R, C - 1, (const int32_t *)m->counts_dev.p,
+                           (const int32_t *)m->src_idx_dev.p, nms_thr, (int32_t *)m->keep_idx_dev.p,
+                           (int32_t *)m->keep_counts_dev.p));
+  }
+  return MPN_OK;
+}
+
+int mpn_model_detect(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
+                     float im_scale, int32_t recompute_features, float *scores, float *bboxes) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, boxes && R > 0, "boxes missing");
+  const int C = m->d.num_classes;
+  if (recompute_features) {
+    MPN_CHECK_ARG(ctx, image, "image missing");
+    const size_t bytes = sizeof(float) * 3 * (size_t)H * W;
+    MPN_TRY(m->image_dev.ensure(ctx, bytes));
+    MPN_CUDA(ctx, cudaMemcpyAsync(m->image_dev.p, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, H, W));
+  } else {
+    MPN_CHECK_ARG(ctx, m->trunk_valid, "recompute_features=false needs cached trunk features (ImageDetect.lua:109-111)");
+  }
+  MPN_TRY(m->boxes_dev.ensure(ctx, sizeof(float) * 4 * (size_t)R));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->boxes_dev.p, boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(detect_tail_dev(m, (const float *)m->boxes_dev.p, R, im_scale, 0, 0.f, 0.f, 0.f, 0.f));
+  if (scores) MPN_CUDA(ctx, cudaMemcpyAsync(scores, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, m->bboxes_dev.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W, const float *boxes_dev,
+                             int64_t R, float im_scale, float W0, float H0, float score_thresh, float nms_thr,
+                             float *scores_dev, float *bboxes_dev, int32_t *keep_idx_dev, int32_t *keep_counts_dev) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image_dev && boxes_dev && R > 0, "image/boxes missing");
+  const int C = m->d.num_classes;
+  MPN_TRY(mpn_model_trunk_dev(m, image_dev, H, W));
+  MPN_TRY(detect_tail_dev(m, boxes_dev, R, im_scale, 1, W0, H0, score_thresh, nms_thr));
+  if (scores_dev) MPN_CUDA(ctx, cudaMemcpyAsync(scores_dev, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (bboxes_dev) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes_dev, m->bboxes_dev.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (keep_idx_dev) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx_dev, m->keep_idx_dev.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (keep_counts_dev) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts_dev, m->keep_counts_dev.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToDevice, ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
+                         float im_scale, float W0, float H0, float score_thresh, float nms_thr, float *scores,
+                         float *bboxes, int32_t *keep_idx, int32_t *keep_counts) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image && boxes && R > 0, "image/boxes missing");
+  const int C = m->d.num_classes;
+  const size_t bytes = sizeof(float) * 3 * (size_t)H * W;
+  MPN_TRY(m->image_dev.ensure(ctx, bytes));
+  MPN_TRY(m->boxes_dev.ensure(ctx, sizeof(float) * 4 * (size_t)R));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->image_dev.p, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->boxes_dev.p, boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, H, W));
+  MPN_TRY(detect_tail_dev(m, (const float *)m->boxes_dev.p, R, im_scale, 1, W0, H0, score_thresh, nms_thr));
+  if (scores) MPN_CUDA(ctx, cudaMemcpyAsync(scores, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, m->bboxes_dev.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, m->keep_idx_dev.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToHost, ctx->stream));
+  if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, m->keep_counts_dev.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_t capacity, int32_t *C, int32_t *H,
+                             int32_t *W) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, m->trunk_valid && slot > 0 && m->trunk_slots.count(slot), "unknown trunk slot or no trunk forward yet");
+  const DTensor &t = m->trunk_slots[slot];
+  const int64_t n = t.N * t.C * t.H * t.W;
+  if (C) *C = (int32_t)t.C; if (H) *H = (int32_t)t.H; if (W) *W = (int32_t)t.W;
+  if (!out_nchw) return MPN_OK;
+  MPN_CHECK_ARG(ctx, capacity >= n, "output buffer too small");
+  void *tmp = nullptr;
+  MPN_TRY(mpn_scratch(ctx, sizeof(float) * (size_t)n, &tmp));
+  MPN_TRY(mpn_nhwc_split_to_nchw_launch(ctx, t, (float *)tmp));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out_nchw, tmp, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// nms.cu — batched greedy NMS on sm_100a, bit-exact against the reference nms.c.
+//
+// Replaces utils.nms -> nms.c:NMS (reference nms.c:59-108, utils.lua:29-33), which the
+// reference calls once per class per image on the CPU (Tester_FRCNN.lua:106-117).
+// Here all classes (segments) of an image go through one launch set:
+//   1. nms_rank_kernel   : stable descending rank of every row by counting (exact,
+//                          ties broken by ascending row => detects ties as a by-product)
+//   2. nms_mask_kernel   : 64x64 tiles of the upper-triangular IoU>thr bitmask, IoU in
+//                          the exact fp32 op order of nms.c:14-41 (no FMA: __f*_rn)
+//   3. nms_scan_kernel   : per segment, 64-row chunks: serial resolve of the diagonal
+//                          word + parallel OR of the kept rows into the removed-bitset
+//   4. nms_exact_kernel  : ONLY for segments that contain tied scores: block-parallel
+//                          emulation of nms.c's pointer-permutation walk (first strict max
+//                          in the current order, swap-to-front, order-preserving survivor
+//                          compaction), because nms.c's tie order is an artefact of that
+//                          permutation and not of any sort order.
+// With distinct scores nms.c keeps rows in descending-score order, which is what 1-3 emit.
+// Layout: segments have uniform capacity `cap`; segment s owns rows [s*cap, s*cap+count[s]).
+#include "common.cuh"
+
+namespace {
+
+// nms.c:14-41 op for op. a = the selected ("best") box, b = the other (argument order of nms.c:92).
+__device__ __forceinline__ float iou_ref(float ax1, float ay1, float ax2, float ay2,
+                                         float bx1, float by1, float bx2, float by2) {
+  float x1 = (ax1 > bx1) ? ax1 : bx1;   // MAX macro: (a>b)?a:b
+  float y1 = (ay1 > by1) ? ay1 : by1;
+  float x2 = (ax2 < bx2) ? ax2 : bx2;   // MIN macro: (a<b)?a:b
+  float y2 = (ay2 < by2) ? ay2 : by2;
+  float w = __fadd_rn(__fsub_rn(x2, x1), 1.0f);
+  float h = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+  float inter = __fmul_rn(w, h);
+  float aarea = __fmul_rn(__fadd_rn(__fsub_rn(ax2, ax1), 1.0f), __fadd_rn(__fsub_rn(ay2, ay1), 1.0f));
+  float barea = __fmul_rn(__fadd_rn(__fsub_rn(bx2, bx1), 1.0f), __fadd_rn(__fsub_rn(by2, by1), 1.0f));
+  float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+  return (w <= 0.0f || h <= 0.0f) ? 0.0f : iou;
+}
+
+constexpr int RANK_THREADS = 256;
+
+// grid (ceil(cap/256), nseg). rank[i] = #{j: s_j > s_i or (s_j == s_i and j < i)}.
+__global__ void __launch_bounds__(RANK_THREADS)
+nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict__ counts,
+                int32_t *__restrict__ order, float4 *__restrict__ sorted_boxes,
+                int32_t *__restrict__ tie_flag) {
+  const int seg = blockIdx.y;
+  const int n = counts ? counts[seg] : cap;
+  if ((int)blockIdx.x * RANK_THREADS >= n) return;
+  const float *seg_sb = sb + (size_t)seg * cap * 5;
+  __shared__ float s_tile[RANK_THREADS];
+  const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
+  const bool valid = i < n;
+  const float si = valid ? seg_sb[(size_t)i * 5 + 4] : 0.0f;
+  int rank = 0; int tied = 0;
+  for (int base = 0; base < n; base += RANK_THREADS) {
+    int j = base + threadIdx.x;
+    s_tile[threadIdx.x] = (j < n) ? seg_sb[(size_t)j * 5 + 4] : 0.0f;
+    __syncthreads();
+    int lim = min(RANK_THREADS, n - base);
+    if (valid) {
+#pragma unroll 8
+      for (int t = 0; t < lim; ++t) {
+        float sj = s_tile[t];
+        int jj = base + t;
+        bool eq = (sj == si);
+        rank += (sj > si) || (eq && jj < i);
+        tied |= (eq && jj != i);
+      }
+    }
+    __syncthreads();
+  }
+  if (valid) {
+    order[(size_t)seg * cap + rank] = i;
+    const float *b = seg_sb + (size_t)i * 5;
+    sorted_boxes[(size_t)seg * cap + rank] = make_float4(b[0], b[1], b[2], b[3]);
+    if (tied) atomicOr(&tie_flag[seg], 1);
+  }
+}
+
+// grid (nwords, nwords, nseg), 64 threads. Block (cb, rb): rows rb*64.., cols cb*64..; only cb >= rb.
+// mask[seg][row][cb] bit c set iff col j=cb*64+c > row i and !(iou(i,j) <= thr)  (nms.c:93 keeps <=).
+__global__ void __launch_bounds__(64)
+nms_mask_kernel(const float4 *__restrict__ sorted_boxes, int cap, int nwords_cap,
+                const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag, float thr,
+                unsigned long long *__restrict__ mask) {
+  const int seg = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  if (tie_flag[seg]) return;                    // exact-emulation path handles this segment
+  const int n = counts ? counts[seg] : cap;
+  if (rb * 64 >= n || cb * 64 >= n) return;
+  const float4 *boxes = sorted_boxes + (size_t)seg * cap;
+  __shared__ float4 s_col[64];
+  const int t = threadIdx.x;
+  const int cj = cb * 64 + t;
+  s_col[t] = (cj < n) ? boxes[cj] : make_float4(0, 0, 0, 0);
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= n) return;
+  const float4 a = boxes[i];
+  unsigned long long bits = 0ull;
+  const int ncols = min(64, n - cb * 64);
+  const int start = (rb == cb) ? t + 1 : 0;
+  for (int c = start; c < ncols; ++c) {
+    float4 b = s_col[c];
+    float v = iou_ref(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
+    if (!(v <= thr)) bits |= (1ull << c);
+  }
+  mask[((size_t)seg * cap + i) * nwords_cap + cb] = bits;
+}
+
+constexpr int SCAN_THREADS = 256;
+
+// one block per segment. keep_idx[seg*cap + k] = original row (via order, then src_idx if given).
+__global__ void __launch_bounds__(SCAN_THREADS)
+nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
+                int cap, int nwords_cap, const int32_t *__restrict__ counts,
+                const int32_t *__restrict__ tie_flag, const int32_t *__restrict__ src_idx,
+                int32_t *__restrict__ keep_idx, int32_t *__restrict__ keep_counts) {
+  const int seg = blockIdx.x;
+  if (tie_flag[seg]) return;
+  const int n = counts ? counts[seg] : cap;
+  extern __shared__ unsigned long long s_removed[];   // nwords_cap words
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_keepbits;
+  const int nwords = (n + 63) / 64;
+  const unsigned long long *m = mask + (size_t)seg * cap * nwords_cap;
+  const int32_t *ord = order + (size_t)seg * cap;
+  for (int w = threadIdx.x; w < nwords; w += SCAN_THREADS) s_removed[w] = 0ull;
+  int nkeep = 0;
+  __syncthreads();
+  for (int c = 0; c < nwords; ++c) {
+    const int row0 = c * 64;
+    if (threadIdx.x < 64) {
+      int r = row0 + threadIdx.x;
+      s_diag[threadIdx.x] = (r < n) ? m[(size_t)r * nwords_cap + c] : 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long cur = s_removed[c], kb = 0ull;
+      const int lim = min(64, n - row0);
+      for (int b = 0; b < lim; ++b) {
+        if (!((cur >> b) & 1ull)) { kb |= (1ull << b); cur |= s_diag[b]; }
+      }
+      s_keepbits = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = s_keepbits;
+    if (threadIdx.x < 64 && ((kb >> threadIdx.x) & 1ull)) {
+      int pos = nkeep + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
+      int o = ord[row0 + threadIdx.x];
+      keep_idx[(size_t)seg * cap + pos] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
+    }
+    nkeep += __popcll(kb);
+    // OR the rows of the kept boxes of this chunk into the words after c
+    for (int w = c + 1 + threadIdx.x; w < nwords; w += SCAN_THREADS) {
+      unsigned long long acc = s_removed[w], bits = kb;
+      while (bits) {
+        int b = __ffsll((long long)bits) - 1;
+        bits &= bits - 1ull;
+        acc |= m[(size_t)(row0 + b) * nwords_cap + w];
+      }
+      s_removed[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) keep_counts[seg] = nkeep;
+}
+
+constexpr int EXACT_THREADS = 512;
+
+// Exact emulation of nms.c:66-100 for segments with tied scores. One block per segment.
+// cur[] (scratch, cap ints per segment) is the reference's pointer array as row indices.
+__global__ void __launch_bounds__(EXACT_THREADS)
+nms_exact_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict__ counts,
+                 const int32_t *__restrict__ tie_flag, float thr, int32_t *__restrict__ cur_all,
+                 const int32_t *__restrict__ src_idx, int32_t *__restrict__ keep_idx,
+                 int32_t *__restrict__ keep_counts) {
+  const int seg = blockIdx.x;
+  if (!tie_flag[seg]) return;
+  const int n = counts ? counts[seg] : cap;
+  const float *seg_sb = sb + (size_t)seg * cap * 5;
+  int32_t *cur = cur_all + (size_t)seg * cap;
+  __shared__ float s_best_s[EXACT_THREADS / 32];
+  __shared__ int s_best_p[EXACT_THREADS / 32];
+  __shared__ int s_warp_tot[EXACT_THREADS / 32];
+  __shared__ int s_sel, s_tile_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < n; i += EXACT_THREADS) cur[i] = i;
+  __syncthreads();
+  int base = 0, num = n, nkeep = 0;
+  while (num > 0) {
+    // ---- first strict maximum in current order (nms.c:74-81): max score, lowest position
+    float bs = -10000000.0f; int bp = -1;
+    for (int p = tid; p < num; p += EXACT_THREADS) {   // ascending p per thread => strict > keeps first
+      float s = seg_sb[(size_t)cur[base + p] * 5 + 4];
+      if (s > bs) { bs = s; bp = p; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      float os = __shfl_xor_sync(0xffffffffu, bs, off);
+      int op = __shfl_xor_sync(0xffffffffu, bp, off);
+      bool take = (op >= 0) && (bp < 0 || os > bs || (os == bs && op < bp));
+      if (take) { bs = os; bp = op; }
+    }
+    if (lane == 0) { s_best_s[wid] = bs; s_best_p[wid] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      float fs = s_best_s[0]; int fp = s_best_p[0];
+      for (int w = 1; w < EXACT_THREADS / 32; ++w) {
+        float os = s_best_s[w]; int op = s_best_p[w];
+        if ((op >= 0) && (fp < 0 || os > fs || (os == fs && op < fp))) { fs = os; fp = op; }
+      }
+      if (fp >= 0) {                                   // swap to front (nms.c:83-86)
+        int32_t b = cur[base + fp]; cur[base + fp] = cur[base]; cur[base] = b;
+        keep_idx[(size_t)seg * cap + nkeep] = src_idx ? src_idx[(size_t)seg * cap + b] : b;
+      }
+      s_sel = fp;
+    }
+    __syncthreads();
+    if (s_sel < 0) break;      // every remaining score <= -1e7 (or NaN): the reference reads boxes[-1] here (UB)
+    const int32_t bidx = cur[base];
+    const float *bb = seg_sb + (size_t)bidx * 5;
+    const float bx1 = bb[0], by1 = bb[1], bx2 = bb[2], by2 = bb[3];
+    nkeep++; base++;
+    const int m = num - 1;
+    // ---- order-preserving survivor compaction (nms.c:90-99)
+    int good = 0;
+    for (int t0 = 0; t0 < m; t0 += EXACT_THREADS) {
+      int p = t0 + tid; int32_t v = -1; int flag = 0;
+      if (p < m) {
+        v = cur[base + p];
+        const float *o = seg_sb + (size_t)v * 5;
+        float ov = iou_ref(bx1, by1, bx2, by2, o[0], o[1], o[2], o[3]);
+        flag = (ov <= thr) ? 1 : 0;
+      }
+      unsigned ball = __ballot_sync(0xffffffffu, flag);
+      int pre = __popc(ball & ((1u << lane) - 1u));
+      if (lane == 0) s_warp_tot[wid] = __popc(ball);
+      __syncthreads();                                  // all reads of this tile done
+      if (tid == 0) {
+        int acc = 0;
+        for (int w = 0; w < EXACT_THREADS / 32; ++w) { int t = s_warp_tot[w]; s_warp_tot[w] = acc; acc += t; }
+        s_tile_total = acc;
+      }
+      __syncthreads();
+      if (flag) cur[base + good + s_warp_tot[wid] + pre] = v;
+      good += s_tile_total;
+      __syncthreads();
+    }
+    num = good;
+  }
+  if (tid == 0) keep_counts[seg] = nkeep;
+}
+
+}  // namespace
+
+// ---- internal launcher (device buffers, uniform capacity) --------------------------
+// Workspace layout inside ctx scratch slot 2.
+int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const int32_t *counts_dev,
+                   const int32_t *src_idx_dev, float thr, int32_t *keep_idx_dev,
+                   int32_t *keep_counts_dev) {
+  if (nseg <= 0 || cap <= 0) return MPN_OK;
+  const int nwords = (cap + 63) / 64;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  size_t o_order = take(sizeof(int32_t) * (size_t)nseg * cap);
+  size_t o_cur = take(sizeof(int32_t) * (size_t)nseg * cap);
+  size_t o_sorted = take(sizeof(float4) * (size_t)nseg * cap);
+  size_t o_tie = take(sizeof(int32_t) * (size_t)nseg);
+  size_t o_mask = take(sizeof(unsigned long long) * (size_t)nseg * cap * nwords);
+  char *ws = nullptr;
+  MPN_TRY(mpn_scratch2(ctx, off, (void **)&ws));
+  int32_t *order = (int32_t *)(ws + o_order);
+  int32_t *cur = (int32_t *)(ws + o_cur);
+  float4 *sorted = (float4 *)(ws + o_sorted);
+  int32_t *tie = (int32_t *)(ws + o_tie);
+  unsigned long long *mask = (unsigned long long *)(ws + o_mask);
+  MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));
+  dim3 g1((cap + RANK_THREADS - 1) / RANK_THREADS, nseg);
+  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
+  MPN_LAUNCHED(ctx);
+  dim3 g2(nwords, nwords, nseg);
+  nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, thr, mask);
+  MPN_LAUNCHED(ctx);
+  nms_scan_kernel<<<nseg, SCAN_THREADS, sizeof(unsigned long long) * nwords, ctx->stream>>>(
+      mask, order, cap, nwords, counts_dev, tie, src_idx_dev, keep_idx_dev, keep_counts_dev);
+  MPN_LAUNCHED(ctx);
+  nms_exact_kernel<<<nseg, EXACT_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, tie, thr, cur,
+                                                            src_idx_dev, keep_idx_dev, keep_counts_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
+// ---- nms_dense (utils.lua:402-462): different IoU rounding order, index output -------
+namespace {
+__device__ __forceinline__ float iou_dense(float4 c, float areac, float4 j, float areaj) {
+  float xx1 = (j.x < c.x) ? c.x : j.x;                       // clamp(x1[c], inf)
+  float yy1 = (j.y < c.y) ? c.y : j.y;
+  float xx2 = (j.z < 0.f) ? 0.f : ((j.z > c.z) ? c.z : j.z); // clamp(0, x2[c])
+  float yy2 = (j.w < 0.f) ? 0.f : ((j.w > c.w) ? c.w : j.w);
+  float w = __fadd_rn(__fsub_rn(xx2, xx1), 1.0f); if (w < 0.f) w = 0.f;
+  float h = __fadd_rn(__fsub_rn(yy2, yy1), 1.0f); if (h < 0.f) h = 0.f;
+  float inter = __fmul_rn(w, h);
+  float uni = __fadd_rn(__fsub_rn(areaj, inter), areac);
+  return __fdiv_rn(inter, uni);
+}
+// same tiling as nms_mask_kernel, but nms_dense marks EVERY j (also j<i; those are
+// already decided when i is reached, so only j>i matters) => identical structure.
+__global__ void __launch_bounds__(64)
+nms_dense_mask_kernel(const float4 *__restrict__ boxes, int n, int nwords, float thr,
+                      unsigned long long *__restrict__ mask) {
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (cb < rb) return;
+  __shared__ float4 s_col[64];
+  const int t = threadIdx.x, cj = cb * 64 + t;
+  s_col[t] = (cj < n) ? boxes[cj] : make_float4(0, 0, 0, 0);
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= n) return;
+  const float4 a = boxes[i];
+  const float areaa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.0f), __fadd_rn(__fsub_rn(a.w, a.y), 1.0f));
+  unsigned long long bits = 0ull;
+  const int ncols = min(64, n - cb * 64);
+  const int start = (rb == cb) ? t + 1 : 0;
+  for (int c = start; c < ncols; ++c) {
+    float4 b = s_col[c];
+    float areab = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.0f), __fadd_rn(__fsub_rn(b.w, b.y), 1.0f));
+    float v = iou_dense(a, areaa, b, areab);
+    if (v > thr) bits |= (1ull << c);
+  }
+  mask[(size_t)i * nwords + cb] = bits;
+}
+}  // namespace
+
+int mpn_nms_dense_launch(mpn_ctx *ctx, const float *sb_dev, int n, float thr, int32_t *pick_dev,
+                         int32_t *count_dev) {
+  if (n <= 0) return MPN_OK;
+  const int nwords = (n + 63) / 64;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  size_t o_order = take(sizeof(int32_t) * n), o_sorted = take(sizeof(float4) * n),
+         o_tie = take(sizeof(int32_t) * 2), o_mask = take(sizeof(unsigned long long) * (size_t)n * nwords);
+  char *ws = nullptr;
+  MPN_TRY(mpn_scratch2(ctx, off, (void **)&ws));
+  int32_t *order = (int32_t *)(ws + o_order);
+  float4 *sorted = (float4 *)(ws + o_sorted);
+  int32_t *tie = (int32_t *)(ws + o_tie);            // tie[0]: real flag (ignored), tie[1]: always 0
+  unsigned long long *mask = (unsigned long long *)(ws + o_mask);
+  MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * 2, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int32_t), ctx->stream));
+  dim3 g1((n + RANK_THREADS - 1) / RANK_THREADS, 1);
+  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, n, nullptr, order, sorted, tie);
+  MPN_LAUNCHED(ctx);
+  dim3 g2(nwords, nwords, 1);
+  nms_dense_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, n, nwords, thr, mask);
+  MPN_LAUNCHED(ctx);
+  nms_scan_kernel<<<1, SCAN_THREADS, sizeof(unsigned long long) * nwords, ctx->stream>>>(
+      mask, order, n, nwords, nullptr, tie + 1, nullptr, pick_dev, count_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
+// ---- bbox_vote (nms.c:110-142): one block per NMS box, fixed-order accumulation -------
+namespace {
+// The reference accumulates over j = 0..N-1 sequentially in fp32. A parallel tree would
+// change the rounding, so each block walks j in order in chunks: lanes evaluate the
+// overlaps in parallel, then ONE thread adds the selected terms in ascending j.
+__global__ void __launch_bounds__(256)
+bbox_vote_kernel(const float *__restrict__ nms_boxes, int K, const float *__restrict__ sb, int N,
+                 float thr, float *__restrict__ res) {
+  const int i = blockIdx.x;
+  if (i >= K) return;
+  __shared__ unsigned char s_sel[256];
+  const float *nb = nms_boxes + (size_t)i * 5;
+  const float nx1 = nb[0], ny1 = nb[1], nx2 = nb[2], ny2 = nb[3];
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+  for (int base = 0; base < N; base += 256) {
+    int j = base + threadIdx.x;
+    unsigned char sel = 0;
+    if (j < N) {
+      const float *o = sb + (size_t)j * 5;
+      float ov = iou_ref(o[0], o[1], o[2], o[3], nx1, ny1, nx2, ny2);   // overlap(scored_j, nms_i), nms.c:129
+      sel = (ov > thr) ? 1 : 0;
+    }
+    s_sel[threadIdx.x] = sel;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int lim = min(256, N - base);
+      for (int t = 0; t < lim; ++t) {
+        if (s_sel[t]) {
+          const float *o = sb + (size_t)(base + t) * 5;
+          float s = o[4];
+          acc0 = __fadd_rn(acc0, __fmul_rn(o[0], s));
+          acc1 = __fadd_rn(acc1, __fmul_rn(o[1], s));
+          acc2 = __fadd_rn(acc2, __fmul_rn(o[2], s));
+          acc3 = __fadd_rn(acc3, __fmul_rn(o[3], s));
+          acc4 = __fadd_rn(acc4, s);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float *r = res + (size_t)i * 5;
+    r[0] = __fdiv_rn(acc0, acc4); r[1] = __fdiv_rn(acc1, acc4);
+    r[2] = __fdiv_rn(acc2, acc4); r[3] = __fdiv_rn(acc3, acc4);
+    r[4] = nb[4];
+  }
+}
+}  // namespace
+
+int mpn_bbox_vote_launch(mpn_ctx *ctx, const float *nms_dev, int K, const float *sb_dev, int N,
+                         float thr, float *res_dev) {
+  if (K <= 0) return MPN_OK;
+  bbox_vote_kernel<<<K, 256, 0, ctx->stream>>>(nms_dev, K, sb_dev, N, thr, res_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
