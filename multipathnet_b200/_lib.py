@@ -1,0 +1,449 @@
+"""ctypes binding of libmpn_b200.so (include/mpn_abi.h).
+
+This is the Python twin of the LuaJIT `ffi.cdef` shim in lua/mpn_ffi.lua: the reference
+binds its only native code the same way (utils.lua:15-26: cdef + ffi.load of ./libnms.so).
+There is NO fallback: if the CUDA library is missing or no B200 is present, loading or
+context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mpn_abi.h")
+
+MPN_LAYER_CONV, MPN_LAYER_MAXPOOL, MPN_LAYER_AVGPOOL, MPN_LAYER_FLATTEN = 1, 2, 3, 4
+
+
+class MpnError(RuntimeError):
+    pass
+
+
+class CLayer(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "kind", "in_slot", "out_slot", "cin", "cout", "kh", "kw", "stride", "pad", "relu",
+        "residual_slot", "ceil_mode", "weight", "bias")]
+
+
+class CTower(C.Structure):
+    _fields_ = [("region", C.c_int32), ("n_levels", C.c_int32), ("level_slot", C.c_int32 * 3),
+                ("level_scale", C.c_float * 3), ("pooled_w", C.c_int32), ("pooled_h", C.c_int32),
+                ("normalize", C.c_int32), ("n_layers", C.c_int32), ("first_layer", C.c_int32),
+                ("out_slot", C.c_int32)]
+
+
+class CHead(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("col_begin", "col_len", "cout", "weight", "bias")]
+
+
+class CModelDesc(C.Structure):
+    _fields_ = [("n_trunk_layers", C.c_int32), ("trunk_layers", C.POINTER(CLayer)),
+                ("n_towers", C.c_int32), ("towers", C.POINTER(CTower)),
+                ("n_tower_layers", C.c_int32), ("tower_layers", C.POINTER(CLayer)),
+                ("n_cls_heads", C.c_int32), ("cls_heads", C.POINTER(CHead)),
+                ("bbox_head", CHead), ("num_classes", C.c_int32), ("roi_variant", C.c_int32),
+                ("no_softmax", C.c_int32), ("has_bbox_norm", C.c_int32),
+                ("bbox_mean", C.c_float * 4), ("bbox_std", C.c_float * 4),
+                ("max_rois", C.c_int32), ("max_h", C.c_int32), ("max_w", C.c_int32)]
+
+
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_vp = C.c_void_p
+
+# name -> (restype, argtypes). Mirrors include/mpn_abi.h one to one (tests check the symbol set).
+SIGNATURES = {
+    "mpn_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "mpn_ctx_destroy": (None, [_vp]),
+    "mpn_last_error": (C.c_char_p, [_vp]),
+    "mpn_ctx_synchronize": (C.c_int, [_vp]),
+    "mpn_ctx_launch_count": (C.c_int64, [_vp]),
+    "mpn_version": (C.c_char_p, []),
+    "mpn_nms": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp, _i64p]),
+    "mpn_nms_batched": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _i64p]),
+    "mpn_nms_batched_dev": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _vp]),
+    "mpn_nms_dense": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp, _i64p]),
+    "mpn_bbox_vote": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_float, _vp]),
+    "mpn_foveal": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "mpn_context_region": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp]),
+    "mpn_bbox_norm": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "mpn_bbox_decode": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp]),
+    "mpn_roi_pool": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64,
+                               C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp]),
+    "mpn_roi_pool_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64,
+                                   C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp]),
+    "mpn_model_create": (C.c_int, [_vp, C.POINTER(CModelDesc), C.POINTER(_vp), _i64p, C.c_int32, C.POINTER(_vp)]),
+    "mpn_model_destroy": (None, [_vp]),
+    "mpn_model_trunk": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    "mpn_model_trunk_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    "mpn_model_heads": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
+    "mpn_model_heads_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),
+    "mpn_model_detect": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_int32, _vp, _vp]),
+    "mpn_model_detect_nms": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "mpn_model_detect_nms_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
+                                           C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "mpn_model_get_trunk_slot": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p, _i32p]),
+    "mpn_model_set_conv_impl": (C.c_int, [_vp, C.c_int32]),
+    "mpn_model_last_flops": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mpn_gemm_check": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp]),
+    "mpn_conv_check": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64,
+                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmpn_b200.so and bind every symbol of the ABI. Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpnError(
+            f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the .so does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(f"cannot take the address of {type(a)}")
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Context:
+    """One mpn_ctx: (thread, device, stream). Mirrors the one-replica-per-thread model of
+    test_runner.lua:55-66."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.mpn_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise MpnError(f"mpn_ctx_create failed ({rc}): {self.lib.mpn_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    def check(self, rc: int, what: str = ""):
+        if rc != 0:
+            raise MpnError(f"{what} failed ({rc}): {self.lib.mpn_last_error(self.h).decode()}")
+
+    def synchronize(self):
+        self.check(self.lib.mpn_ctx_synchronize(self.h), "synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mpn_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mpn_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- NMS family -------------------------------------------------------------------------
+    def nms(self, scored_boxes, thr: float) -> np.ndarray:
+        sb = _f32(scored_boxes).reshape(-1, 5)
+        n = sb.shape[0]
+        keep = np.empty(max(n, 1), dtype=np.int32)
+        cnt = C.c_int64(0)
+        self.check(self.lib.mpn_nms(self.h, _ptr(sb), n, float(thr), _ptr(keep), C.byref(cnt)), "mpn_nms")
+        return keep[: cnt.value].copy()
+
+    def nms_batched(self, scored_boxes, seg_offsets: Sequence[int], thr: float) -> List[np.ndarray]:
+        sb = _f32(scored_boxes).reshape(-1, 5)
+        offs = np.ascontiguousarray(seg_offsets, dtype=np.int64)
+        nseg = len(offs) - 1
+        keep = np.empty(max(sb.shape[0], 1), dtype=np.int32)
+        counts = np.zeros(max(nseg, 1), dtype=np.int64)
+        self.check(self.lib.mpn_nms_batched(self.h, _ptr(sb), offs.ctypes.data_as(_i64p), nseg, float(thr), _ptr(keep),
+                                            counts.ctypes.data_as(_i64p)), "mpn_nms_batched")
+        return [keep[offs[s]: offs[s] + counts[s]].copy() for s in range(nseg)]
+
+    def nms_dense(self, scored_boxes, thr: float) -> np.ndarray:
+        sb = _f32(scored_boxes).reshape(-1, 5)
+        n = sb.shape[0]
+        pick = np.empty(max(n, 1), dtype=np.int32)
+        cnt = C.c_int64(0)
+        self.check(self.lib.mpn_nms_dense(self.h, _ptr(sb), n, float(thr), _ptr(pick), C.byref(cnt)), "mpn_nms_dense")
+        return pick[: cnt.value].copy()
+
+    def bbox_vote(self, nms_boxes, scored_boxes, thr: float) -> np.ndarray:
+        nb = _f32(nms_boxes).reshape(-1, 5)
+        sb = _f32(scored_boxes).reshape(-1, 5)
+        res = np.zeros_like(nb)
+        self.check(self.lib.mpn_bbox_vote(self.h, _ptr(nb), nb.shape[0], _ptr(sb), sb.shape[0], float(thr), _ptr(res)),
+                   "mpn_bbox_vote")
+        return res
+
+    # ---- region modules ---------------------------------------------------------------------
+    def foveal(self, rois) -> np.ndarray:
+        r = _f32(rois)
+        out = np.empty((r.shape[0] * 4, 5), dtype=np.float32)
+        self.check(self.lib.mpn_foveal(self.h, _ptr(r), r.shape[0], _ptr(out)), "mpn_foveal")
+        return out
+
+    def context_region(self, rois, scale: float) -> np.ndarray:
+        r = _f32(rois)
+        out = np.empty_like(r)
+        self.check(self.lib.mpn_context_region(self.h, _ptr(r), r.shape[0], float(scale), _ptr(out)), "mpn_context_region")
+        return out
+
+    def bbox_norm(self, deltas, mean, std) -> np.ndarray:
+        d = _f32(deltas).copy()
+        m, s = _f32(mean).reshape(4), _f32(std).reshape(4)
+        self.check(self.lib.mpn_bbox_norm(self.h, _ptr(d), d.shape[0], d.shape[1], _ptr(m), _ptr(s)), "mpn_bbox_norm")
+        return d
+
+    def bbox_decode(self, deltas, boxes) -> np.ndarray:
+        d, b = _f32(deltas), _f32(boxes)
+        out = np.empty_like(d)
+        self.check(self.lib.mpn_bbox_decode(self.h, _ptr(d), _ptr(b), d.shape[0], d.shape[1] // 4, _ptr(out)), "mpn_bbox_decode")
+        return out
+
+    def roi_pool(self, fmap, rois, pw: int, ph: int, scale: float, variant: int = 2, with_argmax: bool = False):
+        f, r = _f32(fmap), _f32(rois)
+        n, c, h, w = f.shape
+        out = np.empty((r.shape[0], c, ph, pw), dtype=np.float32)
+        am = np.empty(out.shape, dtype=np.int32) if with_argmax else None
+        self.check(self.lib.mpn_roi_pool(self.h, _ptr(f), n, c, h, w, _ptr(r), r.shape[0], pw, ph, float(scale), variant,
+                                         _ptr(out), _ptr(am)), "mpn_roi_pool")
+        return (out, am) if with_argmax else out
+
+    # ---- engine checks ----------------------------------------------------------------------
+    def gemm_check(self, A, B, bias=None, relu=False, impl=0) -> np.ndarray:
+        A, B = _f32(A), _f32(B)
+        m, k = A.shape
+        n = B.shape[0]
+        bias = None if bias is None else _f32(bias)
+        out = np.empty((m, n), dtype=np.float32)
+        self.check(self.lib.mpn_gemm_check(self.h, _ptr(A), _ptr(B), _ptr(bias), m, n, k, int(relu), impl, _ptr(out)), "mpn_gemm_check")
+        return out
+
+    def conv_check(self, x, w, bias=None, stride=1, pad=0, relu=False, impl=0) -> np.ndarray:
+        x, w = _f32(x), _f32(w)
+        n, cin, h, ww = x.shape
+        cout, _, kh, kw = w.shape
+        bias = None if bias is None else _f32(bias)
+        ho, wo = (h + 2 * pad - kh) // stride + 1, (ww + 2 * pad - kw) // stride + 1
+        y = np.empty((n, cout, ho, wo), dtype=np.float32)
+        self.check(self.lib.mpn_conv_check(self.h, _ptr(x), n, cin, h, ww, _ptr(w), _ptr(bias), cout, kh, kw, stride, pad,
+                                           int(relu), impl, _ptr(y)), "mpn_conv_check")
+        return y
+
+
+# ------------------------------------------------------------------------------------------
+# model description (Python twin of mpn_model_desc) — built by multipathnet_b200.models
+@dataclass
+class Layer:
+    kind: int
+    in_slot: int
+    out_slot: int
+    cin: int = 0
+    cout: int = 0
+    kh: int = 1
+    kw: int = 1
+    stride: int = 1
+    pad: int = 0
+    relu: int = 0
+    residual_slot: int = -1
+    ceil_mode: int = 0
+    weight: int = -1
+    bias: int = -1
+
+    def to_c(self) -> CLayer:
+        return CLayer(self.kind, self.in_slot, self.out_slot, self.cin, self.cout, self.kh, self.kw, self.stride,
+                      self.pad, self.relu, self.residual_slot, self.ceil_mode, self.weight, self.bias)
+
+
+@dataclass
+class Tower:
+    region: int
+    levels: List[tuple]            # [(trunk_slot, spatial_scale), ...] channel-concat order
+    pooled_w: int
+    pooled_h: int
+    normalize: int
+    layers: List[Layer]
+    out_slot: int
+
+
+@dataclass
+class Head:
+    col_begin: int
+    col_len: int
+    cout: int
+    weight: int
+    bias: int
+
+    def to_c(self) -> CHead:
+        return CHead(self.col_begin, self.col_len, self.cout, self.weight, self.bias)
+
+
+@dataclass
+class ModelSpec:
+    name: str
+    trunk_layers: List[Layer]
+    towers: List[Tower]
+    cls_heads: List[Head]
+    bbox_head: Head
+    num_classes: int
+    weights: List[np.ndarray]
+    roi_variant: int = 2
+    no_softmax: int = 0
+    has_bbox_norm: int = 1
+    bbox_mean: tuple = (0.0, 0.0, 0.0, 0.0)
+    bbox_std: tuple = (0.1, 0.1, 0.2, 0.2)
+    transformer: str = "ross"      # "ross" | "imagenet"  (model_utils.lua:138-155)
+    taps: dict = field(default_factory=dict)   # name -> trunk slot, for tests
+
+
+class Model:
+    """mpn_model handle: the B200 replacement for the nn.Sequential graph a model file returns."""
+
+    def __init__(self, ctx: Context, spec: ModelSpec, max_rois: int = 2048, max_h: int = 1024, max_w: int = 1344):
+        self.ctx, self.spec = ctx, spec
+        lib = ctx.lib
+        trunk = (CLayer * len(spec.trunk_layers))(*[l.to_c() for l in spec.trunk_layers])
+        tl: List[Layer] = []
+        ctowers = []
+        for t in spec.towers:
+            ct = CTower()
+            ct.region, ct.n_levels = t.region, len(t.levels)
+            for i, (slot, sc) in enumerate(t.levels):
+                ct.level_slot[i] = slot
+                ct.level_scale[i] = sc
+            ct.pooled_w, ct.pooled_h, ct.normalize = t.pooled_w, t.pooled_h, t.normalize
+            ct.n_layers, ct.first_layer, ct.out_slot = len(t.layers), len(tl), t.out_slot
+            tl.extend(t.layers)
+            ctowers.append(ct)
+        towers = (CTower * len(ctowers))(*ctowers)
+        tower_layers = (CLayer * max(len(tl), 1))(*[l.to_c() for l in tl])
+        heads = (CHead * len(spec.cls_heads))(*[h.to_c() for h in spec.cls_heads])
+        d = CModelDesc()
+        d.n_trunk_layers, d.trunk_layers = len(spec.trunk_layers), trunk
+        d.n_towers, d.towers = len(ctowers), towers
+        d.n_tower_layers, d.tower_layers = len(tl), tower_layers
+        d.n_cls_heads, d.cls_heads = len(spec.cls_heads), heads
+        d.bbox_head = spec.bbox_head.to_c()
+        d.num_classes, d.roi_variant = spec.num_classes, spec.roi_variant
+        d.no_softmax, d.has_bbox_norm = spec.no_softmax, spec.has_bbox_norm
+        for i in range(4):
+            d.bbox_mean[i] = spec.bbox_mean[i]
+            d.bbox_std[i] = spec.bbox_std[i]
+        d.max_rois, d.max_h, d.max_w = max_rois, max_h, max_w
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in spec.weights]
+        wptrs = (_vp * len(ws))(*[w.ctypes.data for w in ws])
+        wn = np.array([w.size for w in ws], dtype=np.int64)
+        h = _vp()
+        ctx.check(lib.mpn_model_create(ctx.h, C.byref(d), wptrs, wn.ctypes.data_as(_i64p), len(ws), C.byref(h)),
+                  "mpn_model_create")
+        self.h = h
+        self.C = spec.num_classes
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.mpn_model_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_conv_impl(self, impl: int):
+        self.ctx.check(self.ctx.lib.mpn_model_set_conv_impl(self.h, impl), "set_conv_impl")
+
+    def trunk(self, image_chw):
+        im = _f32(image_chw)
+        assert im.ndim == 3 and im.shape[0] == 3
+        self.ctx.check(self.ctx.lib.mpn_model_trunk(self.h, _ptr(im), im.shape[1], im.shape[2]), "mpn_model_trunk")
+
+    def heads(self, rois):
+        r = _f32(rois)
+        n = r.shape[0]
+        cls = np.empty((n, self.C), dtype=np.float32)
+        bbox = np.empty((n, 4 * self.C), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.mpn_model_heads(self.h, _ptr(r), n, _ptr(cls), _ptr(bbox)), "mpn_model_heads")
+        return cls, bbox
+
+    def forward(self, image_chw, rois):
+        """model:forward{images, rois} (eval mode)."""
+        self.trunk(image_chw)
+        return self.heads(rois)
+
+    def detect(self, image_chw, boxes, im_scale: float, recompute_features: bool = True):
+        b = _f32(boxes)
+        n = b.shape[0]
+        im = None if image_chw is None else _f32(image_chw)
+        scores = np.empty((n, self.C), dtype=np.float32)
+        bboxes = np.empty((n, 4 * self.C), dtype=np.float32)
+        H, W = (im.shape[1], im.shape[2]) if im is not None else (0, 0)
+        self.ctx.check(self.ctx.lib.mpn_model_detect(self.h, _ptr(im), H, W, _ptr(b), n, float(im_scale),
+                                                     int(recompute_features), _ptr(scores), _ptr(bboxes)), "mpn_model_detect")
+        return scores, bboxes
+
+    def detect_nms(self, image_chw, boxes, im_scale: float, W0: float, H0: float, score_thresh: float = -1.5,
+                   nms_thr: float = 0.3, want_raw: bool = True):
+        im, b = _f32(image_chw), _f32(boxes)
+        n = b.shape[0]
+        scores = np.empty((n, self.C), dtype=np.float32) if want_raw else None
+        bboxes = np.empty((n, 4 * self.C), dtype=np.float32) if want_raw else None
+        keep = np.empty((self.C - 1, n), dtype=np.int32)
+        counts = np.empty(self.C - 1, dtype=np.int32)
+        self.ctx.check(self.ctx.lib.mpn_model_detect_nms(
+            self.h, _ptr(im), im.shape[1], im.shape[2], _ptr(b), n, float(im_scale), float(W0), float(H0),
+            float(score_thresh), float(nms_thr), _ptr(scores), _ptr(bboxes), _ptr(keep), _ptr(counts)), "mpn_model_detect_nms")
+        return scores, bboxes, [keep[j, : counts[j]].copy() for j in range(self.C - 1)]
+
+    def detect_nms_dev(self, image_dev, H: int, W: int, boxes_dev, R: int, im_scale: float, W0: float, H0: float,
+                       score_thresh: float, nms_thr: float, scores_dev=None, bboxes_dev=None, keep_idx_dev=None,
+                       keep_counts_dev=None):
+        """Fully device-resident, asynchronous (arguments are torch CUDA tensors or raw addresses)."""
+        self.ctx.check(self.ctx.lib.mpn_model_detect_nms_dev(
+            self.h, _ptr(image_dev), H, W, _ptr(boxes_dev), R, float(im_scale), float(W0), float(H0), float(score_thresh),
+            float(nms_thr), _ptr(scores_dev), _ptr(bboxes_dev), _ptr(keep_idx_dev), _ptr(keep_counts_dev)),
+            "mpn_model_detect_nms_dev")
+
+    def trunk_slot(self, slot: int) -> np.ndarray:
+        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.lib.mpn_model_get_trunk_slot(self.h, slot, None, 0, C.byref(c), C.byref(h), C.byref(w)), "get_trunk_slot")
+        out = np.empty((1, c.value, h.value, w.value), dtype=np.float32)
+        self.ctx.check(self.ctx.lib.mpn_model_get_trunk_slot(self.h, slot, _ptr(out), out.size, C.byref(c), C.byref(h), C.byref(w)),
+                       "get_trunk_slot")
+        return out
+
+    def last_flops(self):
+        a, b = C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.mpn_model_last_flops(self.h, C.byref(a), C.byref(b)), "last_flops")
+        return a.value, b.value

@@ -62,14 +62,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Bounded spin: a protocol bug must surface as a trap with a message, never as a silent
+// GPU hang (a hung box costs a whole gpurun call). ~2^26 polls is seconds of wall time.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && ++spins == (1u << 26)) {
+      printf("[mpn] mbarrier wait timed out: block %d warp %d bar@%u parity %u\n", (int)blockIdx.x,
+             (int)(threadIdx.x >> 5), bar, parity);
+      __trap();
+    }
   } while (!done);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,

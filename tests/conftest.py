@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_built():
+    from oracle import ref
+    ref.build()
+    return ref
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    import multipathnet_b200 as mpn
+    c = mpn.Context(0)       # raises loudly if the .so or the GPU is missing: no fallback
+    yield c
+    c.close()
+
+
+def rel_err(a, b):
+    """normwise relative error max|a-b| / max|b| (SURVEY 7 hard-part 1: elementwise is meaningless near 0)"""
+    import numpy as np
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))

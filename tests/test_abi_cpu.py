@@ -1,0 +1,124 @@
+"""CPU suite, part 2: the C-ABI library loads and exports exactly what include/mpn_abi.h declares
+(no compute without a GPU), and the host-side logic (specs, workloads, ImageDetect geometry)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import multipathnet_b200 as mpn
+from multipathnet_b200 import _lib, models, workloads as wl
+from multipathnet_b200.image_detect import ImageDetect, _bilinear_resize
+from multipathnet_b200.modules import ImageTransformer
+
+
+def _header_functions():
+    src = open(_lib.HEADER_PATH).read()
+    body = src[src.index("MPN_CDEF_BEGIN"):src.index("MPN_CDEF_END")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpn_[a-z0-9_]+)\s*\(", body)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = mpn.load_library()
+    declared = _header_functions()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mpn_abi.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table out of sync with the header"
+    assert b"sm_100a" in lib.mpn_version()
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """without a CUDA device context creation must fail with a message (never a CPU fallback)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mpn.MpnError):
+        mpn.Context(0)
+    lib = mpn.load_library()
+    assert len(lib.mpn_last_error(None)) > 0
+    # NULL-handle calls are rejected, not crashes
+    assert lib.mpn_ctx_synchronize(None) < 0
+    assert lib.mpn_ctx_launch_count(None) == -1
+    lib.mpn_ctx_destroy(None); lib.mpn_model_destroy(None)
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.CLayer) == 14 * 4
+    assert ctypes.sizeof(_lib.CHead) == 5 * 4
+    assert ctypes.sizeof(_lib.CTower) == 4 * (2 + 3 + 3 + 6)
+
+
+def test_vgg16_flops_match_survey():
+    s = models.vgg16_fast_rcnn(21)
+    assert abs(models.trunk_flops(s, 600, 800) / 1e9 - 294.0) < 0.1
+    assert abs(models.head_flops_per_roi(s) / 1e6 - 239.9) < 0.1
+    s81 = models.vgg16_fast_rcnn(81, fc_dim=4096)
+    assert abs(models.head_flops_per_roi(s81) / 1e6 - 242.4) < 0.1
+    assert s.taps == {"conv3": 9, "conv4": 13, "conv5": 17}
+
+
+def test_multipathnet_spec_structure():
+    s = models.vgg16_multipathnet(81)
+    assert [t.region for t in s.towers] == [0, 1, 2, 3, 1]                   # multipathnet.lua:73-113
+    assert [len(t.levels) for t in s.towers] == [3, 2, 2, 1, 3]
+    assert s.cls_heads[0].col_len == 4 * 4096 and s.bbox_head.col_begin == 4 * 4096
+    assert abs(models.head_flops_per_roi(s) / 1e9 - 1.458) < 0.01
+
+
+def test_resnet50_flops_match_survey():
+    s = models.resnet50_fast_rcnn(81, integral_k=6)
+    assert abs(models.trunk_flops(s, 800, 1000) / 1e9 - 104.9) < 1.5
+    assert abs(models.head_flops_per_roi(s) / 1e9 - 1.62) < 0.02
+
+
+def test_workloads_are_seeded_and_valid():
+    b1, b2 = wl.random_boxes(100, 600, 800, 2), wl.random_boxes(100, 600, 800, 2)
+    assert np.array_equal(b1, b2)
+    assert np.all(b1[:, 0] >= 1) and np.all(b1[:, 2] <= 800) and np.all(b1[:, 3] <= 600) and np.all(b1[:, 2] > b1[:, 0])
+    sm = wl.sharpmask_boxes(500, 600, 800, 3)
+    assert np.all(sm[:, 2] > sm[:, 0]) and np.all(sm[:, 3] > sm[:, 1]) and sm.min() >= 1
+    sb = wl.nms_sweep_boxes(64, 3, 5)
+    assert sb.shape == (3, 64, 5) and len(np.unique(sb[0, :, 4])) == 64
+    assert len(np.unique(wl.nms_sweep_boxes(64, 1, 5, ties=True)[0, :, 4])) < 64
+
+
+def test_transformers():
+    im = wl.raw_image(4, 5, 0)
+    r = ImageTransformer("ross").forward(im)
+    np.testing.assert_allclose(r[0], im[2] * 255 - 102.9801, rtol=1e-6)      # BGR swap, x255, -mean
+    i = ImageTransformer("imagenet").forward(im)
+    np.testing.assert_allclose(i[1], (im[1] - 0.45624044862054) / 0.22446679341259, rtol=1e-5)
+
+
+class _FakeModel:
+    C = 21
+    def detect(self, img, boxes, im_scale, rec):
+        self.args = (None if img is None else img.shape, boxes.shape, im_scale, rec)
+        return np.zeros((len(boxes), 21), np.float32), np.zeros((len(boxes), 84), np.float32)
+
+
+def test_image_detect_scaling_rules():
+    """ImageDetect.lua:31-41: im_scale = scale/min side, capped so round(im_scale*max side) <= max_size"""
+    d = ImageDetect(_FakeModel(), ImageTransformer("ross"), [600], 1000)
+    img, s = d.getImages(wl.raw_image(300, 400, 1))
+    assert s == 2.0 and img.shape == (3, 600, 800)
+    img, s = d.getImages(wl.raw_image(300, 900, 1))
+    assert abs(s - 1000 / 900) < 1e-9 and img.shape[2] == 1000
+    img, s = d.getImages(wl.raw_image(600, 800, 1))
+    assert s == 1.0 and img.shape == (3, 600, 800)
+    d.detect(wl.raw_image(600, 800, 1), wl.random_boxes(5, 600, 800, 1))
+    assert d.model.args == ((3, 600, 800), (5, 4), 1.0, True)
+    with pytest.raises(ValueError):
+        ImageDetect(None, ImageTransformer())
+    with pytest.raises(ValueError):
+        ImageDetect(_FakeModel(), ImageTransformer(), [480, 600])
+
+
+def test_bilinear_identity_and_constant():
+    im = wl.raw_image(7, 9, 3)
+    assert _bilinear_resize(im, 7, 9) is im
+    c = np.full((3, 5, 5), 2.5, np.float32)
+    assert np.allclose(_bilinear_resize(c, 11, 13), 2.5)

@@ -1,0 +1,81 @@
+"""GPU parity: the tcgen05 bf16x3 conv/GEMM engine vs fp32 PyTorch-CPU math (the oracle for dense layers).
+Tolerance: 1e-4 normwise per layer (the engine carries ~16 mantissa bits; the path's bar is 1e-3 end to end)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _ref_gemm(A, B, bias, relu):
+    y = torch.from_numpy(A).double() @ torch.from_numpy(B).double().t()
+    if bias is not None:
+        y = y + torch.from_numpy(bias).double()
+    return (F.relu(y) if relu else y).float().numpy()
+
+
+@pytest.mark.parametrize("impl", [1, 0])     # 1 = plain fp32 check kernel first: separates data-prep bugs from engine bugs
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 128), (128, 256, 192), (1, 64, 64), (100, 21, 256),
+                                   (300, 84, 4096), (257, 320, 512), (1000, 4096, 1024), (500, 512, 25088)])
+def test_gemm(ctx, impl, M, N, K):
+    if impl == 1 and M * N * K > 3e9:
+        pytest.skip("check kernel too slow here")
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    got = ctx.gemm_check(A, B, bias, relu=True, impl=impl)
+    assert rel_err(got, _ref_gemm(A, B, bias, True)) < TOL
+
+
+def test_gemm_row_chunk_invariance(ctx):
+    """reference modules/test.lua:85-98 (SequentialSplitBatch_Tensor): chunked rows == unchunked, EXACTLY"""
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((40, 512)).astype(np.float32)
+    B = (rng.standard_normal((9, 512)) / 22).astype(np.float32)
+    b = rng.standard_normal(9).astype(np.float32)
+    full = ctx.gemm_check(A, B, b)
+    parts = np.concatenate([ctx.gemm_check(A[:25], B, b), ctx.gemm_check(A[25:], B, b)])
+    assert np.array_equal(full, parts)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,s,p", [
+    (1, 64, 16, 16, 64, 3, 1, 1), (1, 64, 37, 53, 128, 3, 1, 1), (1, 128, 75, 100, 256, 3, 1, 1), (1, 512, 38, 50, 512, 3, 1, 1),
+    (3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 64, 1, 1, 0), (2, 256, 9, 11, 512, 1, 1, 0), (1, 64, 33, 47, 64, 7, 1, 3),
+    (2, 64, 15, 15, 64, 7, 1, 0)])
+def test_conv_stride1(ctx, impl, N, Cin, H, W, Cout, k, s, p):
+    rng = np.random.default_rng(Cin + H + W + Cout)
+    x = rng.standard_normal((N, Cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = F.relu(F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), stride=s, padding=p)).float().numpy()
+    got = ctx.conv_check(x, w, b, stride=s, pad=p, relu=True, impl=impl)
+    assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("N,Cin,H,W,Cout,k,s,p", [(2, 64, 14, 14, 128, 3, 2, 1), (1, 128, 28, 36, 256, 1, 2, 0), (3, 64, 15, 17, 64, 3, 2, 1)])
+def test_conv_stride2(ctx, impl, N, Cin, H, W, Cout, k, s, p):
+    """ResNet stride-2 convs: TMA elementStrides"""
+    rng = np.random.default_rng(7 + Cin + H)
+    x = rng.standard_normal((N, Cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / np.sqrt(Cin * k * k)).astype(np.float32)
+    ref = F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), None, stride=s, padding=p).float().numpy()
+    got = ctx.conv_check(x, w, None, stride=s, pad=p, relu=False, impl=impl)
+    assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("Cin,Cout,k,s,p,H,W", [(3, 64, 3, 1, 1, 40, 56), (3, 64, 7, 2, 3, 65, 81)])
+def test_first_layer_direct_conv(ctx, Cin, Cout, k, s, p, H, W):
+    rng = np.random.default_rng(11)
+    x = (rng.random((1, Cin, H, W)) * 255 - 110).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, k, k)) / 64).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    ref = F.relu(F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=s, padding=p)).numpy()
+    got = ctx.conv_check(x, w, b, stride=s, pad=p, relu=True, impl=2)
+    assert rel_err(got, ref) < TOL

@@ -1,0 +1,149 @@
+"""GPU parity: whole graphs through the C ABI (trunk, fused Foveal+ROI pooling, heads, decode, softmax, NMS)
+vs the CPU oracle on the same seeded image + proposals. Bars (north_star): class scores and bbox values within
+1e-3 normwise relative fp32; NMS keep indices bit-exact given the same boxes."""
+import numpy as np
+import pytest
+
+import multipathnet_b200 as mpn
+from multipathnet_b200 import models, workloads as wl
+from oracle import graphs as G, ref as O
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _inputs(spec, H, W, R, seed, sharp=False):
+    img = wl.transform(wl.raw_image(H, W, seed), spec.transformer)
+    boxes = (wl.sharpmask_boxes if sharp else wl.random_boxes)(R, H, W, seed)
+    return img, boxes
+
+
+@pytest.fixture(scope="module")
+def small_vgg(ctx):
+    spec = models.vgg16_fast_rcnn(21, seed=7, width_div=4, fc_dim=256)
+    m = mpn.Model(ctx, spec, max_rois=512, max_h=256, max_w=320)
+    yield spec, m
+    m.close()
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_vgg_trunk_features(ctx, small_vgg, impl):
+    spec, m = small_vgg
+    m.set_conv_impl(impl)
+    img, _ = _inputs(spec, 150, 203, 1, 1)
+    m.trunk(img)
+    ts = G.trunk_forward(spec, img)
+    for name, slot in spec.taps.items():
+        got, ref = m.trunk_slot(slot), ts[slot].numpy()
+        assert got.shape == ref.shape, name
+        assert rel_err(got, ref) < 2e-4, name
+    m.set_conv_impl(0)
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+def test_vgg_forward_and_detect(ctx, small_vgg, impl):
+    spec, m = small_vgg
+    m.set_conv_impl(impl)
+    img, boxes = _inputs(spec, 150, 203, 200, 2)
+    rois = O.project_rois(boxes, 1.0)
+    cls, bbox = m.forward(img, rois)
+    rc, rb = G.heads_forward(spec, G.trunk_forward(spec, img), rois)
+    assert rel_err(cls, rc) < TOL and rel_err(bbox, rb) < TOL
+    scores, bboxes = m.detect(img, boxes, 1.0)
+    rs, rbb = G.detect(spec, img, boxes, 1.0)
+    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rbb) < TOL
+    np.testing.assert_allclose(scores.sum(1), 1.0, atol=1e-5)
+    m.set_conv_impl(0)
+
+
+def test_heads_chunk_invariance(ctx, small_vgg):
+    """ImageDetect.lua:126-133 contract: chunked ROI forward == full forward, exactly"""
+    spec, m = small_vgg
+    img, boxes = _inputs(spec, 150, 203, 300, 3)
+    rois = O.project_rois(boxes, 1.0)
+    m.trunk(img)
+    cf, bf = m.heads(rois)
+    c1, b1 = m.heads(rois[:130]); c2, b2 = m.heads(rois[130:])
+    assert np.array_equal(np.concatenate([c1, c2]), cf) and np.array_equal(np.concatenate([b1, b2]), bf)
+
+
+def test_detect_without_recompute_uses_cached_features(ctx, small_vgg):
+    spec, m = small_vgg
+    img, boxes = _inputs(spec, 150, 203, 64, 4)
+    s1, b1 = m.detect(img, boxes, 1.0, True)
+    s2, b2 = m.detect(None, boxes, 1.0, False)            # recompute_features=false (ImageDetect.lua:109-111)
+    assert np.array_equal(s1, s2) and np.array_equal(b1, b2)
+
+
+def test_detect_nms_pipeline(ctx, small_vgg):
+    """Tester_FRCNN:testOne: the GPU keep lists must equal nms.c run on the GPU's own clamped boxes/scores
+    (bit-exact criterion for NMS), and the boxes/scores must be within 1e-3 of the oracle pipeline."""
+    spec, m = small_vgg
+    H, W = 150, 203
+    img, boxes = _inputs(spec, H, W, 250, 5)
+    scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, W, H, -1.5, 0.3)
+    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, W, H)
+    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    assert bboxes[:, 0::2].min() >= 1 and bboxes[:, 0::2].max() <= W and bboxes[:, 1::2].max() <= H
+    for j in range(1, spec.num_classes):
+        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
+        assert np.array_equal(keeps[j - 1], O.nms(sb, 0.3)), f"class {j}"
+    # score threshold gather path (Tester_FRCNN.lua:108-110)
+    thr = float(np.median(scores[:, 1:]))
+    _, _, keeps2 = m.detect_nms(img, boxes, 1.0, W, H, thr, 0.3)
+    for j in range(1, spec.num_classes):
+        sel = np.nonzero(scores[:, j] > thr)[0]
+        sb = np.concatenate([bboxes[sel, 4 * j:4 * j + 4], scores[sel, j:j + 1]], 1).astype(np.float32)
+        assert np.array_equal(keeps2[j - 1], sel[O.nms(sb, 0.3)]), f"class {j}"
+
+
+def test_tester_and_image_detect_mirror(ctx, small_vgg):
+    spec, m = small_vgg
+    raw = wl.raw_image(150, 203, 9)
+    boxes = wl.random_boxes(100, 150, 203, 9)
+    t = mpn.Tester(m, mpn.modules.ImageTransformer(spec.transformer), scale=[150], max_size=400)
+    img_boxes = t.testOne(raw, boxes)
+    assert len(img_boxes) == spec.num_classes - 1 and all(b.shape[1] == 5 for b in img_boxes)
+    det = mpn.ImageDetect(m, mpn.modules.ImageTransformer(spec.transformer), [150], 400)
+    s, b = det.detect(raw, boxes)
+    rs, rb = G.detect(spec, wl.transform(raw, spec.transformer), boxes, 1.0)
+    assert rel_err(s, rs) < TOL and rel_err(b, rb) < TOL
+
+
+def test_multipathnet_small(ctx):
+    """cfg 3 structure at reduced width: 5 towers, foveal regions leaving the image, per-level L2 norm, 1x1 mix"""
+    spec = models.vgg16_multipathnet(21, seed=11, width_div=4, fc_dim=256)
+    m = mpn.Model(ctx, spec, max_rois=256, max_h=256, max_w=320)
+    img, boxes = _inputs(spec, 160, 208, 128, 6, sharp=True)
+    s, b = m.detect(img, boxes, 1.0)
+    rs, rb = G.detect(spec, img, boxes, 1.0)
+    assert rel_err(s, rs) < TOL and rel_err(b, rb) < TOL
+    m.close()
+
+
+def test_multipathnet_integral_head(ctx):
+    spec = models.vgg16_multipathnet(21, seed=12, width_div=4, fc_dim=256, integral_k=3)
+    m = mpn.Model(ctx, spec, max_rois=128, max_h=256, max_w=320)
+    img, boxes = _inputs(spec, 128, 160, 64, 7, sharp=True)
+    s, b = m.detect(img, boxes, 1.0)
+    rs, rb = G.detect(spec, img, boxes, 1.0)
+    assert rel_err(s, rs) < TOL and rel_err(b, rb) < TOL
+    np.testing.assert_allclose(s.sum(1), 1.0, atol=1e-5)
+    m.close()
+
+
+def test_vgg16_full_size_cfg2(ctx):
+    """BASELINE configs[1] at full size: VGG-16, 600x800, R=1000, C=21 — vs the CPU oracle (takes ~10-20 s of CPU)"""
+    spec = models.vgg16_fast_rcnn(21, seed=1234)
+    m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
+    img, boxes = _inputs(spec, 600, 800, 1000, 2)
+    scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
+    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600)
+    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    for j in (1, 7, 20):
+        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
+        assert np.array_equal(keeps[j - 1], O.nms(sb, 0.3))
+    tf, hf = m.last_flops()
+    assert abs(tf / 1e9 - 294.0) < 0.1 and abs(hf / 1e9 - 239.9) < 0.2
+    m.close()
