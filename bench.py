@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — proposals/sec of the detection forward hot path on B200.
+
+Workload (BASELINE.json configs[1], the config `metric` is quoted on): VGG-16 Fast R-CNN, one
+600x800 image + 1000 random proposals per step, C=21, fp32-faithful (bf16x3 split on tcgen05, fp32
+accumulate). A "step" = ONE image through trunk -> fused ROI pooling -> fc6/fc7/cls/bbox -> BBoxNorm
+-> decode + clamp -> softmax -> per-class gather -> batched NMS (20 classes), i.e. everything
+ImageDetect:detect + Tester_FRCNN:testOne do per image.
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (N>1: launched by torchrun, one rank/GPU)
+  python bench.py --impl reference [...]                    the reference's CPU path on the host cores
+
+`value`   : proposals/s with image+proposals already resident in HBM (mpn_model_detect_nms_dev).
+`e2e`     : proposals/s through the host-buffer C-ABI call (mpn_model_detect_nms: pinned host image and
+            boxes copied H2D, scores/boxes/keep lists copied D2H every step, inside the timed region).
+`roofline`: the tcgen05 conv/GEMM kernels (dominant, tensor-bound): algorithmic FLOPs of the step divided
+            by the CUDA-event time of those launches, against MEASURED_PEAKS.json bf16 peak. NOTE the
+            engine issues 3 bf16 MMAs per algorithmic MAC (bf16x3 fp32 emulation); `issued_frac` = 3x.
+`cpu_baseline`: the CPU oracle port (torch-CPU fp32 dense layers + C restatement + literal nms.c) timed
+            on the box's host cores on one image of the same workload (rank 0, N=1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, R, C = 600, 800, 1000, 21
+WORKLOAD = "VGG-16 Fast R-CNN, 600x800 image, 1000 ROIs/image, C=21, detect+NMS (BASELINE configs[1])"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("hbm_gbs"), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores. Torch-7 cannot run
+    here, so the nn graph is the oracle port (PyTorch-CPU fp32 + C restatement) and NMS is the LITERAL nms.c."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from multipathnet_b200 import models, workloads as wl
+    from oracle import graphs as G, ref as O
+    O.build()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = models.vgg16_fast_rcnn(C, seed=1234)
+    use_lit = O.ref_available()
+
+    def nms_fn(sb, thr):          # literal reference nms.c when its build travelled, timing-equivalent restatement otherwise
+        if use_lit:
+            return np.arange(len(O.ref_nms_rows(sb, thr)))
+        return O.nms(sb, thr)
+
+    def step(i):
+        img = wl.transform(wl.raw_image(H, W, 100 + i), spec.transformer)
+        boxes = wl.random_boxes(R, H, W, 100 + i)
+        t0 = time.perf_counter()
+        G.test_one(spec, img, boxes, 1.0, W, H, -1.5, 0.3, nms_fn=nms_fn)
+        return time.perf_counter() - t0
+
+    for i in range(args.warmup):
+        step(i)
+    ts = [step(args.warmup + i) for i in range(args.steps)]
+    total = sum(ts)
+    val = R * args.steps / total
+    line = {"impl": "reference", "metric": "proposals/sec", "value": val, "unit": "proposals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "ms_per_image_p50": 1e3 * statistics.median(ts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host": "CPU only", "threads": cores},
+            "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores,
+                             "kind": "port", "sample": f"{args.steps} full images (1000 ROIs each); dense layers PyTorch-CPU fp32, "
+                                                       f"ROI/decode C restatement, NMS {'literal nms.c' if use_lit else 'nms.c restatement'}"},
+            "e2e": {"value": val, "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps == 40 and args.warmup == 5:
+            args.steps, args.warmup = 3, 1         # defaults sized for a CPU run of a few minutes
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import multipathnet_b200 as mpn
+    from multipathnet_b200 import models, workloads as wl, dist as mdist
+
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream(dev)
+    ctx = mpn.Context(local_rank, stream.cuda_stream if stream.cuda_stream else None)
+    spec = models.vgg16_fast_rcnn(C, seed=1234)
+    model = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
+
+    # ---- synthetic inputs: a small rotating set of distinct images/proposals per rank (seeded by rank)
+    NIMG = 4
+    imgs_h = [wl.transform(wl.raw_image(H, W, 1000 * rank + i), spec.transformer) for i in range(NIMG)]
+    boxes_h = [wl.random_boxes(R, H, W, 1000 * rank + i) for i in range(NIMG)]
+    imgs_d = [torch.from_numpy(x).to(dev) for x in imgs_h]
+    boxes_d = [torch.from_numpy(x).to(dev) for x in boxes_h]
+    scores_d = torch.empty((R, C), dtype=torch.float32, device=dev)
+    bboxes_d = torch.empty((R, 4 * C), dtype=torch.float32, device=dev)
+    keep_d = torch.empty((C - 1, R), dtype=torch.int32, device=dev)
+    counts_d = torch.empty((C - 1,), dtype=torch.int32, device=dev)
+
+    def step_dev(i):
+        k = i % NIMG
+        model.detect_nms_dev(imgs_d[k], H, W, boxes_d[k], R, 1.0, W, H, -1.5, 0.3, scores_d, bboxes_d, keep_d, counts_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+
+    # ---- timed region 1: device-resident throughput (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = ctx.launch_count
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step_dev(i)
+        ev[i + 1].record(stream)
+    if world > 1:
+        # the path's ONE collective: all-gather of this rank's final detections (fixed-size padded records)
+        k = counts_d.clamp(max=mdist.MAX_DET // (C - 1)).to(torch.float32)
+        rec = torch.zeros((1, mdist.REC), dtype=torch.float32, device=dev)
+        rec[0, 0] = k.sum()
+        out = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(out, rec)
+    end_ev = torch.cuda.Event(enable_timing=True); end_ev.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(end_ev)
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * R * args.steps / (total_ms_max / 1e3)
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call (`e2e`)
+    pin_img = [torch.from_numpy(x).pin_memory() for x in imgs_h]
+    pin_box = [torch.from_numpy(x).pin_memory() for x in boxes_h]
+    sc_h = torch.empty((R, C), dtype=torch.float32).pin_memory()
+    bb_h = torch.empty((R, 4 * C), dtype=torch.float32).pin_memory()
+    kp_h = torch.empty((C - 1, R), dtype=torch.int32).pin_memory()
+    ct_h = torch.empty((C - 1,), dtype=torch.int32).pin_memory()
+    lib = ctx.lib
+
+    def step_e2e(i):
+        k = i % NIMG
+        ctx.check(lib.mpn_model_detect_nms(model.h, pin_img[k].data_ptr(), H, W, pin_box[k].data_ptr(), R, 1.0, float(W), float(H),
+                                           -1.5, 0.3, sc_h.data_ptr(), bb_h.data_ptr(), kp_h.data_ptr(), ct_h.data_ptr()), "detect_nms")
+
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * args.steps / float(t.item())
+    h2d = 3 * H * W * 4 + R * 4 * 4
+    d2h = R * C * 4 + R * 4 * C * 4 + (C - 1) * R * 4 + (C - 1) * 4
+
+    # ---- per-kernel-category CUDA-event timing of the same steps (roofline numerators)
+    ctx.profile_begin()
+    for i in range(args.steps):
+        step_dev(i)
+    prof = ctx.profile_end()
+    tflop_step = (models.trunk_flops(spec, H, W) - 2.0 * 3 * 64 * 9 * H * W + models.head_flops_per_roi(spec) * R) / 1e12   # tcgen05 layers only
+    tc_ms_step = prof["conv_gemm_tc"][0] / args.steps
+    peak_tf, hbm_gbs, peak_src = load_peaks()
+    achieved = tflop_step / (tc_ms_step / 1e3) if tc_ms_step > 0 else 0.0
+    n_tc = prof["conv_gemm_tc"][1] // args.steps
+    roofline = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (tcgen05 bf16x3 implicit-GEMM, %d launches/step)" % n_tc,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                "issued_frac": 3.0 * achieved / peak_tf if peak_tf else None, "peak_source": peak_src, "traffic": None,
+                "algorithmic_tflop_per_step": tflop_step, "kernel_ms_per_step": tc_ms_step,
+                "by_category_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    # ROI pooling (HBM-bound secondary kernel): algorithmic bytes = feature map once + rois + pooled output
+    roi_bytes = 512 * 38 * 50 * 4 + R * 5 * 4 + R * 512 * 49 * 4
+    roi_ms = prof["roi_pool"][0] / args.steps
+    roofline["roi_pool"] = {"bound": "hbm", "achieved": roi_bytes / (roi_ms / 1e3) / 1e9 if roi_ms > 0 else None, "peak": hbm_gbs,
+                            "unit": "GB/s", "frac": (roi_bytes / (roi_ms / 1e3) / 1e9 / hbm_gbs) if roi_ms > 0 and hbm_gbs else None,
+                            "algorithmic_bytes": roi_bytes}
+
+    line = {"metric": "proposals/sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "ms_per_image_p50": statistics.median(per_step), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"images sharded over {world} rank(s), 1 all-gather of detections" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: each step streams 0.55 GB of weights + ~1 GB of activations (L2 = 126 MB)",
+                       "nms_thr": 0.3, "score_thresh": -1.5, "roi_variant": 2},
+            "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "mpn_model_detect_nms (host buffers, synchronous)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # bounded CPU sample: ONE full image (1000 ROIs) through the oracle port on all host cores
+        from oracle import graphs as G, ref as O
+        O.build()
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        use_lit = O.ref_available()
+        nms_fn = (lambda sb, thr: np.arange(len(O.ref_nms_rows(sb, thr)))) if use_lit else None
+        t0 = time.perf_counter()
+        G.test_one(spec, imgs_h[0], boxes_h[0], 1.0, W, H, -1.5, 0.3, nms_fn=nms_fn)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": R / dt, "unit": "proposals/s", "cores": cores, "kind": "port",
+                                "sample": f"1 full image (1000 ROIs), {dt:.1f} s; dense layers PyTorch-CPU fp32, ROI/decode C restatement, "
+                                          f"NMS {'literal nms.c' if use_lit else 'nms.c restatement'}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

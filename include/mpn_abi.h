@@ -42,6 +42,11 @@ int mpn_ctx_synchronize(mpn_ctx *ctx);
 /* number of kernels THIS library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx);
 const char *mpn_version(void);
+/* per-category kernel timing for roofline reporting: between begin and end every launch group is
+ * bracketed by CUDA events on the ctx stream. ms_by_cat[6] = {conv/GEMM tcgen05, first-layer direct conv,
+ * fused ROI pooling, NMS, elementwise glue, max/avg pooling}; launches_by_cat likewise (may be NULL). */
+int mpn_ctx_profile_begin(mpn_ctx *ctx);
+int mpn_ctx_profile_end(mpn_ctx *ctx, double *ms_by_cat, int64_t *launches_by_cat);
 
 /* ---- NMS: replaces utils.nms -> nms.c:NMS (utils.lua:29-33, nms.c:59-108) --
  * scored_boxes: N x 5 [x1,y1,x2,y2,score]. Writes the kept ROW INDICES

@@ -1,0 +1,70 @@
+--[[ modules_b200.lua — nn.Module classes with the reference's names whose updateOutput calls the C ABI.
+Loaded INSTEAD of modules/{Foveal,ContextRegion,BBoxNorm}.lua when mpn_backend=b200 (fbcoco.lua:17-21
+requires them by name, torch.load finds classes by name), so serialized models keep loading.
+No C handle is ever stored in a module field (models are torch.save'd, train.lua:195). UNTESTED here. ]]
+local ffi = require 'ffi'
+local mpn = paths.dofile('mpn_ffi.lua')
+local C = mpn.C
+
+-- nn.Foveal (modules/Foveal.lua) ---------------------------------------------------------------
+local Foveal, parent = torch.class('nn.Foveal', 'nn.Module')
+function Foveal:__init() parent.__init(self) end
+function Foveal:updateOutput(input)
+   assert(input:nDimension() == 2)
+   assert(input:size(2) == 5)
+   local cin = input:float():contiguous()
+   local cout = torch.FloatTensor(input:size(1) * 4, 5)
+   local ctx = mpn.ctx()
+   mpn.check(ctx, C.mpn_foveal(ctx, mpn.fptr(cin), cin:size(1), mpn.fptr(cout)), 'mpn_foveal')
+   self.output:resize(cout:size()):copy(cout)
+   return self.output
+end
+
+-- nn.ContextRegion (modules/ContextRegion.lua) ---------------------------------------------------
+local Context, cparent = torch.class('nn.ContextRegion', 'nn.Module')
+function Context:__init(scale) cparent.__init(self); self.scale = scale end
+function Context:updateOutput(input)
+   assert(input:nDimension() == 2)
+   assert(input:size(2) == 5)
+   local cin = input:float():contiguous()
+   local cout = torch.FloatTensor(cin:size())
+   local ctx = mpn.ctx()
+   mpn.check(ctx, C.mpn_context_region(ctx, mpn.fptr(cin), cin:size(1), self.scale, mpn.fptr(cout)), 'mpn_context_region')
+   self.output:resize(cout:size()):copy(cout)
+   return self.output
+end
+function Context:updateGradInput(input, gradOutput)
+   self.gradInput:resizeAs(input):zero()
+   return self.gradInput
+end
+
+-- nn.BBoxNorm (modules/BBoxNorm.lua) -------------------------------------------------------------
+local BBoxNorm, bparent = torch.class('nn.BBoxNorm', 'nn.Module')
+function BBoxNorm:__init(mean, std)
+   assert(mean and std)
+   bparent.__init(self)
+   self.mean = mean; self.std = std
+end
+function BBoxNorm:updateOutput(input)
+   assert(input:dim() == 2 and input:size(2) % 4 == 0)
+   self.output:set(input)
+   if not self.train then
+      local x = input:float():contiguous()
+      local m, s = self.mean:float():contiguous(), self.std:float():contiguous()
+      local ctx = mpn.ctx()
+      mpn.check(ctx, C.mpn_bbox_norm(ctx, mpn.fptr(x), x:size(1), x:size(2), mpn.fptr(m), mpn.fptr(s)), 'mpn_bbox_norm')
+      self._output = self._output or input.new()
+      self._output:resize(x:size()):copy(x)
+      self.output = self._output
+   end
+   return self.output
+end
+function BBoxNorm:updateGradInput(input, gradOutput)
+   assert(self.train, 'cannot updateGradInput in evaluate mode')
+   self.gradInput = gradOutput
+   return self.gradInput
+end
+function BBoxNorm:clearState()
+   nn.utils.clear(self, '_output')
+   return bparent.clearState(self)
+end

@@ -66,6 +66,8 @@ SIGNATURES = {
     "mpn_ctx_synchronize": (C.c_int, [_vp]),
     "mpn_ctx_launch_count": (C.c_int64, [_vp]),
     "mpn_version": (C.c_char_p, []),
+    "mpn_ctx_profile_begin": (C.c_int, [_vp]),
+    "mpn_ctx_profile_end": (C.c_int, [_vp, C.POINTER(C.c_double), _i64p]),
     "mpn_nms": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp, _i64p]),
     "mpn_nms_batched": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _i64p]),
     "mpn_nms_batched_dev": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _vp]),
@@ -159,6 +161,17 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.mpn_ctx_launch_count(self.h))
+
+    PROFILE_CATS = ("conv_gemm_tc", "conv_direct", "roi_pool", "nms", "elementwise", "pool")
+
+    def profile_begin(self):
+        self.check(self.lib.mpn_ctx_profile_begin(self.h), "profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 6)()
+        n = (C.c_int64 * 6)()
+        self.check(self.lib.mpn_ctx_profile_end(self.h, ms, n), "profile_end")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(self.PROFILE_CATS)}
 
     def close(self):
         if getattr(self, "h", None):

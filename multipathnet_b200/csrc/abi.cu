@@ -85,6 +85,8 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
+  for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -101,6 +103,32 @@ int mpn_ctx_synchronize(mpn_ctx *ctx) {
 }
 
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int mpn_ctx_profile_begin(mpn_ctx *ctx) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (auto &r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+  ctx->prof.clear();
+  ctx->profiling = 1;
+  return MPN_OK;
+}
+
+int mpn_ctx_profile_end(mpn_ctx *ctx, double *ms_by_cat, int64_t *launches_by_cat) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->profiling = 0;
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < MPN_NCAT; ++c) { if (ms_by_cat) ms_by_cat[c] = 0.0; if (launches_by_cat) launches_by_cat[c] = 0; }
+  for (auto &r : ctx->prof) {
+    float ms = 0.f;
+    MPN_CUDA(ctx, cudaEventElapsedTime(&ms, r.a, r.b));
+    if (ms_by_cat) ms_by_cat[r.cat] += ms;
+    if (launches_by_cat) launches_by_cat[r.cat] += 1;
+    ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  return MPN_OK;
+}
 
 // ------------------------------------------------------------------ NMS family
 int mpn_nms_batched_dev(mpn_ctx *ctx, const float *scored_boxes_dev, const int64_t *seg_offsets, int64_t nseg,

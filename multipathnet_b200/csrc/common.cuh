@@ -19,6 +19,27 @@ struct mpn_ctx {
   // scratch owned by the ctx (grown on demand, never shrunk)
   void *scratch = nullptr; size_t scratch_bytes = 0;
   void *scratch2 = nullptr; size_t scratch2_bytes = 0;
+  // optional per-category kernel timing (bench.py roofline): CUDA events around every launch group
+  int profiling = 0;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  uint8_t tc_attr_set[4] = {0, 0, 0, 0};
+};
+
+enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };
+
+// RAII: when ctx->profiling is on, brackets the launches issued in its scope with two events on the ctx stream.
+struct MpnProfScope {
+  mpn_ctx *ctx; int idx = -1;
+  MpnProfScope(mpn_ctx *c, int cat) : ctx(c) {
+    if (!c->profiling) return;
+    auto get = [&]() { cudaEvent_t e; if (c->ev_pool.empty()) cudaEventCreate(&e); else { e = c->ev_pool.back(); c->ev_pool.pop_back(); } return e; };
+    mpn_ctx::ProfRec r{cat, get(), get()};
+    cudaEventRecord(r.a, c->stream);
+    c->prof.push_back(r); idx = (int)c->prof.size() - 1;
+  }
+  ~MpnProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream); }
 };
 
 #define MPN_OK 0

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const RefParams p) {
 
 int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
                             const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu, DTensor &y) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_DIRECT);
   MPN_CHECK_ARG(ctx, Cout % 8 == 0, "conv_direct: Cout must be a multiple of 8");
   const long long pixels = (long long)N * y.H * y.W;
   if (pixels <= 0) return MPN_OK;
@@ -119,6 +120,7 @@ int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, i
 }
 
 int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_TC);
   RefParams r;
   r.xh = p.x.hi; r.xl = p.x.lo; r.xld = p.x.ld; r.N = (int)p.x.N; r.H = (int)p.x.H; r.W = (int)p.x.W; r.Cin = (int)p.x.C;
   r.wh = p.w_hi; r.wl = p.w_lo; r.bias = p.bias; r.Cout = p.Cout; r.kh = p.kh; r.kw = p.kw; r.stride = p.stride;

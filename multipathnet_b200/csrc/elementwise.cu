@@ -287,6 +287,7 @@ int mpn_context_region_launch(mpn_ctx *ctx, const float *rois_dev, int64_t R, fl
   return MPN_OK;
 }
 int mpn_bbox_norm_launch(mpn_ctx *ctx, float *d_dev, int64_t R, int64_t C4, const float *mean4, const float *std4) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   int64_t n4 = R * C4 / 4;
   if (n4 <= 0) return MPN_OK;
   bbox_norm_kernel<<<nblk(n4, 256), 256, 0, ctx->stream>>>(
@@ -296,6 +297,7 @@ int mpn_bbox_norm_launch(mpn_ctx *ctx, float *d_dev, int64_t R, int64_t C4, cons
 }
 int mpn_bbox_decode_launch(mpn_ctx *ctx, const float *deltas_dev, const float *boxes_dev, int64_t R, int C,
                            int do_clamp, float W0, float H0, float *out_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R * C <= 0) return MPN_OK;
   bbox_decode_kernel<<<nblk(R * C, 256), 256, 0, ctx->stream>>>(deltas_dev, boxes_dev, R, C, do_clamp, W0, H0, out_dev);
   MPN_LAUNCHED(ctx);
@@ -303,6 +305,7 @@ int mpn_bbox_decode_launch(mpn_ctx *ctx, const float *deltas_dev, const float *b
 }
 int mpn_softmax_mean_launch(mpn_ctx *ctx, const float *logits_dev, int64_t R, int C, int K, int do_softmax,
                             float *out_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R <= 0) return MPN_OK;
   softmax_mean_kernel<<<nblk(R * 32, 256), 256, 0, ctx->stream>>>(logits_dev, R, C, K, do_softmax, out_dev);
   MPN_LAUNCHED(ctx);
@@ -310,12 +313,14 @@ int mpn_softmax_mean_launch(mpn_ctx *ctx, const float *logits_dev, int64_t R, in
 }
 int mpn_gather_scored_launch(mpn_ctx *ctx, const float *scores_dev, const float *bboxes_dev, int R, int C,
                              float thresh, float *sb_dev, int32_t *src_idx_dev, int32_t *counts_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (C <= 1 || R <= 0) return MPN_OK;
   gather_scored_kernel<<<C - 1, 256, 0, ctx->stream>>>(scores_dev, bboxes_dev, R, C, thresh, sb_dev, src_idx_dev, counts_dev);
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
 int mpn_maxpool_launch(mpn_ctx *ctx, const DTensor &in, int k, int s, int p, DTensor &out) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_POOL);
   int64_t total = out.N * out.H * out.W * (out.C / 8);
   if (total <= 0) return MPN_OK;
   maxpool_split_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(in.hi, in.lo, (int)in.N, (int)in.H, (int)in.W, (int)in.C,
@@ -324,6 +329,7 @@ int mpn_maxpool_launch(mpn_ctx *ctx, const DTensor &in, int k, int s, int p, DTe
   return MPN_OK;
 }
 int mpn_avgpool_launch(mpn_ctx *ctx, const DTensor &in, DTensor &out) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   int64_t total = in.N * in.C;
   if (total <= 0) return MPN_OK;
   avgpool_split_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(in.hi, in.lo, (int)in.N, (int)(in.H * in.W), (int)in.C,
@@ -355,6 +361,7 @@ int mpn_nhwc_split_to_nchw_launch(mpn_ctx *ctx, const DTensor &in, float *out_de
 }
 
 int mpn_project_rois_launch(mpn_ctx *ctx, const float *boxes_dev, int64_t R, float im_scale, float *rois_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R <= 0) return MPN_OK;
   project_rois_kernel<<<nblk(R, 128), 128, 0, ctx->stream>>>(boxes_dev, R, im_scale, rois_dev);
   MPN_LAUNCHED(ctx);

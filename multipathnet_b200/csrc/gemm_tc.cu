@@ -361,10 +361,10 @@ int encode_map(mpn_ctx *ctx, CUtensorMap *tm, const void *base, int rank, const 
 template <int BN>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   const int smem = num_stages(BN) * stage_bytes(BN) + 1024 /*align*/ + 256 /*barriers*/;
-  static bool attr_done = false;
-  if (!attr_done) {
+  constexpr int slot = BN == 256 ? 2 : (BN == 128 ? 1 : 0);
+  if (!ctx->tc_attr_set[slot]) {     // per ctx (= per device): the attribute is per device function
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
+    ctx->tc_attr_set[slot] = 1;
   }
   const int total = pl.tiles_img * pl.tiles_h * pl.tiles_w * pl.tiles_n;
   const int grid = std::min(total, ctx->sm_count);
@@ -430,6 +430,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
 }
 
 int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_TC);
   MPN_CHECK_ARG(ctx, pl.valid, "conv_tc_launch: invalid plan");
   TcParams tp;
   if (pl.flat) { tp.N = 1; tp.Ho = 1; tp.Wo = (int)(p.y.N * p.y.H * p.y.W); }

@@ -259,6 +259,7 @@ nms_exact_kernel(const float *__restrict__ sb, int cap, const int32_t *__restric
 int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const int32_t *counts_dev,
                    const int32_t *src_idx_dev, float thr, int32_t *keep_idx_dev,
                    int32_t *keep_counts_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_NMS);
   if (nseg <= 0 || cap <= 0) return MPN_OK;
   const int nwords = (cap + 63) / 64;
   size_t off = 0;
