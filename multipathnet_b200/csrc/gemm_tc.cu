@@ -387,8 +387,6 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
   MPN_CHECK_ARG(ctx, p.x.ld % 8 == 0, "conv_tc: input pixel stride must be a multiple of 8 elements");
   MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
   const int Ho = (int)p.y.H, Wo = (int)p.y.W, N = (int)p.y.N;
-  pl.BN = p.Cout >= 256 ? 256 : (p.Cout >= 128 ? 128 : 64);
-  pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
   pl.flat = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0) ? 1 : 0;
   cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];
   if (pl.flat) {
@@ -417,6 +415,22 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     strides[2] = (cuuint64_t)p.x.H * p.x.W * p.x.ld * 2;
     box[0] = BK; box[1] = (cuuint32_t)(btw * p.stride); box[2] = (cuuint32_t)(bth * p.stride); box[3] = (cuuint32_t)btn;
     estr[0] = 1; estr[1] = (cuuint32_t)p.stride; estr[2] = (cuuint32_t)p.stride; estr[3] = 1;
+  }
+  // N tile: the widest BN that still fills the machine. Cost model per K block and scheduling round:
+  // (BN + 64) ~ operand bytes landing in the SM (A is 128 rows regardless), rounds = ceil(tiles / SMs).
+  // e.g. VGG conv5 (19 m-tiles): BN=256 -> 38 CTAs, BN=128 -> 76 CTAs at 0.6x the per-tile time.
+  {
+    const long long tiles_m = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
+    double best = 1e300; int best_bn = 64;
+    for (int bn = 256; bn >= 64; bn >>= 1) {
+      if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;     // do not pad N by more than one 64-block
+      const long long tn_ = (p.Cout + bn - 1) / bn;
+      const long long rounds = (tiles_m * tn_ + ctx->sm_count - 1) / ctx->sm_count;
+      const double cost = (double)rounds * (bn + 64);
+      if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+    }
+    pl.BN = best_bn;
+    pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
   }
   MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
   MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));

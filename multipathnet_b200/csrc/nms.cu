@@ -81,11 +81,11 @@ nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict
 // mask[seg][row][cb] bit c set iff col j=cb*64+c > row i and !(iou(i,j) <= thr)  (nms.c:93 keeps <=).
 __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4 *__restrict__ sorted_boxes, int cap, int nwords_cap,
-                const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag, float thr,
-                unsigned long long *__restrict__ mask) {
+                const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag, int skip_tied,
+                float thr, unsigned long long *__restrict__ mask) {
   const int seg = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;
-  if (tie_flag[seg]) return;                    // exact-emulation path handles this segment
+  if (skip_tied && tie_flag[seg]) return;       // large-N path: nms_exact_kernel handles tied segments
   const int n = counts ? counts[seg] : cap;
   if (rb * 64 >= n || cb * 64 >= n) return;
   const float4 *boxes = sorted_boxes + (size_t)seg * cap;
@@ -164,6 +164,100 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
     __syncthreads();
   }
   if (threadIdx.x == 0) keep_counts[seg] = nkeep;
+}
+
+// ---- small segments (n <= 1024): the whole suppression mask lives in shared memory and ONE warp walks the
+// greedy selection round by round (no block barriers on the serial chain: ~100 cycles per kept box).
+// Tied scores are resolved exactly like nms.c WITHOUT re-running its O(N) pointer walk per round:
+//   nms.c's array order only ever changes by "the element in the first live slot moves into the slot of the
+//   selected box" (the swap at nms.c:83-86; the survivor compaction at :90-99 is order preserving).
+//   So each element carries a slot label (initially its row index), the head is the live element with the
+//   smallest label (a monotone pointer finds it), and "first strict maximum in current order" (nms.c:74-81)
+//   = among the live boxes sharing the top score, the one with the smallest label.
+constexpr int SMALL_CAP = 1024;
+constexpr int SMALL_THREADS = 256;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
+                      const float *__restrict__ sb, int cap, int nwords_cap, const int32_t *__restrict__ counts,
+                      const int32_t *__restrict__ tie_flag, const int32_t *__restrict__ src_idx,
+                      int32_t *__restrict__ keep_idx, int32_t *__restrict__ keep_counts) {
+  extern __shared__ unsigned long long s_mask[];      // n x nwords
+  __shared__ float s_score[SMALL_CAP];
+  __shared__ int s_label[SMALL_CAP], s_owner[SMALL_CAP];
+  __shared__ unsigned long long s_removed[SMALL_CAP / 64];
+  __shared__ short s_keep[SMALL_CAP];                 // kept sorted positions, resolved to row indices after the walk
+  const int seg = blockIdx.x;
+  const int n = counts ? counts[seg] : cap;
+  if (n <= 0) { if (threadIdx.x == 0) keep_counts[seg] = 0; return; }
+  const int nwords = (n + 63) >> 6;
+  const bool tie = tie_flag[seg] != 0;
+  const unsigned long long *m = mask + (size_t)seg * cap * nwords_cap;
+  const int32_t *ord = order + (size_t)seg * cap;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n * nwords; i += SMALL_THREADS) {
+    const int r = i / nwords, w = i - r * nwords;
+    s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;     // only the upper triangle was computed
+  }
+  if (tie) {
+    const float *seg_sb = sb + (size_t)seg * cap * 5;
+    for (int p = threadIdx.x; p < n; p += SMALL_THREADS) {
+      const int o = ord[p];
+      s_score[p] = seg_sb[(size_t)o * 5 + 4];
+      s_label[p] = o;            // slot label = position in the reference's pointer array
+      s_owner[o] = p;            // slot -> sorted position of its occupant
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned long long rem = ~0ull;                       // lanes >= nwords: nothing alive
+  if (lane < nwords) rem = (lane == nwords - 1 && (n & 63)) ? (~0ull << (n & 63)) : 0ull;
+  if (lane < SMALL_CAP / 64) s_removed[lane] = rem;
+  __syncwarp();
+  auto alive_s = [&](int e) { return !((s_removed[e >> 6] >> (e & 63)) & 1ull); };
+  int nkeep = 0, hp = 0;
+  while (true) {
+    const unsigned long long alive = ~rem;
+    const unsigned ball = __ballot_sync(0xffffffffu, alive != 0ull);
+    if (!ball) break;
+    const int wl = __ffs(ball) - 1;
+    const unsigned long long aw = __shfl_sync(0xffffffffu, alive, wl);
+    const int q = wl * 64 + __ffsll((long long)aw) - 1;       // first live box in (score desc, row asc) order
+    int pb = q;
+    if (tie) {
+      if (lane == 0) {
+        const float s = s_score[q]; int bl = s_label[q];
+        for (int r = q + 1; r < n && s_score[r] == s; ++r)
+          if (alive_s(r) && s_label[r] < bl) { pb = r; bl = s_label[r]; }
+        while (hp < n - 1) { const int e = s_owner[hp]; if (e >= 0 && alive_s(e)) break; ++hp; }
+        const int head = s_owner[hp];
+        if (head != pb) { s_owner[bl] = head; s_label[head] = bl; }      // head takes the selected box's slot
+        s_owner[hp] = -1;                                                // the first slot is vacated either way
+      }
+      pb = __shfl_sync(0xffffffffu, pb, 0);
+    }
+    if (lane == 0) s_keep[nkeep] = (short)pb;        // no global access on the serial chain
+    ++nkeep;
+    const int wb = pb >> 6;
+    if (lane < nwords) {
+      if (lane >= wb) rem |= s_mask[pb * nwords + lane];
+      if (lane == wb) rem |= 1ull << (pb & 63);
+    }
+    if (tie) {
+      // live boxes of the same score that precede pb in sorted order: suppression is symmetric (IoU is), bit [e][pb]
+      for (int e = q; e < pb; ++e)
+        if (((s_mask[e * nwords + wb] >> (pb & 63)) & 1ull) && lane == (e >> 6)) rem |= 1ull << (e & 63);
+      if (lane < SMALL_CAP / 64) s_removed[lane] = rem;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  for (int k = lane; k < nkeep; k += 32) {
+    const int o = ord[s_keep[k]];
+    keep_idx[(size_t)seg * cap + k] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
+  }
+  if (lane == 0) keep_counts[seg] = nkeep;
 }
 
 constexpr int EXACT_THREADS = 512;
@@ -282,8 +376,18 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
-  nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, thr, mask);
+  const bool small = cap <= SMALL_CAP;
+  nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, small ? 0 : 1, thr, mask);
   MPN_LAUNCHED(ctx);
+  if (small) {
+    const size_t smem = sizeof(unsigned long long) * (size_t)cap * nwords;
+    if (smem > 48 * 1024)
+      MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_small_kernel<<<nseg, SMALL_THREADS, smem, ctx->stream>>>(mask, order, sb_dev, cap, nwords, counts_dev, tie,
+                                                                     src_idx_dev, keep_idx_dev, keep_counts_dev);
+    MPN_LAUNCHED(ctx);
+    return MPN_OK;
+  }
   nms_scan_kernel<<<nseg, SCAN_THREADS, sizeof(unsigned long long) * nwords, ctx->stream>>>(
       mask, order, cap, nwords, counts_dev, tie, src_idx_dev, keep_idx_dev, keep_counts_dev);
   MPN_LAUNCHED(ctx);

@@ -147,3 +147,21 @@ def test_vgg16_full_size_cfg2(ctx):
     tf, hf = m.last_flops()
     assert abs(tf / 1e9 - 294.0) < 0.1 and abs(hf / 1e9 - 239.9) < 0.2
     m.close()
+
+
+def test_resnet50_integral_small(ctx):
+    """cfg 4 structure (resnet.lua:28-50 + model_utils.integral): 7x7/2 conv, 3x3/2 pool, bottlenecks with stride-2
+    3x3 + 1x1 shortcut convs and fused residual adds, ROIPooling 14x14, per-ROI layer4 + avgpool, K=3 softmax-mean head."""
+    spec = models.resnet50_fast_rcnn(21, seed=5, integral_k=3)
+    m = mpn.Model(ctx, spec, max_rois=128, max_h=256, max_w=320)
+    img, boxes = _inputs(spec, 160, 224, 48, 8, sharp=True)
+    rois = O.project_rois(boxes, 1.0)
+    m.trunk(img)
+    ts = G.trunk_forward(spec, img)
+    slot = spec.taps["layer3"]
+    assert rel_err(m.trunk_slot(slot), ts[slot].numpy()) < 3e-4
+    s, b = m.detect(img, boxes, 1.0)
+    rs, rb = G.detect(spec, img, boxes, 1.0)
+    assert rel_err(s, rs) < TOL and rel_err(b, rb) < TOL
+    np.testing.assert_allclose(s.sum(1), 1.0, atol=1e-5)
+    m.close()

@@ -114,3 +114,16 @@ def test_bbox_vote_bit_exact(ctx):
     assert np.array_equal(got, O.bbox_vote(rows, sb, 0.5))
     if O.ref_available():
         assert np.array_equal(got, O.ref_bbox_vote(rows, sb, 0.5))
+
+
+def test_nms_sweep_50k_single_class(ctx):
+    """cfg 5 upper end: 50k boxes in one segment (mask 50k x 782 words = 312 MB)"""
+    sb = wl.nms_sweep_boxes(50000, 1, 5 + 50000)[0]
+    assert np.array_equal(ctx.nms(sb, 0.3), O.nms(sb, 0.3))
+
+
+def test_nms_sweep_10k_x_80(ctx):
+    allsb = wl.nms_sweep_boxes(10000, 80, 5 + 10000)
+    keeps = ctx.nms_batched(allsb.reshape(-1, 5), np.arange(81) * 10000, 0.3)
+    for c in (0, 17, 79):
+        assert np.array_equal(keeps[c], O.nms(allsb[c], 0.3))
