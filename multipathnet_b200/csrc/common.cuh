@@ -24,7 +24,7 @@ struct mpn_ctx {
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
-  uint8_t tc_attr_set[4] = {0, 0, 0, 0};
+  uint8_t tc_attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };

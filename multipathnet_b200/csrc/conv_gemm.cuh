@@ -21,6 +21,7 @@ struct ConvProblem {
 struct ConvPlan {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   int BN = 0;                      // 64 / 128 / 256
+  int CG = 1;                      // CTAs per MMA (tcgen05 cta_group): 2 = CTA pair sharing the B tile
   int tn = 0, th = 0, tw = 0;      // 128 output pixels per M tile = tn*th*tw
   int tiles_img = 0, tiles_h = 0, tiles_w = 0, tiles_n = 0;
   int flat = 0;                    // 1: 1x1/s1/p0 => pixels treated as one flat axis
@@ -33,5 +34,5 @@ int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p);           // CUDA-core 
 // first-layer direct conv: x is NCHW fp32 (N x Cin x H x W), w fp32 [Cout][Cin][kh][kw] (Torch layout)
 int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
                             const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu,
-                            DTensor &y);
+                            DTensor &y, const float *w_host = nullptr, const float *bias_host = nullptr);
 double conv_flops(const ConvProblem &p);

@@ -136,6 +136,54 @@ conv_direct_3x3c3_kernel(const float *__restrict__ x, int N, int H, int W, const
   }
 }
 
+// VGG conv1_1, second specialisation (Cout = 64): the whole 64 x 27 filter bank + bias travels as a __grid_constant__
+// kernel parameter (7 KB, constant bank), so every FMA takes its weight as an immediate constant operand: no LDS at
+// all (the smem-broadcast version is LSU-bound at ~110 us; this one is FMA-bound). One thread = one pixel x 64 channels.
+struct Conv1Params { float w[64 * 27]; float b[64]; };
+
+__global__ void __launch_bounds__(128)
+conv_direct_3x3c3_o64_kernel(const float *__restrict__ x, int N, int H, int W, const __grid_constant__ Conv1Params cp,
+                             int relu, __nv_bfloat16 *__restrict__ oh, __nv_bfloat16 *__restrict__ ol, long long ld) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= (long long)N * H * W) return;
+  const int wo = (int)(pix % W), ho = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+  const float *xn = x + (size_t)n * 3 * H * W;
+  float in[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hi = ho + r - 1;
+      const bool hok = (hi >= 0) && (hi < H);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int wi = wo + q - 1;
+        const bool ok = hok && (wi >= 0) && (wi < W);
+        in[(ci * 3 + r) * 3 + q] = ok ? __ldg(xn + ((size_t)ci * H + hi) * W + wi) : 0.f;
+      }
+    }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {                       // 8 output channels at a time -> one 16-byte store per plane
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = cp.b[g * 8 + e];
+#pragma unroll
+      for (int k = 0; k < 27; ++k) a = fmaf(in[k], cp.w[(g * 8 + e) * 27 + k], a);
+      f[e] = relu ? fmaxf(a, 0.f) : a;
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(f[2 * t], h0, l0); split_bf16(f[2 * t + 1], h1, l1);
+      ph[t] = pack_bf16x2(h0, h1); pl[t] = pack_bf16x2(l0, l1);
+    }
+    *reinterpret_cast<uint4 *>(oh + pix * ld + g * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4 *>(ol + pix * ld + g * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
 struct RefParams {
   const __nv_bfloat16 *xh, *xl; long long xld; int N, H, W, Cin;
   const __nv_bfloat16 *wh, *wl;
@@ -178,7 +226,8 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const RefParams p) {
 }  // namespace
 
 int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
-                            const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu, DTensor &y) {
+                            const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu, DTensor &y,
+                            const float *w_host, const float *bias_host) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_DIRECT);
   MPN_CHECK_ARG(ctx, Cout % 8 == 0, "conv_direct: Cout must be a multiple of 8");
   const long long pixels = (long long)N * y.H * y.W;
@@ -186,6 +235,14 @@ int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, i
   const size_t smem = sizeof(float) * DC_CO * Cin * kh * kw;
   MPN_CHECK_ARG(ctx, smem <= 48 * 1024, "conv_direct: filter too large");
   dim3 grid((unsigned)((pixels + 255) / 256), (unsigned)((Cout + DC_CO - 1) / DC_CO));
+  if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout == 64 && w_host && y.ld % 8 == 0) {
+    Conv1Params cp;
+    memcpy(cp.w, w_host, sizeof(cp.w));
+    if (bias_host) memcpy(cp.b, bias_host, sizeof(cp.b)); else memset(cp.b, 0, sizeof(cp.b));
+    conv_direct_3x3c3_o64_kernel<<<(unsigned)((pixels + 127) / 128), 128, 0, ctx->stream>>>(x_nchw, N, H, W, cp, relu, y.hi, y.lo, y.ld);
+    MPN_LAUNCHED(ctx);
+    return MPN_OK;
+  }
   if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1) {
     conv_direct_3x3c3_kernel<<<grid, 256, 0, ctx->stream>>>(x_nchw, N, H, W, w, bias, Cout, relu, y.hi, y.lo, y.ld);
     MPN_LAUNCHED(ctx);

@@ -25,6 +25,7 @@
 // tmem_full/tmem_empty per accumulator buffer).
 #include "conv_gemm.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace {
 
@@ -34,8 +35,12 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;  // 6 warps
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB per plane
 
-__host__ __device__ constexpr int stage_bytes(int BN) { return 2 * A_TILE_BYTES + 2 * BN * BK * 2; }
-__host__ __device__ constexpr int num_stages(int BN) { return BN == 256 ? 2 : (BN == 128 ? 3 : 4); }
+// CG = CTAs per MMA (tcgen05 cta_group): with CG=2 a CTA pair shares one B tile (each CTA stages BN/2 rows),
+// which cuts the operand bytes landing in each SM per MMA cycle from (128+BN) to (128+BN/2) rows x 128 B.
+__host__ __device__ constexpr int stage_bytes(int BN, int CG = 1) { return 2 * A_TILE_BYTES + 2 * (BN / CG) * BK * 2; }
+__host__ __device__ constexpr int num_stages(int BN, int CG = 1) {
+  return (196608 / stage_bytes(BN, CG)) > 4 ? 4 : (196608 / stage_bytes(BN, CG));
+}
 __host__ __device__ constexpr int tmem_cols(int BN) { return BN == 256 ? 512 : (BN == 128 ? 256 : 128); }
 
 struct TcParams {
@@ -91,6 +96,50 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// --- cta_group::2 variants: both CTAs of the pair load into their own smem, completion lands on the LEADER's barrier
+// (its shared::cluster address, obtained with mapa for CTA rank 0)
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local_addr) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(0u));
+  return ra;
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -140,15 +189,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const TcParams p) {
-  constexpr int S = num_stages(BN);
-  constexpr int STAGE = stage_bytes(BN);
-  constexpr int B_TILE_BYTES = BN * BK * 2;
-  constexpr uint32_t IDESC = make_idesc(BM, BN);
+  constexpr int S = num_stages(BN, CG);
+  constexpr int STAGE = stage_bytes(BN, CG);
+  constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;            // this CTA's share of the B tile
+  constexpr uint32_t IDESC = make_idesc(BM * CG, BN);         // cta_group::2: one 256 x BN MMA over the pair
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for SWIZZLE_128B tiles
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -163,23 +212,37 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CG=2: the grid is made of CTA pairs (cluster 2x1x1). Pair `unit` walks the schedule; CTA `rank` of the pair owns
+  // m-tile 2*mp+rank and rows [rank*BN/2, (rank+1)*BN/2) of the B tile; rank 0 (leader) issues the MMAs for both.
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tiles_m = p.tiles_img * p.tiles_h * p.tiles_w;
-  const int total_tiles = tiles_m * p.tiles_n;
+  const int tiles_mu = (tiles_m + CG - 1) / CG;               // m-tiles per scheduling unit
+  const int total_tiles = tiles_mu * p.tiles_n;
   const int num_kb = p.kh * p.kw * p.cblocks;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    // full: one arrival per producing CTA (on the leader's barrier when CG=2); tempty: one per epilogue warp of the pair
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {   // TMEM allocation is warp-collective (same warp id in both CTAs for CG=2); the same warp frees it
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // barrier inits must be visible to the peer before any remote arrive / multicast
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -187,28 +250,39 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;   // mt >= tiles_m => fully OOB => zeros
         const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
         const int w_in0 = twi * p.tw * p.stride - p.pad, h_in0 = thi * p.th * p.stride - p.pad, n0 = tni * p.tn;
+        const int b_row0 = nt * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % S; const uint32_t ph = (it / S) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           const int khi = tap / p.kw, kwi = tap - khi * p.kw;
           const uint32_t sa = smem_base + (uint32_t)s * STAGE;
-          mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
-          tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-          tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-          tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, nt * BN);
-          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, nt * BN);
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(full_bar(s), (uint32_t)(2 * STAGE));      // bytes of BOTH CTAs land on the leader's barrier
+            else mbar_arrive_remote(full_bar(s), 0u);
+            const uint32_t lbar = leader_addr(full_bar(s));
+            tma_load_4d_2sm(sa, &tmA_hi, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+            tma_load_4d_2sm(sa + A_TILE_BYTES, &tmA_lo, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES, &tmB_hi, lbar, kb * BK, b_row0);
+            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, lbar, kb * BK, b_row0);
+          } else {
+            mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
+            tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+            tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+            tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, b_row0);
+            tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, b_row0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (leader CTA only when CG=2) =====================
     uint32_t it = 0, lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = unit; rank == 0 && tile < total_tiles; tile += num_units, ++lt) {
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       mbar_wait(tempty_bar(a), aph ^ 1u);        // epilogue has drained this accumulator
       tc_fence_after();
@@ -225,12 +299,23 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
-            tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
-            tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-            tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            if (CG == 2) {
+              tc_mma_bf16_2sm(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+              tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            } else {
+              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+              tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            }
           }
-          tc_commit(empty_bar(s));                 // stage reusable once these MMAs retire
-          if (kb == num_kb - 1) tc_commit(tfull_bar(a));   // accumulator complete
+          if (CG == 2) {                             // multicast: frees the stage / publishes the accumulator in BOTH CTAs
+            tc_commit_2sm(empty_bar(s));
+            if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(a));
+          } else {
+            tc_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+            if (kb == num_kb - 1) tc_commit(tfull_bar(a));   // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -241,9 +326,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int row = q * 32 + lane;               // accumulator row = pixel within the tile
     const int wl = row & (p.tw - 1), hl = (row / p.tw) & (p.th - 1), nl = row / (p.tw * p.th);
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++lt) {
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
-      const int nt = tile % p.tiles_n, mt = tile / p.tiles_n;
+      const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
       const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
       const int wo = twi * p.tw + wl, ho = thi * p.th + hl, n = tni * p.tn + nl;
       const bool row_ok = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
@@ -314,16 +399,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(a));   // 4 arrivals (one per epilogue warp) free the buffer
+      if (lane == 0) {                             // 4*CG arrivals (one per epilogue warp of the pair) free the buffer
+        if (CG == 2 && rank != 0) mbar_arrive_remote(tempty_bar(a), 0u);   // the MMA issuer waits on the leader's barrier
+        else mbar_arrive(tempty_bar(a));
+      }
     }
   }
 
-  // ---- teardown: everyone done with TMEM before the allocating warp frees it
+  // ---- teardown: everyone (both CTAs) done with TMEM / peer smem / peer barriers before anything is freed
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
   }
 }
 
@@ -358,17 +449,24 @@ int encode_map(mpn_ctx *ctx, CUtensorMap *tm, const void *base, int rank, const 
   return MPN_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
-  const int smem = num_stages(BN) * stage_bytes(BN) + 1024 /*align*/ + 256 /*barriers*/;
-  constexpr int slot = BN == 256 ? 2 : (BN == 128 ? 1 : 0);
+  const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int slot = (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1);
   if (!ctx->tc_attr_set[slot]) {     // per ctx (= per device): the attribute is per device function
-    MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->tc_attr_set[slot] = 1;
   }
-  const int total = pl.tiles_img * pl.tiles_h * pl.tiles_w * pl.tiles_n;
-  const int grid = std::min(total, ctx->sm_count);
-  conv_gemm_tc_kernel<BN><<<grid, TC_THREADS, smem, ctx->stream>>>(pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp);
+  const int tiles_m = pl.tiles_img * pl.tiles_h * pl.tiles_w;
+  const int units = ((tiles_m + CG - 1) / CG) * pl.tiles_n;
+  const int grid = std::min(units, ctx->sm_count / CG) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = (CG > 1) ? 1 : 0;
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -416,27 +514,35 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     box[0] = BK; box[1] = (cuuint32_t)(btw * p.stride); box[2] = (cuuint32_t)(bth * p.stride); box[3] = (cuuint32_t)btn;
     estr[0] = 1; estr[1] = (cuuint32_t)p.stride; estr[2] = (cuuint32_t)p.stride; estr[3] = 1;
   }
-  // N tile: the widest BN that still fills the machine. Cost model per K block and scheduling round:
-  // (BN + 64) ~ operand bytes landing in the SM (A is 128 rows regardless), rounds = ceil(tiles / SMs).
-  // e.g. VGG conv5 (19 m-tiles): BN=256 -> 38 CTAs, BN=128 -> 76 CTAs at 0.6x the per-tile time.
+  // (CG, BN): cost model per K block and scheduling round = operand rows landing in each SM: 128 (A) + BN/CG (B);
+  // rounds = ceil(units / (SMs / CG)). The engine is operand-ingest-bound (~35 B/cycle/SM measured), so CTA pairs
+  // (tcgen05 cta_group::2, B tile split across the pair) win whenever there are >= 2 m-tiles.
+  // e.g. VGG conv5 (19 m-tiles): 1-CTA BN=256 -> 38 CTAs; pair BN=128 -> 40 pairs = 80 CTAs at 2/3 of the bytes.
   {
     const long long tiles_m = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
-    double best = 1e300; int best_bn = 64;
-    for (int bn = 256; bn >= 64; bn >>= 1) {
-      if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;     // do not pad N by more than one 64-block
-      const long long tn_ = (p.Cout + bn - 1) / bn;
-      const long long rounds = (tiles_m * tn_ + ctx->sm_count - 1) / ctx->sm_count;
-      const double cost = (double)rounds * (bn + 64);
-      if (cost < best - 1e-9) { best = cost; best_bn = bn; }
+    const char *env = getenv("MPN_TC_CTA_GROUP");                 // debug knob: "1" forces the single-CTA engine
+    const int max_cg = (env && env[0] == '1') ? 1 : 2;
+    double best = 1e300; int best_bn = 64, best_cg = 1;
+    for (int cg = 1; cg <= max_cg; ++cg) {
+      if (cg == 2 && tiles_m < 2) continue;
+      for (int bn = 256; bn >= 64; bn >>= 1) {
+        if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
+        const long long tn_ = (p.Cout + bn - 1) / bn;
+        const long long units = ((tiles_m + cg - 1) / cg) * tn_;
+        const long long slots = ctx->sm_count / cg;
+        const long long rounds = (units + slots - 1) / slots;
+        const double cost = (double)rounds * (128 + bn / cg);
+        if (cost < best - 1e-9) { best = cost; best_bn = bn; best_cg = cg; }
+      }
     }
-    pl.BN = best_bn;
+    pl.BN = best_bn; pl.CG = best_cg;
     pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
   }
   MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
   MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));
   const long long Ktot = (long long)p.kh * p.kw * p.x.C;
   cuuint64_t bd[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout}, bs[1] = {(cuuint64_t)Ktot * 2};
-  cuuint32_t bb[2] = {BK, (cuuint32_t)pl.BN}, be[2] = {1, 1};
+  cuuint32_t bb[2] = {BK, (cuuint32_t)(pl.BN / pl.CG)}, be[2] = {1, 1};   // each CTA of a pair stages BN/CG weight rows
   MPN_TRY(encode_map(ctx, &pl.tmB_hi, p.w_hi, 2, bd, bs, bb, be));
   MPN_TRY(encode_map(ctx, &pl.tmB_lo, p.w_lo, 2, bd, bs, bb, be));
   pl.valid = 1;
@@ -459,9 +565,16 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.out_f32 = p.y.f32; tp.out_f32_ld = p.y_f32_ld;
   tp.relu = p.relu;
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
+  if (pl.CG == 2) {
+    switch (pl.BN) {
+      case 256: return launch_bn<256, 2>(ctx, pl, tp);
+      case 128: return launch_bn<128, 2>(ctx, pl, tp);
+      default: return launch_bn<64, 2>(ctx, pl, tp);
+    }
+  }
   switch (pl.BN) {
-    case 256: return launch_bn<256>(ctx, pl, tp);
-    case 128: return launch_bn<128>(ctx, pl, tp);
-    default: return launch_bn<64>(ctx, pl, tp);
+    case 256: return launch_bn<256, 1>(ctx, pl, tp);
+    case 128: return launch_bn<128, 1>(ctx, pl, tp);
+    default: return launch_bn<64, 1>(ctx, pl, tp);
   }
 }

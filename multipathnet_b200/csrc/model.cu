@@ -77,6 +77,7 @@ struct mpn_model {
   std::vector<mpn_head> cls_heads;
   std::vector<std::unique_ptr<WeightDev>> weights;
   std::vector<int64_t> w_elems;
+  std::vector<std::vector<float>> w_host_small;   // host copies of small arrays (first-layer filter bank / bias travel as kernel parameters)
   std::vector<int> w_prepared;     // 0 = raw only, 1 = split prepared with (Cin,kh,kw) below
   int conv_impl = 0;
 
@@ -224,7 +225,9 @@ int run_trunk(mpn_model *m, const float *image_dev) {
         const float *bias = L.bias >= 0 ? (const float *)m->weights[L.bias]->f32.p : nullptr;
         MPN_TRY(conv_direct_nchw_launch(ctx, image_dev, 1, L.cin, (int)e.in.H, (int)e.in.W,
                                         (const float *)m->weights[L.weight]->f32.p, bias, L.cout, L.kh, L.kw, L.stride,
-                                        L.pad, L.relu, e.out));
+                                        L.pad, L.relu, e.out,
+                                        m->w_host_small[L.weight].empty() ? nullptr : m->w_host_small[L.weight].data(),
+                                        (L.bias >= 0 && !m->w_host_small[L.bias].empty()) ? m->w_host_small[L.bias].data() : nullptr));
       } else {
         MPN_TRY(run_conv(m, e));
       }
@@ -444,7 +447,9 @@ int mpn_model_create(mpn_ctx *ctx, const mpn_model_desc *desc, const float *cons
     }
   }
   m->weights.resize(n_weights); m->w_elems.assign(n_elem, n_elem + n_weights); m->w_prepared.assign(n_weights, 0);
+  m->w_host_small.resize(n_weights);
   for (int i = 0; i < n_weights; ++i) {
+    if (n_elem[i] <= 4096) m->w_host_small[i].assign(weights[i], weights[i] + n_elem[i]);
     m->weights[i].reset(new WeightDev());
     int r = upload_weight_raw(m, i, weights[i], n_elem[i]);
     if (r != MPN_OK) { delete m; return r; }

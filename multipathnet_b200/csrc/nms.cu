@@ -226,16 +226,45 @@ nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int32_t
     const int q = wl * 64 + __ffsll((long long)aw) - 1;       // first live box in (score desc, row asc) order
     int pb = q;
     if (tie) {
-      if (lane == 0) {
-        const float s = s_score[q]; int bl = s_label[q];
-        for (int r = q + 1; r < n && s_score[r] == s; ++r)
-          if (alive_s(r) && s_label[r] < bl) { pb = r; bl = s_label[r]; }
-        while (hp < n - 1) { const int e = s_owner[hp]; if (e >= 0 && alive_s(e)) break; ++hp; }
-        const int head = s_owner[hp];
-        if (head != pb) { s_owner[bl] = head; s_label[head] = bl; }      // head takes the selected box's slot
-        s_owner[hp] = -1;                                                // the first slot is vacated either way
+      // (a) other live boxes with the same score as q? (they are contiguous after q in sorted order). Warp-parallel
+      //     probe of the next 32 positions; the rare hit falls back to a serial walk by lane 0.
+      const float sq = s_score[q];
+      int bl = s_label[q];
+      {
+        const int r = q + 1 + lane;
+        const bool eq = (r < n) && (s_score[r] == sq);
+        const bool hit = eq && alive_s(r);
+        // walk serially if a live tied box is in the window, or the tie group runs past the 32-position window
+        if (__ballot_sync(0xffffffffu, hit) || __ballot_sync(0xffffffffu, eq) == 0xffffffffu) {
+          if (lane == 0)
+            for (int rr = q + 1; rr < n && s_score[rr] == sq; ++rr)
+              if (alive_s(rr) && s_label[rr] < bl) { pb = rr; bl = s_label[rr]; }
+          pb = __shfl_sync(0xffffffffu, pb, 0);
+          bl = __shfl_sync(0xffffffffu, bl, 0);
+        }
       }
-      pb = __shfl_sync(0xffffffffu, pb, 0);
+      // (b) head = live occupant of the first live slot: warp-parallel scan, 32 slots per step, monotone pointer
+      int head = -1;
+      while (true) {
+        const int sl = hp + lane;
+        const int e = (sl < n) ? s_owner[sl] : -1;
+        const bool ok = (e >= 0) && alive_s(e);
+        const unsigned hb = __ballot_sync(0xffffffffu, ok);
+        if (hb) {
+          const int first = __ffs(hb) - 1;
+          head = __shfl_sync(0xffffffffu, e, first);
+          hp += first;
+          break;
+        }
+        hp += 32;
+        if (hp >= n) break;                       // cannot happen while a live box exists
+      }
+      // (c) nms.c:83-86: the head moves into the selected box's slot; the first slot is vacated either way
+      if (lane == 0 && head >= 0) {
+        if (head != pb) { s_owner[bl] = head; s_label[head] = bl; }
+        s_owner[hp] = -1;
+      }
+      __syncwarp();
     }
     if (lane == 0) s_keep[nkeep] = (short)pb;        // no global access on the serial chain
     ++nkeep;

@@ -56,12 +56,11 @@ elif kind == "conv":
 ''' % ROOT
 
 CASES = [
-    ("gemm", 1, [128, 64, 64]), ("gemm", 0, [128, 64, 64]), ("gemm", 0, [128, 64, 128]), ("gemm", 0, [128, 64, 512]),
-    ("gemm", 0, [128, 128, 64]), ("gemm", 0, [128, 256, 64]), ("gemm", 0, [128, 256, 1024]), ("gemm", 0, [256, 64, 64]),
-    ("gemm", 0, [1000, 512, 256]), ("gemm", 0, [100, 21, 256]), ("gemm", 0, [40000, 64, 576]),
-    ("conv", 1, [1, 64, 16, 16, 64, 3, 1, 1]), ("conv", 0, [1, 64, 16, 16, 64, 3, 1, 1]), ("conv", 0, [1, 64, 16, 16, 64, 1, 1, 0]),
-    ("conv", 0, [1, 128, 37, 53, 256, 3, 1, 1]), ("conv", 0, [3, 64, 7, 7, 64, 3, 1, 1]),
-    ("conv", 0, [2, 64, 14, 14, 128, 3, 2, 1]), ("conv", 0, [1, 128, 28, 36, 256, 1, 2, 0]),
+    ("gemm", 0, [256, 64, 64]), ("gemm", 0, [256, 256, 64]), ("gemm", 0, [256, 128, 256]), ("gemm", 0, [384, 256, 128]),
+    ("gemm", 0, [1000, 512, 256]), ("gemm", 0, [1000, 4096, 1024]), ("gemm", 0, [40000, 64, 576]), ("gemm", 0, [300, 84, 4096]),
+    ("gemm", 0, [128, 64, 64]), ("gemm", 0, [100, 21, 256]),
+    ("conv", 0, [1, 64, 16, 16, 64, 3, 1, 1]), ("conv", 0, [1, 128, 37, 53, 256, 3, 1, 1]), ("conv", 0, [3, 64, 7, 7, 64, 3, 1, 1]),
+    ("conv", 0, [2, 64, 14, 14, 128, 3, 2, 1]), ("conv", 0, [1, 128, 28, 36, 256, 1, 2, 0]), ("conv", 0, [1, 512, 38, 50, 512, 3, 1, 1]),
 ]
 
 
