@@ -31,8 +31,85 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# BASELINE.json configs[1..3] (configs[4], the NMS sweep, is --config nms_sweep). The default, and the line the driver
+# records, is configs[1]; the others are extra evidence for SURVEY 8 rows a6/a7/a9/a11/a13.
+WORKLOADS = {
+    "vgg16_frcnn": dict(H=600, W=800, R=1000, C=21, boxes="random", model="vgg16_fast_rcnn", kw={},
+                        name="VGG-16 Fast R-CNN, 600x800 image, 1000 ROIs/image, C=21, detect+NMS (BASELINE configs[1])"),
+    "multipathnet": dict(H=600, W=800, R=1000, C=81, boxes="sharpmask", model="vgg16_multipathnet", kw={},
+                         name="VGG-16 MultiPathNet 4-foveal + het tower, skip-concat, 600x800, 1000 SharpMask-shaped ROIs, C=81 (BASELINE configs[2])"),
+    "resnet50": dict(H=800, W=1000, R=2000, C=81, boxes="sharpmask", model="resnet50_fast_rcnn", kw={"integral_k": 6},
+                     name="ResNet-50 Fast R-CNN + integral-loss head (K=6), 800x1000, 2000 ROIs, C=81 (BASELINE configs[3], per-GPU shard)"),
+}
 H, W, R, C = 600, 800, 1000, 21
-WORKLOAD = "VGG-16 Fast R-CNN, 600x800 image, 1000 ROIs/image, C=21, detect+NMS (BASELINE configs[1])"
+WORKLOAD = WORKLOADS["vgg16_frcnn"]["name"]
+
+
+def roi_algorithmic_bytes(spec, shapes, R):
+    """each pooled feature map once + R*5*4 + sum over towers of the pooled output (fp32-equivalent bytes)."""
+    used = {}
+    out = 0
+    for t in spec.towers:
+        ct = 0
+        for slot, _ in t.levels:
+            used[slot] = shapes[slot]
+            ct += shapes[slot][0]
+        out += R * ct * t.pooled_h * t.pooled_w * 4
+    return sum(c * h * w * 4 for (c, h, w) in used.values()) + R * 5 * 4 + out
+
+
+def trunk_shapes(spec, H, W):
+    from multipathnet_b200.models import _pool_out
+    shp = {0: (3, H, W)}
+    for L in spec.trunk_layers:
+        c, h, w = shp[L.in_slot]
+        if L.kind == 1:
+            shp[L.out_slot] = (L.cout, (h + 2 * L.pad - L.kh) // L.stride + 1, (w + 2 * L.pad - L.kw) // L.stride + 1)
+        else:
+            shp[L.out_slot] = (c, _pool_out(h, L.kh, L.stride, L.pad, L.ceil_mode), _pool_out(w, L.kw, L.stride, L.pad, L.ceil_mode))
+    return shp
+
+
+def run_nms_sweep(args, rank, world, local_rank):
+    """BASELINE configs[4]: NMS over N boxes x 80 classes, N in {1k..50k}; classes sharded across ranks."""
+    import numpy as np
+    import torch
+    import multipathnet_b200 as mpn
+    from multipathnet_b200 import workloads as wl
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = mpn.Context(local_rank)
+    ncls = 80 // world
+    res = {}
+    for N in (1000, 2000, 5000, 10000, 20000, 50000):
+        if N * N // 8 * ncls > 60e9:
+            cls_here = max(1, int(60e9 // (N * N // 8)))
+        else:
+            cls_here = ncls
+        sb = torch.from_numpy(wl.nms_sweep_boxes(N, cls_here, 5 + N + rank).reshape(-1, 5)).to(dev)
+        keep = torch.empty((cls_here * N,), dtype=torch.int32, device=dev)
+        cnt = torch.empty((cls_here,), dtype=torch.int32, device=dev)
+        offs = (np.arange(cls_here + 1) * N).astype(np.int64)
+        import ctypes as C
+        def call():
+            ctx.check(ctx.lib.mpn_nms_batched_dev(ctx.h, sb.data_ptr(), offs.ctypes.data_as(C.POINTER(C.c_int64)), cls_here, 0.3,
+                                                  keep.data_ptr(), cnt.data_ptr()), "nms_batched_dev")
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10 if N <= 10000 else 3
+        e0.record()
+        for _ in range(reps):
+            call()
+        e1.record(); torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        res[N] = {"classes": cls_here, "ms": ms, "boxes_per_s": world * cls_here * N / (ms / 1e3), "pair_ious_per_s": world * cls_here * N * N / 2 / (ms / 1e3),
+                  "kept_mean": float(cnt.float().mean().item())}
+    if rank == 0:
+        print(json.dumps({"metric": "NMS boxes/sec (80-class sweep)", "value": res[10000]["boxes_per_s"], "unit": "boxes/s", "n_gpus": world,
+                          "higher_is_better": True, "scaling": "strong (classes sharded)", "dtype": "fp32", "data": "synthetic",
+                          "config": {"workload": "NMS sweep N x 80 classes, thr 0.3 (BASELINE configs[4])"}, "sweep": res}))
 
 
 def load_peaks():
@@ -54,7 +131,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -130,17 +207,24 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="vgg16_frcnn", choices=list(WORKLOADS) + ["nms_sweep"])
     args = ap.parse_args()
+    global H, W, R, C, WORKLOAD
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps == 40 and args.warmup == 5:
+        if args.steps == 200 and args.warmup == 5:
             args.steps, args.warmup = 3, 1         # defaults sized for a CPU run of a few minutes
         return run_reference(args, rank, world)
+
+    if args.config == "nms_sweep":
+        return run_nms_sweep(args, rank, world, local_rank)
+    wk = WORKLOADS[args.config]
+    H, W, R, C, WORKLOAD = wk["H"], wk["W"], wk["R"], wk["C"], wk["name"]
 
     import numpy as np
     import torch
@@ -156,13 +240,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream(dev)
     ctx = mpn.Context(local_rank, stream.cuda_stream if stream.cuda_stream else None)
-    spec = models.vgg16_fast_rcnn(C, seed=1234)
-    model = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
+    spec = getattr(models, wk["model"])(C, seed=1234, **wk["kw"])
+    model = mpn.Model(ctx, spec, max_rois=max(R, 1024), max_h=H + 8, max_w=W)
 
     # ---- synthetic inputs: a small rotating set of distinct images/proposals per rank (seeded by rank)
     NIMG = 4
     imgs_h = [wl.transform(wl.raw_image(H, W, 1000 * rank + i), spec.transformer) for i in range(NIMG)]
-    boxes_h = [wl.random_boxes(R, H, W, 1000 * rank + i) for i in range(NIMG)]
+    mkbox = wl.random_boxes if wk["boxes"] == "random" else wl.sharpmask_boxes
+    boxes_h = [mkbox(R, H, W, 1000 * rank + i) for i in range(NIMG)]
     imgs_d = [torch.from_numpy(x).to(dev) for x in imgs_h]
     boxes_d = [torch.from_numpy(x).to(dev) for x in boxes_h]
     scores_d = torch.empty((R, C), dtype=torch.float32, device=dev)
@@ -247,7 +332,9 @@ def main():
     for i in range(args.steps):
         step_dev(i)
     prof = ctx.profile_end()
-    tflop_step = (models.trunk_flops(spec, H, W) - 2.0 * 3 * 64 * 9 * H * W + models.head_flops_per_roi(spec) * R) / 1e12   # tcgen05 layers only
+    L0 = spec.trunk_layers[0]
+    first_flops = 2.0 * L0.cin * L0.cout * L0.kh * L0.kw * ((H + 2 * L0.pad - L0.kh) // L0.stride + 1) * ((W + 2 * L0.pad - L0.kw) // L0.stride + 1)
+    tflop_step = (models.trunk_flops(spec, H, W) - first_flops + models.head_flops_per_roi(spec) * R) / 1e12   # tcgen05 layers only
     tc_ms_step = prof["conv_gemm_tc"][0] / args.steps
     peak_tf, hbm_gbs, peak_src = load_peaks()
     achieved = tflop_step / (tc_ms_step / 1e3) if tc_ms_step > 0 else 0.0
@@ -258,7 +345,7 @@ def main():
                 "algorithmic_tflop_per_step": tflop_step, "kernel_ms_per_step": tc_ms_step,
                 "by_category_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     # ROI pooling (HBM-bound secondary kernel): algorithmic bytes = feature map once + rois + pooled output
-    roi_bytes = 512 * 38 * 50 * 4 + R * 5 * 4 + R * 512 * 49 * 4
+    roi_bytes = roi_algorithmic_bytes(spec, trunk_shapes(spec, H, W), R)
     roi_ms = prof["roi_pool"][0] / args.steps
     roofline["roi_pool"] = {"bound": "hbm", "achieved": roi_bytes / (roi_ms / 1e3) / 1e9 if roi_ms > 0 else None, "peak": hbm_gbs,
                             "unit": "GB/s", "frac": (roi_bytes / (roi_ms / 1e3) / 1e9 / hbm_gbs) if roi_ms > 0 and hbm_gbs else None,
@@ -274,7 +361,7 @@ def main():
                     "api": "mpn_model_detect_nms (host buffers, synchronous)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "vgg16_frcnn":
         # bounded CPU sample: ONE full image (1000 ROIs) through the oracle port on all host cores
         from oracle import graphs as G, ref as O
         O.build()

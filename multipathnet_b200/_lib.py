@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mpn_abi.h")
 
 MPN_LAYER_CONV, MPN_LAYER_MAXPOOL, MPN_LAYER_AVGPOOL, MPN_LAYER_FLATTEN = 1, 2, 3, 4
+MPN_LAYER_LRN = 5       # CaffeNet local response norm: CPU-oracle plumbing config only (BASELINE configs[0]), not on the B200 path
 
 
 class MpnError(RuntimeError):
@@ -293,8 +294,12 @@ class Layer:
     ceil_mode: int = 0
     weight: int = -1
     bias: int = -1
+    groups: int = 1          # grouped conv (CaffeNet conv2/4/5): CPU-oracle plumbing config only
 
     def to_c(self) -> CLayer:
+        if self.groups != 1 or self.kind == MPN_LAYER_LRN:
+            raise MpnError("grouped convolution / LRN (CaffeNet, BASELINE configs[0]) is the CPU plumbing configuration; "
+                           "it is not part of the B200 path")
         return CLayer(self.kind, self.in_slot, self.out_slot, self.cin, self.cout, self.kh, self.kw, self.stride,
                       self.pad, self.relu, self.residual_slot, self.ceil_mode, self.weight, self.bias)
 
@@ -343,9 +348,9 @@ class ModelSpec:
 class Model:
     """mpn_model handle: the B200 replacement for the nn.Sequential graph a model file returns."""
 
-    def __init__(self, ctx: Context, spec: ModelSpec, max_rois: int = 2048, max_h: int = 1024, max_w: int = 1344):
-        self.ctx, self.spec = ctx, spec
-        lib = ctx.lib
+    @staticmethod
+    def build_desc(spec: ModelSpec, max_rois: int = 2048, max_h: int = 1024, max_w: int = 1344):
+        """ModelSpec -> (mpn_model_desc, keep-alive objects). Pure host code (no GPU needed)."""
         trunk = (CLayer * len(spec.trunk_layers))(*[l.to_c() for l in spec.trunk_layers])
         tl: List[Layer] = []
         ctowers = []
@@ -374,6 +379,12 @@ class Model:
             d.bbox_mean[i] = spec.bbox_mean[i]
             d.bbox_std[i] = spec.bbox_std[i]
         d.max_rois, d.max_h, d.max_w = max_rois, max_h, max_w
+        return d, (trunk, towers, tower_layers, heads)
+
+    def __init__(self, ctx: Context, spec: ModelSpec, max_rois: int = 2048, max_h: int = 1024, max_w: int = 1344):
+        self.ctx, self.spec = ctx, spec
+        lib = ctx.lib
+        d, self._keep = Model.build_desc(spec, max_rois, max_h, max_w)
         ws = [np.ascontiguousarray(w, dtype=np.float32) for w in spec.weights]
         wptrs = (_vp * len(ws))(*[w.ctypes.data for w in ws])
         wn = np.array([w.size for w in ws], dtype=np.int64)

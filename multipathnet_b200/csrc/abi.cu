@@ -33,6 +33,7 @@ static int grow(mpn_ctx *ctx, void **p, size_t *have, size_t bytes, void **out) 
 }
 int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes, out); }
 int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, bytes, out); }
+int mpn_scratch3(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch3, &ctx->scratch3_bytes, bytes, out); }
 
 // bump allocator over scratch slot 1 for the host-wrapper calls
 struct Arena {
@@ -85,6 +86,7 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
+  if (ctx->scratch3) cudaFree(ctx->scratch3);
   for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;

@@ -19,6 +19,7 @@ struct mpn_ctx {
   // scratch owned by the ctx (grown on demand, never shrunk)
   void *scratch = nullptr; size_t scratch_bytes = 0;
   void *scratch2 = nullptr; size_t scratch2_bytes = 0;
+  void *scratch3 = nullptr; size_t scratch3_bytes = 0;   // split-K partial accumulators
   // optional per-category kernel timing (bench.py roofline): CUDA events around every launch group
   int profiling = 0;
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -84,6 +85,7 @@ inline int mpn_fail(mpn_ctx *ctx, int code, const std::string &msg) {
 
 int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out);    // slot 1
 int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out);   // slot 2
+int mpn_scratch3(mpn_ctx *ctx, size_t bytes, void **out);   // slot 3
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -24,6 +24,7 @@ struct ConvPlan {
   int CG = 1;                      // CTAs per MMA (tcgen05 cta_group): 2 = CTA pair sharing the B tile
   int tn = 0, th = 0, tw = 0;      // 128 output pixels per M tile = tn*th*tw
   int tiles_img = 0, tiles_h = 0, tiles_w = 0, tiles_n = 0;
+  int splitk = 1, kb_per_split = 0; // split-K over K blocks for tiny GEMMs (deterministic two-pass reduce)
   int flat = 0;                    // 1: 1x1/s1/p0 => pixels treated as one flat axis
   int valid = 0;
 };

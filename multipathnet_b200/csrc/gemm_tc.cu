@@ -54,6 +54,8 @@ struct TcParams {
   __nv_bfloat16 *out_hi, *out_lo; long long out_ld;
   float *out_f32; long long out_f32_ld;
   int relu;
+  int splitk, kb_per_split;      // split-K: unit = (tile, split); each split owns kb_per_split K blocks and writes raw fp32 partials
+  long long split_stride;        // elements between the partial planes of consecutive splits (out_f32 is the workspace then)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -250,12 +252,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
+      for (int u = unit; u < total_tiles * p.splitk; u += num_units) {
+        const int tile = u / p.splitk, split = u - tile * p.splitk;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;   // mt >= tiles_m => fully OOB => zeros
         const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
         const int w_in0 = twi * p.tw * p.stride - p.pad, h_in0 = thi * p.th * p.stride - p.pad, n0 = tni * p.tn;
         const int b_row0 = nt * BN + (int)rank * (BN / CG);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % S; const uint32_t ph = (it / S) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
@@ -282,12 +286,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only when CG=2) =====================
     uint32_t it = 0, lt = 0;
-    for (int tile = unit; rank == 0 && tile < total_tiles; tile += num_units, ++lt) {
+    for (int u = unit; rank == 0 && u < total_tiles * p.splitk; u += num_units, ++lt) {
+      const int split = u % p.splitk;
+      const int kb0 = split * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       mbar_wait(tempty_bar(a), aph ^ 1u);        // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % S; const uint32_t ph = (it / S) & 1u;
         mbar_wait(full_bar(s), ph);                // TMA bytes landed
         tc_fence_after();
@@ -300,21 +306,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
             if (CG == 2) {
-              tc_mma_bf16_2sm(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_bf16_2sm(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - kb0) | k) != 0 ? 1u : 0u);
               tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
               tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
             } else {
-              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb | k) != 0 ? 1u : 0u);
+              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - kb0) | k) != 0 ? 1u : 0u);
               tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
               tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
             }
           }
           if (CG == 2) {                             // multicast: frees the stage / publishes the accumulator in BOTH CTAs
             tc_commit_2sm(empty_bar(s));
-            if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(a));
+            if (kb == kb1 - 1) tc_commit_2sm(tfull_bar(a));
           } else {
             tc_commit(empty_bar(s));                 // stage reusable once these MMAs retire
-            if (kb == num_kb - 1) tc_commit(tfull_bar(a));   // accumulator complete
+            if (kb == kb1 - 1) tc_commit(tfull_bar(a));   // accumulator complete
           }
         }
         __syncwarp();
@@ -326,9 +332,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const int row = q * 32 + lane;               // accumulator row = pixel within the tile
     const int wl = row & (p.tw - 1), hl = (row / p.tw) & (p.th - 1), nl = row / (p.tw * p.th);
     uint32_t lt = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++lt) {
+    for (int u = unit; u < total_tiles * p.splitk; u += num_units, ++lt) {
+      const int tile = u / p.splitk, split = u - tile * p.splitk;
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
+      float *const out_f32 = p.out_f32 ? p.out_f32 + (long long)split * p.split_stride : nullptr;
       const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
       const int wo = twi * p.tw + wl, ho = thi * p.th + hl, n = tni * p.tn + nl;
       const bool row_ok = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
@@ -385,8 +393,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
               *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
             }
-            if (p.out_f32) {
-              float *o = p.out_f32 + pix * p.out_f32_ld + c;
+            if (out_f32) {
+              float *o = out_f32 + pix * p.out_f32_ld + c;
               if (full8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                 reinterpret_cast<float4 *>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
                 reinterpret_cast<float4 *>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -416,6 +424,26 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
   }
+}
+
+// split-K second pass: out = epilogue(sum over splits in FIXED order) — deterministic (no atomics), so the
+// row-chunk invariance the reference asserts (modules/test.lua:85-98) still holds bit for bit.
+struct ReduceParams {
+  const float *ws; long long split_stride; int splitk; long long pixels; int Cout;
+  const float *bias; const __nv_bfloat16 *res_hi, *res_lo; long long res_ld; int relu;
+  __nv_bfloat16 *out_hi, *out_lo; long long out_ld; float *out_f32; long long out_f32_ld;
+};
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceParams r) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= r.pixels * r.Cout) return;
+  const long long pix = idx / r.Cout; const int c = (int)(idx - pix * r.Cout);
+  float acc = 0.f;
+  for (int s = 0; s < r.splitk; ++s) acc += r.ws[(long long)s * r.split_stride + idx];
+  if (r.bias) acc += __ldg(r.bias + c);
+  if (r.res_hi) acc += join_bf16(r.res_hi[pix * r.res_ld + c], r.res_lo[pix * r.res_ld + c]);
+  if (r.relu) acc = fmaxf(acc, 0.f);
+  if (r.out_hi) { __nv_bfloat16 h, l; split_bf16(acc, h, l); r.out_hi[pix * r.out_ld + c] = h; r.out_lo[pix * r.out_ld + c] = l; }
+  if (r.out_f32) r.out_f32[pix * r.out_f32_ld + c] = acc;
 }
 
 // ---------------------------------------------------------------- host: TMA descriptors
@@ -458,7 +486,7 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
     ctx->tc_attr_set[slot] = 1;
   }
   const int tiles_m = pl.tiles_img * pl.tiles_h * pl.tiles_w;
-  const int units = ((tiles_m + CG - 1) / CG) * pl.tiles_n;
+  const int units = ((tiles_m + CG - 1) / CG) * pl.tiles_n * pl.splitk;
   const int grid = std::min(units, ctx->sm_count / CG) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
@@ -537,6 +565,20 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     }
     pl.BN = best_bn; pl.CG = best_cg;
     pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
+    // split-K for GEMMs too small to fill the machine (cls/bbox heads: 4-8 units, 64 K blocks each, latency-bound):
+    // as many splits as there are idle unit slots, at least 8 K blocks per split
+    const long long units = ((tiles_m + pl.CG - 1) / pl.CG) * pl.tiles_n;
+    const long long slots = ctx->sm_count / pl.CG;
+    const long long num_kb = (long long)p.kh * p.kw * (p.x.C / BK);
+    // the split count depends on K only (so results do not change with the number of rows, as long as the GEMM stays
+    // small); it is either that value or 1
+    long long sk = std::min<long long>(num_kb / 8, 8);
+    if (sk < 2 || units * sk > slots) sk = 1;
+    const char *env2 = getenv("MPN_TC_SPLITK");
+    if (env2 && env2[0] == '0') sk = 1;
+    pl.splitk = (int)std::max<long long>(sk, 1);
+    pl.kb_per_split = (int)((num_kb + pl.splitk - 1) / pl.splitk);
+    pl.splitk = (int)((num_kb + pl.kb_per_split - 1) / pl.kb_per_split);     // no empty splits
   }
   MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
   MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));
@@ -564,7 +606,28 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.out_hi = p.y.hi; tp.out_lo = p.y.lo; tp.out_ld = p.y.ld;
   tp.out_f32 = p.y.f32; tp.out_f32_ld = p.y_f32_ld;
   tp.relu = p.relu;
+  tp.splitk = pl.splitk; tp.kb_per_split = pl.kb_per_split; tp.split_stride = 0;
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
+  if (pl.splitk > 1) {
+    // partial accumulators go to a dense fp32 workspace [split][pixel][Cout]; bias/residual/ReLU/output split move to the reduce
+    const long long pixels = (long long)p.y.N * p.y.H * p.y.W;
+    float *ws = nullptr;
+    MPN_TRY(mpn_scratch3(ctx, sizeof(float) * (size_t)pl.splitk * pixels * p.Cout, (void **)&ws));
+    tp.bias = nullptr; tp.res_hi = tp.res_lo = nullptr; tp.relu = 0; tp.out_hi = tp.out_lo = nullptr;
+    tp.out_f32 = ws; tp.out_f32_ld = p.Cout; tp.split_stride = pixels * p.Cout;
+    int rc;
+    if (pl.CG == 2) rc = pl.BN == 256 ? launch_bn<256, 2>(ctx, pl, tp) : (pl.BN == 128 ? launch_bn<128, 2>(ctx, pl, tp) : launch_bn<64, 2>(ctx, pl, tp));
+    else rc = pl.BN == 256 ? launch_bn<256, 1>(ctx, pl, tp) : (pl.BN == 128 ? launch_bn<128, 1>(ctx, pl, tp) : launch_bn<64, 1>(ctx, pl, tp));
+    MPN_TRY(rc);
+    ReduceParams r;
+    r.ws = ws; r.split_stride = tp.split_stride; r.splitk = pl.splitk; r.pixels = pixels; r.Cout = p.Cout;
+    r.bias = p.bias; r.res_hi = p.res.hi; r.res_lo = p.res.lo; r.res_ld = p.res.ld; r.relu = p.relu;
+    r.out_hi = p.y.hi; r.out_lo = p.y.lo; r.out_ld = p.y.ld; r.out_f32 = p.y.f32; r.out_f32_ld = p.y_f32_ld;
+    const long long total = pixels * p.Cout;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(r);
+    MPN_LAUNCHED(ctx);
+    return MPN_OK;
+  }
   if (pl.CG == 2) {
     switch (pl.BN) {
       case 256: return launch_bn<256, 2>(ctx, pl, tp);

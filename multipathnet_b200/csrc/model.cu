@@ -87,6 +87,9 @@ struct mpn_model {
   std::map<int, DTensor> trunk_slots; std::map<int, std::unique_ptr<SplitBuf>> trunk_bufs;
   DevBuf image_dev;
   double trunk_flops = 0, head_flops = 0;
+  // max pyramids of the trunk slots that towers pool from (roi.cu): level k>=1 buffers per slot
+  struct Pyramid { std::vector<std::unique_ptr<SplitBuf>> lv; int nlev = 1; };
+  std::map<int, Pyramid> pyramids;
 
   // ---- heads state
   int64_t hR = 0; bool heads_planned = false;
@@ -212,6 +215,22 @@ int plan_trunk(mpn_model *m, int H, int W) {
     m->trunk_slots[L.out_slot] = out;
     m->trunk_exec.push_back(e);
   }
+  // max pyramids for every slot a tower pools from: levels with 2^k <= min(H, W), at most ROI_MAX_LEVELS-1 extra copies
+  for (const mpn_tower &T : m->towers)
+    for (int l = 0; l < T.n_levels; ++l) {
+      const int slot = T.level_slot[l];
+      MPN_CHECK_ARG(ctx, m->trunk_slots.count(slot) && slot > 0, "tower level reads an undefined trunk slot");
+      const DTensor &f = m->trunk_slots[slot];
+      mpn_model::Pyramid &P = m->pyramids[slot];
+      int nlev = 1;
+      while (nlev < ROI_MAX_LEVELS && (1 << nlev) <= std::min(f.H, f.W)) ++nlev;
+      P.nlev = nlev;
+      P.lv.resize(nlev);
+      for (int k = 1; k < nlev; ++k) {
+        if (!P.lv[k]) P.lv[k].reset(new SplitBuf());
+        MPN_TRY(P.lv[k]->ensure(ctx, (size_t)(f.N * f.H * f.W * f.C)));
+      }
+    }
   m->tH = H; m->tW = W; m->trunk_valid = false; m->heads_planned = false;
   return MPN_OK;
 }
@@ -233,6 +252,16 @@ int run_trunk(mpn_model *m, const float *image_dev) {
       }
     } else {
       MPN_TRY(mpn_maxpool_launch(ctx, e.in, L.kh, L.stride, L.pad, e.out));
+    }
+  }
+  for (auto &kv : m->pyramids) {
+    const DTensor &f = m->trunk_slots[kv.first];
+    const __nv_bfloat16 *ph = f.hi, *pl = f.lo; long long ld = f.ld;
+    for (int k = 1; k < kv.second.nlev; ++k) {
+      SplitBuf &b = *kv.second.lv[k];
+      MPN_TRY(mpn_maxpyr_launch(ctx, ph, pl, (int)f.N, (int)f.H, (int)f.W, (int)f.C, ld, 1 << (k - 1), (__nv_bfloat16 *)b.hi.p,
+                                (__nv_bfloat16 *)b.lo.p));
+      ph = (const __nv_bfloat16 *)b.hi.p; pl = (const __nv_bfloat16 *)b.lo.p; ld = f.C;
     }
   }
   m->trunk_valid = true;
@@ -281,6 +310,10 @@ int plan_heads(mpn_model *m, int64_t R) {
       j.hi = f.hi; j.lo = f.lo; j.H = (int)f.H; j.W = (int)f.W; j.C = (int)f.C; j.ld = f.ld; j.scale = T.level_scale[l];
       j.region = T.region; j.out_hi = X.pooled.hi; j.out_lo = X.pooled.lo; j.out_ld = X.ctot; j.out_ch_off = ch_off;
       j.normalize = T.normalize;
+      const mpn_model::Pyramid &P = m->pyramids[T.level_slot[l]];
+      j.nlev = P.nlev;
+      for (int k = 0; k < ROI_MAX_LEVELS; ++k) { j.hi_lv[k] = f.hi; j.lo_lv[k] = f.lo; }
+      for (int k = 1; k < P.nlev; ++k) { j.hi_lv[k] = (const __nv_bfloat16 *)P.lv[k]->hi.p; j.lo_lv[k] = (const __nv_bfloat16 *)P.lv[k]->lo.p; }
       ch_off += (int)f.C;
     }
     // shape walk

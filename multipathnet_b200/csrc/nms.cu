@@ -105,6 +105,7 @@ nms_mask_kernel(const float4 *__restrict__ sorted_boxes, int cap, int nwords_cap
     float v = iou_ref(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w);
     if (!(v <= thr)) bits |= (1ull << c);
   }
+  if (rb == cb) bits |= 1ull << t;              // a selected box also removes itself (saves the special case in the walk)
   mask[((size_t)seg * cap + i) * nwords_cap + cb] = bits;
 }
 
@@ -166,42 +167,183 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
   if (threadIdx.x == 0) keep_counts[seg] = nkeep;
 }
 
-// ---- small segments (n <= 1024): the whole suppression mask lives in shared memory and ONE warp walks the
-// greedy selection round by round (no block barriers on the serial chain: ~100 cycles per kept box).
+// ---- segments up to 4096 boxes: ONE warp walks the greedy selection round by round, the removed-bitset lives in
+// registers (2 x 64 bits per lane), the suppression mask in shared memory when it fits (n <= 1024) else in L2.
+// No block barrier sits on the serial chain (~100-150 cycles per kept box with the smem mask).
+//
 // Tied scores are resolved exactly like nms.c WITHOUT re-running its O(N) pointer walk per round:
 //   nms.c's array order only ever changes by "the element in the first live slot moves into the slot of the
-//   selected box" (the swap at nms.c:83-86; the survivor compaction at :90-99 is order preserving).
-//   So each element carries a slot label (initially its row index), the head is the live element with the
-//   smallest label (a monotone pointer finds it), and "first strict maximum in current order" (nms.c:74-81)
-//   = among the live boxes sharing the top score, the one with the smallest label.
-constexpr int SMALL_CAP = 1024;
-constexpr int SMALL_THREADS = 256;
+//   selected box" (the swap at nms.c:83-86; the survivor compaction at :90-99 is order preserving). So each element
+//   carries a slot label (initially its row index), the head is the live occupant of the smallest live slot (a
+//   monotone pointer finds it), and "first strict maximum in current order" (nms.c:74-81) = among the live boxes
+//   sharing the top score, the one with the smallest label.
+//   The label bookkeeping is LAZY: the walk records every selection and each box's death round; only when a round
+//   actually has two live boxes with the top score is the slot history replayed up to that round (by one lane,
+//   no warp collectives), and the tie broken by label. Segments whose ties never meet pay (almost) nothing.
+constexpr int WARP_CAP = 4096;
+constexpr int WARP_SMEM_MASK_CAP = 1024;
+constexpr int WARPK_THREADS = 256;
 
-__global__ void __launch_bounds__(SMALL_THREADS)
-nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
-                      const float *__restrict__ sb, int cap, int nwords_cap, const int32_t *__restrict__ counts,
-                      const int32_t *__restrict__ tie_flag, const int32_t *__restrict__ src_idx,
-                      int32_t *__restrict__ keep_idx, int32_t *__restrict__ keep_counts) {
-  extern __shared__ unsigned long long s_mask[];      // n x nwords
-  __shared__ float s_score[SMALL_CAP];
-  __shared__ int s_label[SMALL_CAP], s_owner[SMALL_CAP];
-  __shared__ unsigned long long s_removed[SMALL_CAP / 64];
-  __shared__ short s_keep[SMALL_CAP];                 // kept sorted positions, resolved to row indices after the walk
+struct WalkCtx {
+  const unsigned long long *s_mask, *m; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
+  unsigned short *s_keep;
+  int n, nwords, nwords_cap, use_smem_mask;
+};
+
+// The serial walk, one warp. TIE: the segment has equal scores. TWO: more than 32 mask words (n > 2048) -> two
+// removed-words per lane. A single warp cannot hide instruction latency, so every instruction on this chain costs
+// ~5 cycles: the common path is kept to a few dozen instructions per kept box, and the slot-label bookkeeping that
+// nms.c's tie order needs is LAZY: only when a round really has two live boxes with the top score does `replay`
+// re-walk the recorded selections [replayed, nkeep) (liveness re-derived from the same mask rows) while tracking the
+// head moves, after which the tie is broken by slot label. Segments whose ties never meet pay one shuffle per round.
+template <bool TIE, bool TWO>
+__device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
+  const int n = c.n, nwords = c.nwords;
+  auto init_word = [&](int w) -> unsigned long long {
+    if (w >= nwords) return ~0ull;
+    return (w == nwords - 1 && (n & 63)) ? (~0ull << (n & 63)) : 0ull;
+  };
+  auto mask_word = [&](int row, int w) -> unsigned long long {
+    return c.use_smem_mask ? c.s_mask[row * nwords + w] : __ldg(c.m + (size_t)row * c.nwords_cap + w);
+  };
+  unsigned long long rem0 = init_word(lane), rem1 = TWO ? init_word(lane + 32) : ~0ull;
+  unsigned long long tn0 = 0ull, tn1 = 0ull;       // tienext bit p: score[p] == score[p+1] in sorted order
+  unsigned long long rr0 = rem0, rr1 = rem1;       // replay state: removed-set at round `replayed`
+  if (TIE) {
+    for (int b = 0; b < 64; ++b) {
+      const int p0 = lane * 64 + b, p1 = (lane + 32) * 64 + b;
+      if (p0 + 1 < n && c.s_score[p0] == c.s_score[p0 + 1]) tn0 |= 1ull << b;
+      if (TWO && p1 + 1 < n && c.s_score[p1] == c.s_score[p1 + 1]) tn1 |= 1ull << b;
+    }
+  }
+  int nkeep = 0, hp = 0, replayed = 0;
+  while (true) {
+    // ---- first live box in (score desc, row asc) order
+    unsigned ball = __ballot_sync(0xffffffffu, rem0 != ~0ull);
+    int half = 0;
+    if (!ball) {
+      if (!TWO) break;
+      ball = __ballot_sync(0xffffffffu, rem1 != ~0ull); half = 1;
+      if (!ball) break;
+    }
+    const int wl = __ffs(ball) - 1;
+    const unsigned long long aw = ~__shfl_sync(0xffffffffu, (TWO && half) ? rem1 : rem0, wl);
+    const int qb = __ffsll((long long)aw) - 1;
+    const int q = (wl + (TWO ? 32 * half : 0)) * 64 + qb;
+    int pb = q;
+    if (TIE) {
+      const unsigned long long tw = __shfl_sync(0xffffffffu, (TWO && half) ? tn1 : tn0, wl);
+      if ((tw >> qb) & 1ull) {           // q's score continues into q+1: is a tied box still alive? (rare path)
+        // publish the current removed-set so any lane can test liveness
+        c.s_rrem[lane] = rem0; if (TWO) c.s_rrem[lane + 32] = rem1;
+        __syncwarp();
+        const float sq = c.s_score[q];
+        int need = 0;
+        if (lane == 0)
+          for (int r = q + 1; r < n && c.s_score[r] == sq; ++r)
+            if (!((c.s_rrem[r >> 6] >> (r & 63)) & 1ull)) { need = 1; break; }
+        need = __shfl_sync(0xffffffffu, need, 0);
+        if (need) {
+          // ---- replay rounds [replayed, nkeep): nms.c:83-86 moves the head (live occupant of the first live slot)
+          //      into the selected box's slot, every round
+          for (int tt = replayed; tt < nkeep; ++tt) {
+            const int pbt = c.s_keep[tt];
+            __syncwarp();
+            c.s_rrem[lane] = rr0; if (TWO) c.s_rrem[lane + 32] = rr1;
+            __syncwarp();
+            int head = -1;
+            while (true) {                                   // warp-parallel scan, 32 slots per step, monotone pointer
+              const int sl = hp + lane;
+              const int e = (sl < n) ? c.s_owner[sl] : -1;
+              const bool ok = (e >= 0) && !((c.s_rrem[e >> 6] >> (e & 63)) & 1ull);
+              const unsigned hb = __ballot_sync(0xffffffffu, ok);
+              if (hb) { const int first = __ffs(hb) - 1; head = __shfl_sync(0xffffffffu, e, first); hp += first; break; }
+              hp += 32;
+              if (hp >= n) break;
+            }
+            if (lane == 0 && head >= 0) {
+              const int lb = c.s_label[pbt];
+              if (head != pbt) { c.s_owner[lb] = head; c.s_label[head] = lb; }
+              c.s_owner[hp] = -1;
+            }
+            // first live box of that round (start of its tie group), then apply the round's suppression to the replay set
+            unsigned rb = __ballot_sync(0xffffffffu, rr0 != ~0ull); int rh = 0;
+            if (!rb && TWO) { rb = __ballot_sync(0xffffffffu, rr1 != ~0ull); rh = 1; }
+            const int rwl = __ffs(rb) - 1;
+            const unsigned long long raw = ~__shfl_sync(0xffffffffu, (TWO && rh) ? rr1 : rr0, rwl);
+            const int qt = (rwl + (TWO ? 32 * rh : 0)) * 64 + __ffsll((long long)raw) - 1;
+            const int wbt = pbt >> 6;
+            if (lane >= wbt && lane < nwords) rr0 |= mask_word(pbt, lane);
+            if (TWO && lane + 32 >= wbt && lane + 32 < nwords) rr1 |= mask_word(pbt, lane + 32);
+            for (int e = qt; e < pbt; ++e)
+              if ((mask_word(e, wbt) >> (pbt & 63)) & 1ull) {
+                if (lane == (e >> 6)) rr0 |= 1ull << (e & 63);
+                if (TWO && lane + 32 == (e >> 6)) rr1 |= 1ull << (e & 63);
+              }
+          }
+          replayed = nkeep;
+          __syncwarp();
+          // ---- nms.c:74-81: first strict maximum in current order = smallest slot label among the live tied boxes
+          c.s_rrem[lane] = rem0; if (TWO) c.s_rrem[lane + 32] = rem1;
+          __syncwarp();
+          if (lane == 0) {
+            int bl = c.s_label[q];
+            for (int r = q + 1; r < n && c.s_score[r] == sq; ++r)
+              if (!((c.s_rrem[r >> 6] >> (r & 63)) & 1ull) && c.s_label[r] < bl) { pb = r; bl = c.s_label[r]; }
+          }
+          pb = __shfl_sync(0xffffffffu, pb, 0);
+        }
+      }
+    }
+    if (lane == 0) c.s_keep[nkeep] = (unsigned short)pb;       // no global access on the serial chain
+    // ---- suppress: removed |= mask row of pb (upper triangle incl. the diagonal bit = pb itself)
+    const int wb = pb >> 6;
+    if (lane >= wb && lane < nwords) rem0 |= mask_word(pb, lane);
+    if (TWO && lane + 32 >= wb && lane + 32 < nwords) rem1 |= mask_word(pb, lane + 32);
+    if (TIE && pb != q) {
+      // live boxes of the same score that precede pb in sorted order: suppression is symmetric (IoU is): bit [e][pb]
+      for (int e = q; e < pb; ++e)
+        if ((mask_word(e, wb) >> (pb & 63)) & 1ull) {
+          if (lane == (e >> 6)) rem0 |= 1ull << (e & 63);
+          if (TWO && lane + 32 == (e >> 6)) rem1 |= 1ull << (e & 63);
+        }
+    }
+    ++nkeep;
+  }
+  return nkeep;
+}
+
+__global__ void __launch_bounds__(WARPK_THREADS)
+nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
+                     const float *__restrict__ sb, int cap, int nwords_cap, int use_smem_mask,
+                     const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag,
+                     const int32_t *__restrict__ src_idx, int32_t *__restrict__ keep_idx,
+                     int32_t *__restrict__ keep_counts) {
+  extern __shared__ unsigned long long s_dyn[];
   const int seg = blockIdx.x;
   const int n = counts ? counts[seg] : cap;
   if (n <= 0) { if (threadIdx.x == 0) keep_counts[seg] = 0; return; }
   const int nwords = (n + 63) >> 6;
   const bool tie = tie_flag[seg] != 0;
+  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap] [keep u16 cap]
+  unsigned long long *s_mask = s_dyn;
+  unsigned long long *s_rrem = s_dyn + (use_smem_mask ? (size_t)cap * nwords_cap : 0);
+  float *s_score = reinterpret_cast<float *>(s_rrem + 64);
+  int *s_label = reinterpret_cast<int *>(s_score + cap);
+  int *s_owner = s_label + cap;
+  unsigned short *s_keep = reinterpret_cast<unsigned short *>(s_owner + cap);
   const unsigned long long *m = mask + (size_t)seg * cap * nwords_cap;
   const int32_t *ord = order + (size_t)seg * cap;
+  if (use_smem_mask) {
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n * nwords; i += SMALL_THREADS) {
-    const int r = i / nwords, w = i - r * nwords;
-    s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;     // only the upper triangle was computed
+    for (int i = threadIdx.x; i < n * nwords; i += WARPK_THREADS) {
+      const int r = i / nwords, w = i - r * nwords;
+      s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;   // only the upper triangle was computed
+    }
   }
   if (tie) {
     const float *seg_sb = sb + (size_t)seg * cap * 5;
-    for (int p = threadIdx.x; p < n; p += SMALL_THREADS) {
+    for (int p = threadIdx.x; p < n; p += WARPK_THREADS) {
       const int o = ord[p];
       s_score[p] = seg_sb[(size_t)o * 5 + 4];
       s_label[p] = o;            // slot label = position in the reference's pointer array
@@ -211,76 +353,10 @@ nms_scan_small_kernel(const unsigned long long *__restrict__ mask, const int32_t
   __syncthreads();
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  unsigned long long rem = ~0ull;                       // lanes >= nwords: nothing alive
-  if (lane < nwords) rem = (lane == nwords - 1 && (n & 63)) ? (~0ull << (n & 63)) : 0ull;
-  if (lane < SMALL_CAP / 64) s_removed[lane] = rem;
-  __syncwarp();
-  auto alive_s = [&](int e) { return !((s_removed[e >> 6] >> (e & 63)) & 1ull); };
-  int nkeep = 0, hp = 0;
-  while (true) {
-    const unsigned long long alive = ~rem;
-    const unsigned ball = __ballot_sync(0xffffffffu, alive != 0ull);
-    if (!ball) break;
-    const int wl = __ffs(ball) - 1;
-    const unsigned long long aw = __shfl_sync(0xffffffffu, alive, wl);
-    const int q = wl * 64 + __ffsll((long long)aw) - 1;       // first live box in (score desc, row asc) order
-    int pb = q;
-    if (tie) {
-      // (a) other live boxes with the same score as q? (they are contiguous after q in sorted order). Warp-parallel
-      //     probe of the next 32 positions; the rare hit falls back to a serial walk by lane 0.
-      const float sq = s_score[q];
-      int bl = s_label[q];
-      {
-        const int r = q + 1 + lane;
-        const bool eq = (r < n) && (s_score[r] == sq);
-        const bool hit = eq && alive_s(r);
-        // walk serially if a live tied box is in the window, or the tie group runs past the 32-position window
-        if (__ballot_sync(0xffffffffu, hit) || __ballot_sync(0xffffffffu, eq) == 0xffffffffu) {
-          if (lane == 0)
-            for (int rr = q + 1; rr < n && s_score[rr] == sq; ++rr)
-              if (alive_s(rr) && s_label[rr] < bl) { pb = rr; bl = s_label[rr]; }
-          pb = __shfl_sync(0xffffffffu, pb, 0);
-          bl = __shfl_sync(0xffffffffu, bl, 0);
-        }
-      }
-      // (b) head = live occupant of the first live slot: warp-parallel scan, 32 slots per step, monotone pointer
-      int head = -1;
-      while (true) {
-        const int sl = hp + lane;
-        const int e = (sl < n) ? s_owner[sl] : -1;
-        const bool ok = (e >= 0) && alive_s(e);
-        const unsigned hb = __ballot_sync(0xffffffffu, ok);
-        if (hb) {
-          const int first = __ffs(hb) - 1;
-          head = __shfl_sync(0xffffffffu, e, first);
-          hp += first;
-          break;
-        }
-        hp += 32;
-        if (hp >= n) break;                       // cannot happen while a live box exists
-      }
-      // (c) nms.c:83-86: the head moves into the selected box's slot; the first slot is vacated either way
-      if (lane == 0 && head >= 0) {
-        if (head != pb) { s_owner[bl] = head; s_label[head] = bl; }
-        s_owner[hp] = -1;
-      }
-      __syncwarp();
-    }
-    if (lane == 0) s_keep[nkeep] = (short)pb;        // no global access on the serial chain
-    ++nkeep;
-    const int wb = pb >> 6;
-    if (lane < nwords) {
-      if (lane >= wb) rem |= s_mask[pb * nwords + lane];
-      if (lane == wb) rem |= 1ull << (pb & 63);
-    }
-    if (tie) {
-      // live boxes of the same score that precede pb in sorted order: suppression is symmetric (IoU is), bit [e][pb]
-      for (int e = q; e < pb; ++e)
-        if (((s_mask[e * nwords + wb] >> (pb & 63)) & 1ull) && lane == (e >> 6)) rem |= 1ull << (e & 63);
-      if (lane < SMALL_CAP / 64) s_removed[lane] = rem;
-      __syncwarp();
-    }
-  }
+  int nkeep;
+  const WalkCtx wc{s_mask, m, s_score, s_label, s_owner, s_rrem, s_keep, n, nwords, nwords_cap, use_smem_mask};
+  if (tie) nkeep = (nwords > 32) ? nms_walk<true, true>(wc, lane) : nms_walk<true, false>(wc, lane);
+  else nkeep = (nwords > 32) ? nms_walk<false, true>(wc, lane) : nms_walk<false, false>(wc, lane);
   __syncwarp();
   for (int k = lane; k < nkeep; k += 32) {
     const int o = ord[s_keep[k]];
@@ -405,15 +481,16 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
-  const bool small = cap <= SMALL_CAP;
+  const bool small = cap <= WARP_CAP;
   nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, small ? 0 : 1, thr, mask);
   MPN_LAUNCHED(ctx);
   if (small) {
-    const size_t smem = sizeof(unsigned long long) * (size_t)cap * nwords;
+    const int use_smem_mask = cap <= WARP_SMEM_MASK_CAP ? 1 : 0;
+    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 14 + 64 * 8 + 64;
     if (smem > 48 * 1024)
-      MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_small_kernel<<<nseg, SMALL_THREADS, smem, ctx->stream>>>(mask, order, sb_dev, cap, nwords, counts_dev, tie,
-                                                                     src_idx_dev, keep_idx_dev, keep_counts_dev);
+      MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_scan_warp_kernel<<<nseg, WARPK_THREADS, smem, ctx->stream>>>(mask, order, sb_dev, cap, nwords, use_smem_mask, counts_dev,
+                                                                    tie, src_idx_dev, keep_idx_dev, keep_counts_dev);
     MPN_LAUNCHED(ctx);
     return MPN_OK;
   }
@@ -463,6 +540,7 @@ nms_dense_mask_kernel(const float4 *__restrict__ boxes, int n, int nwords, float
     float v = iou_dense(a, areaa, b, areab);
     if (v > thr) bits |= (1ull << c);
   }
+  if (rb == cb) bits |= 1ull << t;
   mask[(size_t)i * nwords + cb] = bits;
 }
 }  // namespace

@@ -14,7 +14,7 @@ from typing import List, Tuple
 import numpy as np
 
 from ._lib import (Head, Layer, ModelSpec, Tower, MPN_LAYER_AVGPOOL, MPN_LAYER_CONV, MPN_LAYER_FLATTEN,
-                   MPN_LAYER_MAXPOOL)
+                   MPN_LAYER_LRN, MPN_LAYER_MAXPOOL)
 
 VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 
@@ -133,6 +133,36 @@ def vgg16_multipathnet(num_classes: int = 81, seed: int = 1234, width_div: int =
     return ModelSpec(name=f"vgg16_multipathnet/{width_div}", trunk_layers=trunk, towers=towers, cls_heads=cls,
                      bbox_head=Head(nreg * fc_dim, fc_dim, 4 * num_classes, wb, bb), num_classes=num_classes,
                      weights=W.arrays, no_softmax=1 if integral_k > 0 else 0, transformer="ross", taps=taps)
+
+
+def alexnet_fast_rcnn(num_classes: int = 21, seed: int = 1234) -> ModelSpec:
+    """models/alexnet.lua:14-26 (CaffeNet Fast R-CNN, ROIPooling(6,6,1/16), fc6 9216->4096). BASELINE configs[0]:
+    the reference's own CPU-runnable plumbing case — used with the CPU oracle only (grouped convs + LRN are not
+    part of the B200 path; Model() refuses this spec)."""
+    W = _W(seed)
+    L: List[Layer] = []
+    def conv(i, o, cin, cout, k, s, p, g=1, gain=1.0):
+        w, b = W.conv(cout, cin // g, k, k, gain=gain)
+        L.append(Layer(MPN_LAYER_CONV, i, o, cin=cin, cout=cout, kh=k, kw=k, stride=s, pad=p, relu=1, weight=w, bias=b, groups=g))
+    conv(0, 1, 3, 96, 11, 4, 0, gain=1.0 / 64)
+    L.append(Layer(MPN_LAYER_MAXPOOL, 1, 2, kh=3, kw=3, stride=2, ceil_mode=1))
+    L.append(Layer(MPN_LAYER_LRN, 2, 3))
+    conv(3, 4, 96, 256, 5, 1, 2, g=2)
+    L.append(Layer(MPN_LAYER_MAXPOOL, 4, 5, kh=3, kw=3, stride=2, ceil_mode=1))
+    L.append(Layer(MPN_LAYER_LRN, 5, 6))
+    conv(6, 7, 256, 384, 3, 1, 1)
+    conv(7, 8, 384, 384, 3, 1, 1, g=2)
+    conv(8, 9, 384, 256, 3, 1, 1, g=2)
+    w6, b6 = W.linear(4096, 256 * 36)
+    w7, b7 = W.linear(4096, 4096)
+    tl = [Layer(MPN_LAYER_FLATTEN, 0, 1), Layer(MPN_LAYER_CONV, 1, 2, cin=9216, cout=4096, relu=1, weight=w6, bias=b6),
+          Layer(MPN_LAYER_CONV, 2, 3, cin=4096, cout=4096, relu=1, weight=w7, bias=b7)]
+    tower = Tower(region=0, levels=[(9, 1.0 / 16)], pooled_w=6, pooled_h=6, normalize=0, layers=tl, out_slot=3)
+    wc, bc = W.linear(num_classes, 4096, std=0.01, zero_bias=True)
+    wb, bb = W.linear(4 * num_classes, 4096, std=0.001, zero_bias=True)
+    return ModelSpec(name="alexnet_fast_rcnn", trunk_layers=L, towers=[tower], cls_heads=[Head(0, 4096, num_classes, wc, bc)],
+                     bbox_head=Head(0, 4096, 4 * num_classes, wb, bb), num_classes=num_classes, weights=W.arrays,
+                     transformer="ross", taps={"conv5": 9})
 
 
 def _bottleneck(W: _W, layers: List[Layer], slot_in: int, next_slot: int, cin: int, mid: int, cout: int, stride: int):

@@ -11,7 +11,7 @@ import torch.nn.functional as F
 
 from . import ref as O
 
-CONV, MAXPOOL, AVGPOOL, FLATTEN = 1, 2, 3, 4
+CONV, MAXPOOL, AVGPOOL, FLATTEN, LRN = 1, 2, 3, 4, 5
 
 
 def _t(a):
@@ -27,7 +27,8 @@ def _run_layers(layers, slots, weights):
             if x.dim() == 2:                                   # Linear on a flattened tensor
                 y = F.linear(x, w.reshape(L.cout, -1), b)
             else:
-                y = F.conv2d(x, w.reshape(L.cout, L.cin, L.kh, L.kw), b, stride=L.stride, padding=L.pad)
+                g = getattr(L, "groups", 1)
+                y = F.conv2d(x, w.reshape(L.cout, L.cin // g, L.kh, L.kw), b, stride=L.stride, padding=L.pad, groups=g)
             if L.residual_slot >= 0:
                 y = y + slots[L.residual_slot]
             if L.relu:
@@ -36,6 +37,8 @@ def _run_layers(layers, slots, weights):
             y = F.max_pool2d(x, (L.kh, L.kw), L.stride, L.pad, ceil_mode=bool(L.ceil_mode))
         elif L.kind == AVGPOOL:
             y = x.mean(dim=(2, 3))                              # avgpool 7 + View (resnet.lua:39)
+        elif L.kind == LRN:                                     # CaffeNet norm1/norm2: local_size 5, alpha 1e-4, beta 0.75
+            y = F.local_response_norm(x, 5, alpha=1e-4, beta=0.75, k=1.0)
         elif L.kind == FLATTEN:
             y = x.reshape(x.shape[0], -1)                       # (c, ph, pw) order: View(-1):setNumInputDims(3)
         else:

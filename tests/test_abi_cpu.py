@@ -122,3 +122,32 @@ def test_bilinear_identity_and_constant():
     assert _bilinear_resize(im, 7, 9) is im
     c = np.full((3, 5, 5), 2.5, np.float32)
     assert np.allclose(_bilinear_resize(c, 11, 13), 2.5)
+
+
+def test_cfg1_alexnet_cpu_plumbing(oracle_built):
+    """BASELINE configs[0]: AlexNet (CaffeNet) Fast R-CNN, one synthetic 224px image, 64 random boxes, CPU nn path —
+    the whole detect + testOne pipeline through the oracle, no GPU (SURVEY 8d cfg 1)."""
+    from oracle import graphs as G
+    O = oracle_built
+    spec = models.alexnet_fast_rcnn(21, seed=1)
+    img = wl.transform(wl.raw_image(224, 224, 1), spec.transformer)
+    boxes = wl.random_boxes(64, 224, 224, 1, wmax=64, hmax=64)
+    scores, bboxes, keeps = G.test_one(spec, img, boxes, 1.0, 224, 224)
+    assert scores.shape == (64, 21) and bboxes.shape == (64, 84) and len(keeps) == 20
+    np.testing.assert_allclose(scores.sum(1), 1.0, atol=1e-5)
+    assert bboxes.min() >= 1 and bboxes[:, 0::2].max() <= 224
+    ts = G.trunk_forward(spec, img)
+    assert tuple(ts[9].shape) == (1, 256, 13, 13)                 # conv5 of CaffeNet at 224 px
+    for j, k in enumerate(keeps, start=1):                        # keep lists = the literal nms.c on the same rows
+        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
+        assert np.array_equal(sb[k], O.ref_nms_rows(sb, 0.3))
+    # the B200 path refuses this configuration loudly (grouped conv + LRN are CPU-plumbing only)
+    with pytest.raises(mpn.MpnError):
+        mpn.Model.build_desc(spec)
+
+
+def test_model_desc_builds_without_gpu():
+    d, keep = mpn.Model.build_desc(models.vgg16_fast_rcnn(21, width_div=4, fc_dim=256))
+    assert d.n_trunk_layers == 17 and d.n_towers == 1 and d.num_classes == 21 and d.bbox_head.cout == 84
+    d, keep = mpn.Model.build_desc(models.vgg16_multipathnet(81, width_div=4, fc_dim=256))
+    assert d.n_towers == 5 and d.n_tower_layers == 20 and d.towers[4].region == 1 and d.towers[4].n_levels == 3

@@ -165,3 +165,32 @@ def test_resnet50_integral_small(ctx):
     assert rel_err(s, rs) < TOL and rel_err(b, rb) < TOL
     np.testing.assert_allclose(s.sum(1), 1.0, atol=1e-5)
     m.close()
+
+
+def test_multipathnet_full_size_cfg3(ctx):
+    """BASELINE configs[2] at full size: VGG-16 MultiPathNet, 5 towers, 600x800, 1000 SharpMask-shaped ROIs, C=81"""
+    spec = models.vgg16_multipathnet(81, seed=1234)
+    m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
+    img, boxes = _inputs(spec, 600, 800, 1000, 3, sharp=True)
+    scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
+    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600)
+    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    for j in (1, 40, 80):
+        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
+        assert np.array_equal(keeps[j - 1], O.nms(sb, 0.3))
+    tf, hf = m.last_flops()
+    assert abs(hf / 1e12 - 1.458) < 0.01                     # SURVEY 8a12: 1.458 GFLOP/ROI x 1000
+    m.close()
+
+
+def test_resnet50_full_size_cfg4(ctx):
+    """BASELINE configs[3] per-GPU shard at full size: ResNet-50 + integral head K=6, 800x1000, 2000 ROIs, C=81"""
+    spec = models.resnet50_fast_rcnn(81, seed=1234, integral_k=6)
+    m = mpn.Model(ctx, spec, max_rois=2048, max_h=808, max_w=1000)
+    img, boxes = _inputs(spec, 800, 1000, 2000, 4, sharp=True)
+    scores, bboxes = m.detect(img, boxes, 1.0)
+    rs, rb = G.detect(spec, img, boxes, 1.0)
+    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    tf, hf = m.last_flops()
+    assert abs(tf / 1e9 - 104.9) < 1.5 and abs(hf / 2000 / 1e9 - 1.62) < 0.02
+    m.close()

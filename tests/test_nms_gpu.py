@@ -127,3 +127,24 @@ def test_nms_sweep_10k_x_80(ctx):
     keeps = ctx.nms_batched(allsb.reshape(-1, 5), np.arange(81) * 10000, 0.3)
     for c in (0, 17, 79):
         assert np.array_equal(keeps[c], O.nms(allsb[c], 0.3))
+
+
+@pytest.mark.parametrize("n,seed", [(1025, 1), (1500, 2), (2048, 3), (3000, 4), (4096, 5), (4097, 6)])
+def test_nms_medium_segments_with_ties(ctx, n, seed):
+    """1024 < n <= 4096: warp-serial walk with the mask in L2 (2 removed-words per lane); 4097: chunked path"""
+    sb = wl.nms_sweep_boxes(n, 1, 3000 + seed, ties=True)[0]
+    assert np.array_equal(ctx.nms(sb, 0.3), _expect_rows(sb, 0.3))
+    sb2 = wl.nms_sweep_boxes(n, 1, 3100 + seed)[0]
+    assert np.array_equal(ctx.nms(sb2, 0.3), _expect_rows(sb2, 0.3))
+
+
+def test_nms_duplicate_rows_many_classes(ctx):
+    """identical proposals (same pooled features => same score in EVERY class) are the common source of ties in the
+    pipeline: 80 segments that all contain the same tied pairs"""
+    base = wl.nms_sweep_boxes(600, 80, 4242)
+    for c in range(80):
+        base[c, 100:110] = base[c, 200:210]          # 10 exact duplicates (box and score)
+        base[c, 300:305, 4] = base[c, 400:405, 4]    # 5 score ties with different boxes
+    keeps = ctx.nms_batched(base.reshape(-1, 5), np.arange(81) * 600, 0.3)
+    for c in range(0, 80, 7):
+        assert np.array_equal(keeps[c], O.nms(base[c], 0.3))

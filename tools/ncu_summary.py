@@ -18,6 +18,9 @@ def main(path):
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
+    for h, i in list(col.items()):            # metrics of the Triage sections carry a "UNIT.Section." prefix
+        if "." in h and h.split(".", 2)[-1] not in col and h.count(".") >= 2:
+            col.setdefault(h.split(".", 2)[-1], i)
     print(f"# ncu summary of `{path}` (cold-cache, serialised replays: compare shares, not absolutes)\n")
     for r in rows[2:]:
         name = r[col["Kernel Name"]].split("(")[0].replace("<unnamed>::", "")
