@@ -205,6 +205,17 @@ int mpn_model_last_flops(const mpn_model *m, double *trunk_flops, double *head_f
  * buffers, computed with the same split-bf16 tcgen05 kernel the model uses.  */
 int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bias, int64_t M,
                    int64_t N, int64_t K, int32_t relu, int32_t impl, float *C);
+/* engine microbenchmark (diagnostics, tools/engine_sweep.py): times `iters` back-to-back launches of the tcgen05 engine on
+ * device-resident random operands, C[M,N] = A[M,K] * B[N,K]^T, returns the mean milliseconds per launch and the chosen
+ * configuration (BN, CTA group, split-K). */
+int mpn_gemm_bench(mpn_ctx *ctx, int64_t M, int64_t N, int64_t K, int32_t iters, double *ms_per_launch,
+                   int32_t *bn, int32_t *cta_group, int32_t *splitk);
+/* conv microbenchmark with pipeline-wait counters of CTA 0 (3x3 A-reuse kernel only; all zero otherwise):
+ * dbg[0..2] producer {wait emptyA, wait emptyB, total}, [3..6] MMA issuer {wait fullA, wait fullB, wait tempty, total},
+ * [7..9] epilogue warp {wait tfull, store time, total} — SM cycles summed over the launch. */
+int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride,
+                   int32_t pad, int32_t iters, double *ms_per_launch, int32_t *bn, int32_t *cta_group, int32_t *mode,
+                   uint64_t *dbg16);
 /* standalone conv check entry (tests): x N x Cin x H x W, w Cout x Cin x kh x kw (Torch layouts) */
 int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t H, int64_t W,
                    const float *w, const float *bias, int64_t Cout, int32_t kh, int32_t kw,

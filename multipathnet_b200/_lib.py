@@ -96,6 +96,9 @@ SIGNATURES = {
     "mpn_model_get_trunk_slot": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p, _i32p]),
     "mpn_model_set_conv_impl": (C.c_int, [_vp, C.c_int32]),
     "mpn_model_last_flops": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mpn_gemm_bench": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_double), _i32p, _i32p, _i32p]),
+    "mpn_conv_bench": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.POINTER(C.c_double), _i32p, _i32p, _i32p, C.POINTER(C.c_uint64)]),
     "mpn_gemm_check": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _vp]),
     "mpn_conv_check": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, C.c_int64,
                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
@@ -263,6 +266,17 @@ class Context:
         out = np.empty((m, n), dtype=np.float32)
         self.check(self.lib.mpn_gemm_check(self.h, _ptr(A), _ptr(B), _ptr(bias), m, n, k, int(relu), impl, _ptr(out)), "mpn_gemm_check")
         return out
+
+    def gemm_bench(self, M, N, K, iters=20):
+        ms = C.c_double(); bn = C.c_int32(); cg = C.c_int32(); sk = C.c_int32()
+        self.check(self.lib.mpn_gemm_bench(self.h, M, N, K, iters, C.byref(ms), C.byref(bn), C.byref(cg), C.byref(sk)), "mpn_gemm_bench")
+        return ms.value, bn.value, cg.value, sk.value
+
+    def conv_bench(self, N, Cin, H, W, Cout, k=3, stride=1, pad=1, iters=20):
+        ms = C.c_double(); bn = C.c_int32(); cg = C.c_int32(); mode = C.c_int32(); dbg = (C.c_uint64 * 16)()
+        self.check(self.lib.mpn_conv_bench(self.h, N, Cin, H, W, Cout, k, stride, pad, iters, C.byref(ms), C.byref(bn), C.byref(cg),
+                                           C.byref(mode), dbg), "mpn_conv_bench")
+        return ms.value, bn.value, cg.value, mode.value, [int(x) for x in dbg]
 
     def conv_check(self, x, w, bias=None, stride=1, pad=0, relu=False, impl=0) -> np.ndarray:
         x, w = _f32(x), _f32(w)

@@ -369,6 +369,91 @@ int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t
   return MPN_OK;
 }
 
+int mpn_gemm_bench(mpn_ctx *ctx, int64_t M, int64_t N, int64_t K, int32_t iters, double *ms_per_launch, int32_t *bn,
+                   int32_t *cta_group, int32_t *splitk) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, M > 0 && N > 0 && K > 0 && K % 64 == 0 && iters > 0 && ms_per_launch, "bad arguments");
+  const size_t na = (size_t)(M * K), nb = (size_t)(N * K), nc = (size_t)(M * N);
+  Arena a{ctx};
+  size_t o_ah = a.reserve(2 * na), o_al = a.reserve(2 * na), o_bh = a.reserve(2 * nb), o_bl = a.reserve(2 * nb),
+         o_ch = a.reserve(2 * nc + 64), o_cl = a.reserve(2 * nc + 64);
+  MPN_TRY(a.commit());
+  // operand contents do not matter for timing; 0x3c00-ish bf16 patterns keep everything finite
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_ah), 0x3c, 2 * na, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_al), 0x30, 2 * na, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_bh), 0x3c, 2 * nb, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_bl), 0x30, 2 * nb, ctx->stream));
+  ConvProblem p;
+  p.x.hi = a.at<__nv_bfloat16>(o_ah); p.x.lo = a.at<__nv_bfloat16>(o_al); p.x.N = M; p.x.H = 1; p.x.W = 1; p.x.C = K; p.x.ld = K;
+  p.w_hi = a.at<__nv_bfloat16>(o_bh); p.w_lo = a.at<__nv_bfloat16>(o_bl); p.Cout = (int)N; p.relu = 1;
+  const int64_t Npad = (N + 7) / 8 * 8;
+  (void)Npad;
+  if (N % 8 == 0) { p.y.hi = a.at<__nv_bfloat16>(o_ch); p.y.lo = a.at<__nv_bfloat16>(o_cl); }
+  else { p.y.f32 = a.at<float>(o_ch); }
+  p.y.N = M; p.y.H = 1; p.y.W = 1; p.y.C = N; p.y.ld = N; p.y_f32_ld = N;
+  if (!(N % 8 == 0)) MPN_CHECK_ARG(ctx, 4 * nc <= 2 * (2 * nc + 64), "internal");
+  ConvPlan pl;
+  MPN_TRY(conv_tc_plan(ctx, p, pl));
+  if (bn) *bn = pl.BN; if (cta_group) *cta_group = pl.CG; if (splitk) *splitk = pl.splitk;
+  for (int i = 0; i < 3; ++i) MPN_TRY(conv_tc_launch(ctx, p, pl));
+  cudaEvent_t e0, e1;
+  MPN_CUDA(ctx, cudaEventCreate(&e0)); MPN_CUDA(ctx, cudaEventCreate(&e1));
+  MPN_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < iters; ++i) MPN_TRY(conv_tc_launch(ctx, p, pl));
+  MPN_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  MPN_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  MPN_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / iters;
+  return MPN_OK;
+}
+
+int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride,
+                   int32_t pad, int32_t iters, double *ms_per_launch, int32_t *bn, int32_t *cta_group, int32_t *mode,
+                   uint64_t *dbg16) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, N > 0 && Cin % 64 == 0 && Cout % 8 == 0 && iters > 0 && ms_per_launch, "bad arguments");
+  const int64_t Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const size_t nx = (size_t)(N * H * W * Cin), nw = (size_t)(Cout * Cin * k * k), ny = (size_t)(N * Ho * Wo * Cout);
+  Arena a{ctx};
+  size_t o_xh = a.reserve(2 * nx), o_xl = a.reserve(2 * nx), o_wh = a.reserve(2 * nw), o_wl = a.reserve(2 * nw),
+         o_yh = a.reserve(2 * ny), o_yl = a.reserve(2 * ny), o_dbg = a.reserve(16 * 8);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_xh), 0x3c, 2 * nx, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_xl), 0x30, 2 * nx, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_wh), 0x3c, 2 * nw, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_wl), 0x30, 2 * nw, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(a.at<char>(o_dbg), 0, 128, ctx->stream));
+  ConvProblem p;
+  p.x.hi = a.at<__nv_bfloat16>(o_xh); p.x.lo = a.at<__nv_bfloat16>(o_xl); p.x.N = N; p.x.H = H; p.x.W = W; p.x.C = Cin; p.x.ld = Cin;
+  p.w_hi = a.at<__nv_bfloat16>(o_wh); p.w_lo = a.at<__nv_bfloat16>(o_wl); p.Cout = (int)Cout; p.kh = k; p.kw = k; p.stride = stride; p.pad = pad; p.relu = 1;
+  p.y.hi = a.at<__nv_bfloat16>(o_yh); p.y.lo = a.at<__nv_bfloat16>(o_yl); p.y.N = N; p.y.H = Ho; p.y.W = Wo; p.y.C = Cout; p.y.ld = Cout;
+  ConvPlan pl;
+  MPN_TRY(conv_tc_plan(ctx, p, pl));
+  if (bn) *bn = pl.BN; if (cta_group) *cta_group = pl.CG; if (mode) *mode = pl.mode;
+  for (int i = 0; i < 3; ++i) MPN_TRY(conv_tc_launch(ctx, p, pl));
+  cudaEvent_t e0, e1;
+  MPN_CUDA(ctx, cudaEventCreate(&e0)); MPN_CUDA(ctx, cudaEventCreate(&e1));
+  MPN_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  for (int i = 0; i < iters; ++i) MPN_TRY(conv_tc_launch(ctx, p, pl));
+  MPN_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  MPN_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  MPN_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / iters;
+  if (dbg16) {       // one extra, instrumented launch
+    p.dbg = a.at<char>(o_dbg);
+    MPN_TRY(conv_tc_launch(ctx, p, pl));
+    MPN_CUDA(ctx, cudaMemcpyAsync(dbg16, a.at<char>(o_dbg), 128, cudaMemcpyDeviceToHost, ctx->stream));
+    MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return MPN_OK;
+}
+
 int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bias, int64_t M, int64_t N, int64_t K,
                    int32_t relu, int32_t impl, float *C) {
   if (!ctx) return MPN_ERR_ARG;

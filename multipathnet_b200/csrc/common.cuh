@@ -25,7 +25,7 @@ struct mpn_ctx {
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
-  uint8_t tc_attr_set[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint8_t tc_attr_set[16] = {0};
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };
@@ -96,6 +96,14 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// two values at once: one packed conversion per plane (cvt.rn.bf16x2.f32), low half = first value
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi2, uint32_t &lo2) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  hi2 = *reinterpret_cast<const uint32_t *>(&h);
+  const float r0 = x0 - __uint_as_float(hi2 << 16), r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+  lo2 = *reinterpret_cast<const uint32_t *>(&l);
 }
 __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);

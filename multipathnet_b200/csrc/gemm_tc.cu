@@ -32,7 +32,8 @@ namespace {
 constexpr int BM = 128;          // UMMA M (pixels per tile)
 constexpr int BK = 64;           // bf16 elements per K block = one 128B swizzle row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 192;  // 6 warps
+constexpr int TC_THREADS = 320;  // 10 warps: TMA producer, MMA issuer, 8 epilogue (two per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB per plane
 
 // CG = CTAs per MMA (tcgen05 cta_group): with CG=2 a CTA pair shares one B tile (each CTA stages BN/2 rows),
@@ -41,7 +42,11 @@ __host__ __device__ constexpr int stage_bytes(int BN, int CG = 1) { return 2 * A
 __host__ __device__ constexpr int num_stages(int BN, int CG = 1) {
   return (196608 / stage_bytes(BN, CG)) > 4 ? 4 : (196608 / stage_bytes(BN, CG));
 }
-__host__ __device__ constexpr int tmem_cols(int BN) { return BN == 256 ? 512 : (BN == 128 ? 256 : 128); }
+// Accumulator rotation: back-to-back tcgen05.mma into the SAME TMEM accumulator serialise on its read-modify-write
+// latency (~117 cycles measured, independent of N), so for N <= 128 (32/64 cycles of tensor work per instruction) the
+// three bf16x3 products go to separate accumulators (3 for BN=64, 2 for BN=128) that the epilogue sums.
+__host__ __device__ constexpr int num_acc(int BN) { return BN == 256 ? 1 : (BN == 128 ? 2 : 3); }
+__host__ __device__ constexpr int tmem_cols(int BN) { return 512; }       // 2 buffers x num_acc(BN) x BN columns (384 or 512)
 
 struct TcParams {
   int N, Ho, Wo, Cout;           // output geometry (flat mode: N=1, Ho=1, Wo=pixels)
@@ -56,6 +61,7 @@ struct TcParams {
   int relu;
   int splitk, kb_per_split;      // split-K: unit = (tile, split); each split owns kb_per_split K blocks and writes raw fp32 partials
   long long split_stride;        // elements between the partial planes of consecutive splits (out_f32 is the workspace then)
+  unsigned long long *dbg;       // optional (diagnostics): CTA 0 accumulates cycles spent in each pipeline wait
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -86,6 +92,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   } while (!done);
+}
+// mbar_wait that accumulates the cycles it blocked (diagnostics only; `acc` lives in a register)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, unsigned long long &acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1,
                                             int c2, int c3) {
@@ -142,6 +155,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// one elected lane of a fully converged warp (the issuing code around it stays warp-uniform, so descriptors live in
+// uniform registers; issuing from `if (lane == 0)` made ptxas wrap EVERY tcgen05.mma in an ELECT + 5x R2UR.BROADCAST +
+// retry loop, ~117 cycles per instruction — the measured floor of the first engine versions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -190,6 +211,99 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- epilogue of one accumulator tile (shared by both kernels)
+// warp q reads its 32 TMEM lanes 32 columns at a time; + bias (+ residual) (ReLU); re-split to bf16 hi/lo and/or fp32
+template <int BN>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tmem_base, int q, int a, int nt, bool row_ok,
+                                                 long long pix, float *out_f32, int ch_first) {
+  // two warps share each TMEM lane quarter: this one takes chunks ch_first, ch_first + 2, ...
+#pragma unroll 1
+  for (int ch = ch_first; ch < BN / 32; ch += 2) {
+    uint32_t v[32];
+    const int col0 = nt * BN + ch * 32;
+    // bias for this chunk: fetched BEFORE the TMEM load so its latency hides behind tcgen05.ld / wait
+    float4 bq[8];
+    const bool bias_vec = (p.bias != nullptr) && (col0 + 32 <= p.Cout);
+    if (bias_vec) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) bq[t] = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + t);
+    }
+    constexpr int NACC = num_acc(BN);
+    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NACC * BN + ch * 32);
+    tc_ld32(tcol, v);
+    if (NACC >= 2) {                       // sum the per-product accumulators (fixed order: deterministic)
+      uint32_t w[32];
+      tc_ld32(tcol + BN, w);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+      if (NACC == 3) {
+        tc_ld32(tcol + 2 * BN, w);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+      }
+    } else {
+      tc_wait_ld();
+    }
+    if (row_ok && col0 < p.Cout) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {             // 8 output channels per group
+        const int c = col0 + g * 8;
+        if (c >= p.Cout) break;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
+        const bool full8 = (c + 8 <= p.Cout);
+        if (p.bias) {
+          if (bias_vec) {
+            const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          } else if (full8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + c + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          } else {
+            for (int e = 0; e < 8 && c + e < p.Cout; ++e) f[e] += __ldg(p.bias + c + e);
+          }
+        }
+        if (p.res_hi && full8) {
+          const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + c);
+          const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + c);
+          const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 x = bf16x2_to_float2(hh[t]), y = bf16x2_to_float2(ll[t]);
+            f[2 * t] += x.x + y.x; f[2 * t + 1] += x.y + y.y;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+        }
+        if (p.out_hi && full8) {
+          uint32_t oh[4], ol[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) split_bf16x2(f[2 * t], f[2 * t + 1], oh[t], ol[t]);      // packed cvt.rn.bf16x2.f32
+          *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        }
+        if (out_f32) {
+          float *o = out_f32 + pix * p.out_f32_ld + c;
+          if (full8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            reinterpret_cast<float4 *>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4 *>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            for (int e = 0; e < 8 && c + e < p.Cout; ++e) o[e] = f[e];
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -228,7 +342,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
     // full: one arrival per producing CTA (on the leader's barrier when CG=2); tempty: one per epilogue warp of the pair
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), CG); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * CG); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation is warp-collective (same warp id in both CTAs for CG=2); the same warp frees it
@@ -249,8 +363,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop uniformly; one elected lane issues) =====================
+    {
       uint32_t it = 0;
       for (int u = unit; u < total_tiles * p.splitk; u += num_units) {
         const int tile = u / p.splitk, split = u - tile * p.splitk;
@@ -265,21 +379,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
           const int khi = tap / p.kw, kwi = tap - khi * p.kw;
           const uint32_t sa = smem_base + (uint32_t)s * STAGE;
-          if (CG == 2) {
-            if (rank == 0) mbar_expect_tx(full_bar(s), (uint32_t)(2 * STAGE));      // bytes of BOTH CTAs land on the leader's barrier
-            else mbar_arrive_remote(full_bar(s), 0u);
-            const uint32_t lbar = leader_addr(full_bar(s));
-            tma_load_4d_2sm(sa, &tmA_hi, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-            tma_load_4d_2sm(sa + A_TILE_BYTES, &tmA_lo, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES, &tmB_hi, lbar, kb * BK, b_row0);
-            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, lbar, kb * BK, b_row0);
-          } else {
-            mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
-            tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-            tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
-            tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, b_row0);
-            tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, b_row0);
+          if (elect_one()) {
+            if (CG == 2) {
+              if (rank == 0) mbar_expect_tx(full_bar(s), (uint32_t)(2 * STAGE));      // bytes of BOTH CTAs land on the leader's barrier
+              else mbar_arrive_remote(full_bar(s), 0u);
+              const uint32_t lbar = leader_addr(full_bar(s));
+              tma_load_4d_2sm(sa, &tmA_hi, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+              tma_load_4d_2sm(sa + A_TILE_BYTES, &tmA_lo, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+              tma_load_2d_2sm(sa + 2 * A_TILE_BYTES, &tmB_hi, lbar, kb * BK, b_row0);
+              tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, lbar, kb * BK, b_row0);
+            } else {
+              mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
+              tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+              tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
+              tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, b_row0);
+              tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, b_row0);
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -292,27 +409,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       mbar_wait(tempty_bar(a), aph ^ 1u);        // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+      constexpr int NACC = num_acc(BN);
+      const uint32_t d_base = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(a * NACC * BN), 0);
+      const uint32_t d_lh = (NACC == 2) ? d_base + BN : d_base;                       // A_lo * B_hi
+      const uint32_t d_hl = (NACC >= 2) ? d_base + BN : d_base;                       // A_hi * B_lo
+      const uint32_t d_hh = (NACC == 3) ? d_base + 2 * BN : d_base;                   // A_hi * B_hi
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % S; const uint32_t ph = (it / S) & 1u;
         mbar_wait(full_bar(s), ph);                // TMA bytes landed
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_base + (uint32_t)s * STAGE;
-          const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
-          const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+        const uint32_t sa = __shfl_sync(0xffffffffu, smem_base + (uint32_t)s * STAGE, 0);      // warp-uniform by construction
+        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
+        const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
+        const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
+            const uint32_t later = ((kb - kb0) | k) != 0 ? 1u : 0u;     // 0 on the first k16 of the tile: zero-init
+            const uint32_t f_lh = later, f_hh = (NACC >= 2) ? later : 1u, f_hl = (NACC == 3) ? later : 1u;
             if (CG == 2) {
-              tc_mma_bf16_2sm(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - kb0) | k) != 0 ? 1u : 0u);
-              tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-              tc_mma_bf16_2sm(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+              tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+              tc_mma_bf16_2sm(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
+              tc_mma_bf16_2sm(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
             } else {
-              tc_mma_bf16(d_tmem, a_lo + adv, b_hi + adv, IDESC, ((kb - kb0) | k) != 0 ? 1u : 0u);
-              tc_mma_bf16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-              tc_mma_bf16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+              tc_mma_bf16(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+              tc_mma_bf16(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
+              tc_mma_bf16(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
             }
           }
           if (CG == 2) {                             // multicast: frees the stage / publishes the accumulator in BOTH CTAs
@@ -343,68 +466,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + ch * 32), v);
-        tc_wait_ld();
-        const int col0 = nt * BN + ch * 32;
-        if (row_ok && col0 < p.Cout) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {             // 8 output channels per group
-            const int c = col0 + g * 8;
-            if (c >= p.Cout) break;
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-            const bool full8 = (c + 8 <= p.Cout);
-            if (p.bias) {
-              if (full8) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + c));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + c + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              } else {
-                for (int e = 0; e < 8 && c + e < p.Cout; ++e) f[e] += __ldg(p.bias + c + e);
-              }
-            }
-            if (p.res_hi && full8) {
-              const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + c);
-              const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + c);
-              const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                float2 x = bf16x2_to_float2(hh[t]), y = bf16x2_to_float2(ll[t]);
-                f[2 * t] += x.x + y.x; f[2 * t + 1] += x.y + y.y;
-              }
-            }
-            if (p.relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-            }
-            if (p.out_hi && full8) {
-              uint32_t oh[4], ol[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(f[2 * t], h0, l0); split_bf16(f[2 * t + 1], h1, l1);
-                oh[t] = pack_bf16x2(h0, h1); ol[t] = pack_bf16x2(l0, l1);
-              }
-              *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-              *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            }
-            if (out_f32) {
-              float *o = out_f32 + pix * p.out_f32_ld + c;
-              if (full8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                reinterpret_cast<float4 *>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
-                reinterpret_cast<float4 *>(o)[1] = make_float4(f[4], f[5], f[6], f[7]);
-              } else {
-                for (int e = 0; e < 8 && c + e < p.Cout; ++e) o[e] = f[e];
-              }
-            }
-          }
-        }
-      }
+      tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                             // 4*CG arrivals (one per epilogue warp of the pair) free the buffer
@@ -415,6 +477,233 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 
   // ---- teardown: everyone (both CTAs) done with TMEM / peer smem / peer barriers before anything is freed
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- 3x3 / stride 1 / pad 1 convolution with A-tile reuse
+// The generic kernel re-fetches the 128-pixel A tile for each of the 9 filter taps. Here the M tile is a 16-row x 8-col
+// patch, so one 8-row group of the UMMA A operand = one image row of the patch, and a vertical tap shift (kh) is a shift
+// by whole 1024-byte groups of the SAME smem tile: per 64-channel block only THREE A boxes are fetched (kw = 0,1,2;
+// each {64 ch, 8 px, 18 rows} = 18 groups), and the three kh taps read it through descriptors offset by kh*1024 B
+// (group-aligned, so the 128B swizzle phase is untouched). A traffic drops from 9 x 32 KB to 3 x 36 KB per channel
+// block; B (one tile per tap) streams through its own ring. Two rings, two barrier families.
+constexpr int R3_A_PLANE = 18 * 1024;            // 18 rows x 8 px x 128 B
+constexpr int R3_A_STAGE = 2 * R3_A_PLANE;       // hi + lo
+__host__ __device__ constexpr int r3_b_stage(int BN, int CG) { return 2 * (BN / CG) * BK * 2; }
+__host__ __device__ constexpr int r3_sa(int BN, int CG) { return (BN / CG) >= 128 ? 2 : 3; }
+__host__ __device__ constexpr int r3_sb(int BN, int CG) {
+  return (196608 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 8 ? 8 : (196608 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
+}
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const TcParams p) {
+  constexpr int SA = r3_sa(BN, CG), SB = r3_sb(BN, CG);
+  constexpr int B_STAGE = r3_b_stage(BN, CG);
+  constexpr int B_TILE_BYTES = B_STAGE / 2;
+  constexpr uint32_t IDESC = make_idesc(BM * CG, BN);
+  static_assert(SB >= 2, "B ring too shallow");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)SA * R3_A_STAGE + (size_t)SB * B_STAGE);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * SA + 2 * SB + 4);
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t b_base = a_base + (uint32_t)SA * R3_A_STAGE;
+  const uint32_t bar_base = smem_u32(bars);
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (2 * SA + SB + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_m = p.tiles_img * p.tiles_h * p.tiles_w;
+  const int tiles_mu = (tiles_m + CG - 1) / CG;
+  const int total_tiles = tiles_mu * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_hi); prefetch_tmap(&tmB_lo);
+    for (int s = 0; s < SA; ++s) { mbar_init(fullA(s), CG); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(fullB(s), CG); mbar_init(emptyB(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)tmem_cols(BN)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool trace = (p.dbg != nullptr) && (blockIdx.x == 0);
+  unsigned long long wc0 = 0ull, wc1 = 0ull, wc2 = 0ull;
+  const long long t_start = clock64();
+  if (warp == 0) {
+    // ===================== TMA producer: A ring (one box per kw) + B ring (one tile per tap) =====================
+    // (whole warp runs the loop uniformly; one elected lane issues)
+    {
+      uint32_t itA = 0, itB = 0;
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
+        const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
+        const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+        const int w0 = twi * 8, h0 = thi * 16, n0 = tni;
+        const int b_row0 = nt * BN + (int)rank * (BN / CG);
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int kwi = 0; kwi < 3; ++kwi) {
+            {
+              const int s = itA % SA; const uint32_t ph = (itA / SA) & 1u;
+              mbar_wait_t(emptyA(s), ph ^ 1u, wc0, trace);
+              const uint32_t sa = a_base + (uint32_t)s * R3_A_STAGE;
+              if (elect_one()) {
+                if (CG == 2) {
+                  if (rank == 0) mbar_expect_tx(fullA(s), (uint32_t)(2 * R3_A_STAGE)); else mbar_arrive_remote(fullA(s), 0u);
+                  const uint32_t lbar = leader_addr(fullA(s));
+                  tma_load_4d_2sm(sa, &tmA_hi, lbar, cb * BK, w0 + kwi - 1, h0 - 1, n0);
+                  tma_load_4d_2sm(sa + R3_A_PLANE, &tmA_lo, lbar, cb * BK, w0 + kwi - 1, h0 - 1, n0);
+                } else {
+                  mbar_expect_tx(fullA(s), (uint32_t)R3_A_STAGE);
+                  tma_load_4d(sa, &tmA_hi, fullA(s), cb * BK, w0 + kwi - 1, h0 - 1, n0);
+                  tma_load_4d(sa + R3_A_PLANE, &tmA_lo, fullA(s), cb * BK, w0 + kwi - 1, h0 - 1, n0);
+                }
+              }
+              __syncwarp();
+              ++itA;
+            }
+            for (int khi = 0; khi < 3; ++khi, ++itB) {
+              const int s = itB % SB; const uint32_t ph = (itB / SB) & 1u;
+              mbar_wait_t(emptyB(s), ph ^ 1u, wc1, trace);
+              const uint32_t sb = b_base + (uint32_t)s * B_STAGE;
+              const int kcol = ((khi * 3 + kwi) * p.cblocks + cb) * BK;          // weights are [Cout][(kh,kw,ci)]
+              if (elect_one()) {
+                if (CG == 2) {
+                  if (rank == 0) mbar_expect_tx(fullB(s), (uint32_t)(2 * B_STAGE)); else mbar_arrive_remote(fullB(s), 0u);
+                  const uint32_t lbar = leader_addr(fullB(s));
+                  tma_load_2d_2sm(sb, &tmB_hi, lbar, kcol, b_row0);
+                  tma_load_2d_2sm(sb + B_TILE_BYTES, &tmB_lo, lbar, kcol, b_row0);
+                } else {
+                  mbar_expect_tx(fullB(s), (uint32_t)B_STAGE);
+                  tma_load_2d(sb, &tmB_hi, fullB(s), kcol, b_row0);
+                  tma_load_2d(sb + B_TILE_BYTES, &tmB_lo, fullB(s), kcol, b_row0);
+                }
+              }
+              __syncwarp();
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t itA = 0, itB = 0, lt = 0;
+    for (int tile = unit; rank == 0 && tile < total_tiles; tile += num_units, ++lt) {
+      const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
+      mbar_wait_t(tempty_bar(a), aph ^ 1u, wc2, trace);
+      tc_fence_after();
+      constexpr int NACC = num_acc(BN);
+      const uint32_t d_base = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(a * NACC * BN), 0);
+      const uint32_t d_lh = (NACC == 2) ? d_base + BN : d_base;
+      const uint32_t d_hl = (NACC >= 2) ? d_base + BN : d_base;
+      const uint32_t d_hh = (NACC == 3) ? d_base + 2 * BN : d_base;
+      uint32_t first = 1u;
+      for (int cb = 0; cb < p.cblocks; ++cb)
+        for (int kwi = 0; kwi < 3; ++kwi, ++itA) {
+          const int sA = itA % SA; const uint32_t phA = (itA / SA) & 1u;
+          mbar_wait_t(fullA(sA), phA, wc0, trace);
+          for (int khi = 0; khi < 3; ++khi, ++itB) {
+            const int sB = itB % SB; const uint32_t phB = (itB / SB) & 1u;
+            mbar_wait_t(fullB(sB), phB, wc1, trace);
+            tc_fence_after();
+            // rows khi*8 .. khi*8+127 of the A box; all values warp-uniform by construction
+            const uint32_t sa = __shfl_sync(0xffffffffu, a_base + (uint32_t)sA * R3_A_STAGE + (uint32_t)khi * 1024u, 0);
+            const uint32_t sb = __shfl_sync(0xffffffffu, b_base + (uint32_t)sB * B_STAGE, 0);
+            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + R3_A_PLANE);
+            const uint64_t b_hi = make_smem_desc(sb), b_lo = make_smem_desc(sb + B_TILE_BYTES);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                const uint32_t later = (first && k == 0) ? 0u : 1u;
+                const uint32_t f_lh = later, f_hh = (NACC >= 2) ? later : 1u, f_hl = (NACC == 3) ? later : 1u;
+                if (CG == 2) {
+                  tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                  tc_mma_bf16_2sm(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
+                  tc_mma_bf16_2sm(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
+                } else {
+                  tc_mma_bf16(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                  tc_mma_bf16(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
+                  tc_mma_bf16(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
+                }
+              }
+              const bool last = (cb == p.cblocks - 1) && (kwi == 2) && (khi == 2);
+              if (CG == 2) {
+                tc_commit_2sm(emptyB(sB));
+                if (khi == 2) tc_commit_2sm(emptyA(sA));
+                if (last) tc_commit_2sm(tfull_bar(a));
+              } else {
+                tc_commit(emptyB(sB));
+                if (khi == 2) tc_commit(emptyA(sA));
+                if (last) tc_commit(tfull_bar(a));
+              }
+            }
+            first = 0u;
+            __syncwarp();
+          }
+        }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5): identical to the generic kernel, patch = 16 rows x 8 cols =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int wl = row & 7, hl = row >> 3;
+    uint32_t lt = 0;
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++lt) {
+      const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
+      const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
+      const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
+      const int wo = twi * 8 + wl, ho = thi * 16 + hl, n = tni;
+      const bool row_ok = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
+      const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
+      mbar_wait_t(tfull_bar(a), aph, wc0, trace);
+      tc_fence_after();
+      { const long long te = clock64(); tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2); if (trace) wc1 += (unsigned long long)(clock64() - te); }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) mbar_arrive_remote(tempty_bar(a), 0u);
+        else mbar_arrive(tempty_bar(a));
+      }
+    }
+  }
+
+  if (trace && lane == 0) {
+    // dbg[0..2] producer: wait emptyA, wait emptyB, total; [3..6] MMA: wait fullA, fullB, tempty, total; [7..9] epilogue warp 2: wait tfull, store time, total
+    const unsigned long long tot = (unsigned long long)(clock64() - t_start);
+    if (warp == 0) { p.dbg[0] = wc0; p.dbg[1] = wc1; p.dbg[2] = tot; }
+    if (warp == 1) { p.dbg[3] = wc0; p.dbg[4] = wc1; p.dbg[5] = wc2; p.dbg[6] = tot; }
+    if (warp == 2) { p.dbg[7] = wc0; p.dbg[8] = wc1; p.dbg[9] = tot; }
+  }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
@@ -499,6 +788,28 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   return MPN_OK;
 }
 
+template <int BN, int CG>
+int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
+  const int smem = r3_sa(BN, CG) * R3_A_STAGE + r3_sb(BN, CG) * r3_b_stage(BN, CG) + 1024 + 512;
+  constexpr int slot = 8 + (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1);
+  if (!ctx->tc_attr_set[slot]) {
+    MPN_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ctx->tc_attr_set[slot] = 1;
+  }
+  const int tiles_m = pl.tiles_img * pl.tiles_h * pl.tiles_w;
+  const int units = ((tiles_m + CG - 1) / CG) * pl.tiles_n;
+  const int grid = std::min(units, ctx->sm_count / CG) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = (CG > 1) ? 1 : 0;
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
 }  // namespace
 
 double conv_flops(const ConvProblem &p) {
@@ -514,9 +825,59 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
   MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
   const int Ho = (int)p.y.H, Wo = (int)p.y.W, N = (int)p.y.N;
   pl.flat = (p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0) ? 1 : 0;
+  pl.mode = 0; pl.splitk = 1;
   cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];
+  int gtn = 1, gth = 1, gtw = BM;                       // generic-mode patch
+  if (!pl.flat) {
+    // choose the power-of-two patch tn x th x tw (=128) that wastes the fewest MMA rows
+    double best = -1.0;
+    for (int tw = 1; tw <= 128; tw <<= 1)
+      for (int th = 1; th * tw <= 128; th <<= 1) {
+        const int tn = 128 / (tw * th);
+        if (tw * p.stride > 256 || th * p.stride > 256) continue;
+        const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
+        const double util = (double)N * Ho * Wo / (double)(tiles * 128) + 1e-6 * tw;   // tie-break: wider rows
+        if (util > best) { best = util; gtn = tn; gth = th; gtw = tw; }
+      }
+  }
+  const long long P = (long long)p.x.N * p.x.H * p.x.W;
+  const long long g_tiles_m = pl.flat ? (P + BM - 1) / BM
+                                      : (long long)((Wo + gtw - 1) / gtw) * ((Ho + gth - 1) / gth) * ((N + gtn - 1) / gtn);
+  const bool r3_ok = (p.kh == 3 && p.kw == 3 && p.stride == 1 && p.pad == 1);
+  const long long r_tiles_m = (long long)((Wo + 7) / 8) * ((Ho + 15) / 16) * N;
+  // (mode, CG, BN): estimated cycles per 64-channel block and scheduling round =
+  //   max(MMA: taps * 6*BN, operand ingest: rows * 256 B / ~35 B per cycle per SM), rounds = ceil(units / (SMs / CG)).
+  //   generic: rows = taps * (128 + BN/CG);  3x3 A-reuse: rows = 3*144 + 9*BN/CG.
+  // CTA pairs (cta_group::2) halve the B rows per SM; the A-reuse kernel cuts the A rows 2.7x for 3x3 convs.
+  {
+    const char *env = getenv("MPN_TC_CTA_GROUP");                 // debug knobs: force the single-CTA / generic engines
+    const int max_cg = (env && env[0] == '1') ? 1 : 2;
+    const char *env3 = getenv("MPN_TC_R3");
+    const int max_mode = (r3_ok && !(env3 && env3[0] == '0')) ? 1 : 0;
+    const int taps = p.kh * p.kw;
+    double best = 1e300; int best_bn = 64, best_cg = 1, best_mode = 0;
+    for (int mode = 0; mode <= max_mode; ++mode) {
+      const long long tiles_m = mode ? r_tiles_m : g_tiles_m;
+      for (int cg = 1; cg <= max_cg; ++cg) {
+        if (cg == 2 && tiles_m < 2) continue;
+        for (int bn = 256; bn >= 64; bn >>= 1) {
+          if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
+          if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
+          const long long tn_ = (p.Cout + bn - 1) / bn;
+          const long long units = ((tiles_m + cg - 1) / cg) * tn_;
+          const long long slots = ctx->sm_count / cg;
+          const long long rounds = (units + slots - 1) / slots;
+          const double rows = mode ? (3.0 * 144 + 9.0 * bn / cg) : (double)taps * (128 + bn / cg);
+          const double cyc = std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
+          const double cost = (double)rounds * cyc;
+          if (cost < best * 0.999) { best = cost; best_bn = bn; best_cg = cg; best_mode = mode; }
+        }
+      }
+    }
+    pl.BN = best_bn; pl.CG = best_cg; pl.mode = best_mode;
+    pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
+  }
   if (pl.flat) {
-    const long long P = (long long)p.x.N * p.x.H * p.x.W;
     pl.tn = 1; pl.th = 1; pl.tw = BM;
     pl.tiles_img = 1; pl.tiles_h = 1; pl.tiles_w = (int)((P + BM - 1) / BM);
     dims[0] = (cuuint64_t)p.x.C; dims[1] = (cuuint64_t)P; dims[2] = 1; dims[3] = 1;
@@ -524,54 +885,24 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     box[0] = BK; box[1] = BM; box[2] = 1; box[3] = 1;
     estr[0] = estr[1] = estr[2] = estr[3] = 1;
   } else {
-    // choose the power-of-two patch tn x th x tw (=128) that wastes the fewest MMA rows
-    double best = -1.0; int btn = 1, bth = 1, btw = 128;
-    for (int tw = 1; tw <= 128; tw <<= 1)
-      for (int th = 1; th * tw <= 128; th <<= 1) {
-        const int tn = 128 / (tw * th);
-        if (tw * p.stride > 256 || th * p.stride > 256) continue;
-        const long long tiles = (long long)((Wo + tw - 1) / tw) * ((Ho + th - 1) / th) * ((N + tn - 1) / tn);
-        const double util = (double)N * Ho * Wo / (double)(tiles * 128) + 1e-6 * tw;   // tie-break: wider rows
-        if (util > best) { best = util; btn = tn; bth = th; btw = tw; }
-      }
-    pl.tn = btn; pl.th = bth; pl.tw = btw;
-    pl.tiles_w = (Wo + btw - 1) / btw; pl.tiles_h = (Ho + bth - 1) / bth; pl.tiles_img = (N + btn - 1) / btn;
+    if (pl.mode == 1) { pl.tn = 1; pl.th = 16; pl.tw = 8; }
+    else { pl.tn = gtn; pl.th = gth; pl.tw = gtw; }
+    pl.tiles_w = (Wo + pl.tw - 1) / pl.tw; pl.tiles_h = (Ho + pl.th - 1) / pl.th; pl.tiles_img = (N + pl.tn - 1) / pl.tn;
     dims[0] = (cuuint64_t)p.x.C; dims[1] = (cuuint64_t)p.x.W; dims[2] = (cuuint64_t)p.x.H; dims[3] = (cuuint64_t)p.x.N;
     strides[0] = (cuuint64_t)p.x.ld * 2; strides[1] = (cuuint64_t)p.x.W * p.x.ld * 2;
     strides[2] = (cuuint64_t)p.x.H * p.x.W * p.x.ld * 2;
-    box[0] = BK; box[1] = (cuuint32_t)(btw * p.stride); box[2] = (cuuint32_t)(bth * p.stride); box[3] = (cuuint32_t)btn;
+    if (pl.mode == 1) { box[0] = BK; box[1] = 8; box[2] = 18; box[3] = 1; }       // patch + one halo row above and below
+    else { box[0] = BK; box[1] = (cuuint32_t)(pl.tw * p.stride); box[2] = (cuuint32_t)(pl.th * p.stride); box[3] = (cuuint32_t)pl.tn; }
     estr[0] = 1; estr[1] = (cuuint32_t)p.stride; estr[2] = (cuuint32_t)p.stride; estr[3] = 1;
   }
-  // (CG, BN): cost model per K block and scheduling round = operand rows landing in each SM: 128 (A) + BN/CG (B);
-  // rounds = ceil(units / (SMs / CG)). The engine is operand-ingest-bound (~35 B/cycle/SM measured), so CTA pairs
-  // (tcgen05 cta_group::2, B tile split across the pair) win whenever there are >= 2 m-tiles.
-  // e.g. VGG conv5 (19 m-tiles): 1-CTA BN=256 -> 38 CTAs; pair BN=128 -> 40 pairs = 80 CTAs at 2/3 of the bytes.
-  {
-    const long long tiles_m = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
-    const char *env = getenv("MPN_TC_CTA_GROUP");                 // debug knob: "1" forces the single-CTA engine
-    const int max_cg = (env && env[0] == '1') ? 1 : 2;
-    double best = 1e300; int best_bn = 64, best_cg = 1;
-    for (int cg = 1; cg <= max_cg; ++cg) {
-      if (cg == 2 && tiles_m < 2) continue;
-      for (int bn = 256; bn >= 64; bn >>= 1) {
-        if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
-        const long long tn_ = (p.Cout + bn - 1) / bn;
-        const long long units = ((tiles_m + cg - 1) / cg) * tn_;
-        const long long slots = ctx->sm_count / cg;
-        const long long rounds = (units + slots - 1) / slots;
-        const double cost = (double)rounds * (128 + bn / cg);
-        if (cost < best - 1e-9) { best = cost; best_bn = bn; best_cg = cg; }
-      }
-    }
-    pl.BN = best_bn; pl.CG = best_cg;
-    pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
+  if (pl.mode == 0) {
     // split-K for GEMMs too small to fill the machine (cls/bbox heads: 4-8 units, 64 K blocks each, latency-bound):
-    // as many splits as there are idle unit slots, at least 8 K blocks per split
+    // the split count depends on K only (so results do not change with the number of rows, as long as the GEMM stays
+    // small); it is either that value or 1
+    const long long tiles_m = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
     const long long units = ((tiles_m + pl.CG - 1) / pl.CG) * pl.tiles_n;
     const long long slots = ctx->sm_count / pl.CG;
     const long long num_kb = (long long)p.kh * p.kw * (p.x.C / BK);
-    // the split count depends on K only (so results do not change with the number of rows, as long as the GEMM stays
-    // small); it is either that value or 1
     long long sk = std::min<long long>(num_kb / 8, 8);
     if (sk < 2 || units * sk > slots) sk = 1;
     const char *env2 = getenv("MPN_TC_SPLITK");
@@ -579,6 +910,8 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     pl.splitk = (int)std::max<long long>(sk, 1);
     pl.kb_per_split = (int)((num_kb + pl.splitk - 1) / pl.splitk);
     pl.splitk = (int)((num_kb + pl.kb_per_split - 1) / pl.kb_per_split);     // no empty splits
+  } else {
+    pl.splitk = 1; pl.kb_per_split = 9 * (int)(p.x.C / BK);
   }
   MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
   MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));
@@ -607,6 +940,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.out_f32 = p.y.f32; tp.out_f32_ld = p.y_f32_ld;
   tp.relu = p.relu;
   tp.splitk = pl.splitk; tp.kb_per_split = pl.kb_per_split; tp.split_stride = 0;
+  tp.dbg = (unsigned long long *)p.dbg;
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
   if (pl.splitk > 1) {
     // partial accumulators go to a dense fp32 workspace [split][pixel][Cout]; bias/residual/ReLU/output split move to the reduce
@@ -627,6 +961,10 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(r);
     MPN_LAUNCHED(ctx);
     return MPN_OK;
+  }
+  if (pl.mode == 1) {
+    if (pl.CG == 2) return pl.BN == 256 ? launch_r3<256, 2>(ctx, pl, tp) : (pl.BN == 128 ? launch_r3<128, 2>(ctx, pl, tp) : launch_r3<64, 2>(ctx, pl, tp));
+    return pl.BN == 128 ? launch_r3<128, 1>(ctx, pl, tp) : launch_r3<64, 1>(ctx, pl, tp);
   }
   if (pl.CG == 2) {
     switch (pl.BN) {
