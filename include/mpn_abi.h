@@ -196,7 +196,9 @@ int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, in
 int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_t capacity,
                              int32_t *C, int32_t *H, int32_t *W);
 /* select conv/GEMM implementation: 0 = tcgen05 tensor-core path (default, product),
- * 1 = plain fp32 CUDA-core check kernel (debug/verification only, very slow). */
+ * 1 = plain fp32 CUDA-core check kernel (debug/verification only, very slow),
+ * 2 = tcgen05 path with the conv -> 2x2 max-pool epilogue fusion disabled, so every trunk slot is
+ *     materialised (mpn_model_get_trunk_slot fails loudly for a slot the fusion elided). */
 int mpn_model_set_conv_impl(mpn_model *m, int32_t impl);
 /* algorithmic FLOPs of the last trunk / heads call (SURVEY 8d definition)    */
 int mpn_model_last_flops(const mpn_model *m, double *trunk_flops, double *head_flops);
@@ -212,7 +214,8 @@ int mpn_gemm_bench(mpn_ctx *ctx, int64_t M, int64_t N, int64_t K, int32_t iters,
                    int32_t *bn, int32_t *cta_group, int32_t *splitk);
 /* conv microbenchmark with pipeline-wait counters of CTA 0 (3x3 A-reuse kernel only; all zero otherwise):
  * dbg[0..2] producer {wait emptyA, wait emptyB, total}, [3..6] MMA issuer {wait fullA, wait fullB, wait tempty, total},
- * [7..9] epilogue warp {wait tfull, store time, total} — SM cycles summed over the launch. */
+ * [7..9] epilogue warp {wait tfull, store time, total} — SM cycles summed over the launch.
+ * *mode: bit 0 = 3x3 A-reuse kernel, bit 4 = stream-K schedule. */
 int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride,
                    int32_t pad, int32_t iters, double *ms_per_launch, int32_t *bn, int32_t *cta_group, int32_t *mode,
                    uint64_t *dbg16);

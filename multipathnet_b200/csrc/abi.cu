@@ -87,6 +87,8 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
   if (ctx->scratch3) cudaFree(ctx->scratch3);
+  if (ctx->sk_ws) cudaFree(ctx->sk_ws);
+  if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
@@ -433,7 +435,7 @@ int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, i
   p.y.hi = a.at<__nv_bfloat16>(o_yh); p.y.lo = a.at<__nv_bfloat16>(o_yl); p.y.N = N; p.y.H = Ho; p.y.W = Wo; p.y.C = Cout; p.y.ld = Cout;
   ConvPlan pl;
   MPN_TRY(conv_tc_plan(ctx, p, pl));
-  if (bn) *bn = pl.BN; if (cta_group) *cta_group = pl.CG; if (mode) *mode = pl.mode;
+  if (bn) *bn = pl.BN; if (cta_group) *cta_group = pl.CG; if (mode) *mode = pl.mode | (pl.streamk << 4);
   for (int i = 0; i < 3; ++i) MPN_TRY(conv_tc_launch(ctx, p, pl));
   cudaEvent_t e0, e1;
   MPN_CUDA(ctx, cudaEventCreate(&e0)); MPN_CUDA(ctx, cudaEventCreate(&e1));

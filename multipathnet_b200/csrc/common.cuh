@@ -26,6 +26,8 @@ struct mpn_ctx {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   uint8_t tc_attr_set[16] = {0};
+  // stream-K (gemm_tc.cu): per-CTA partial-tile slots + per-(CTA, epilogue warp) flags holding the launch epoch
+  float *sk_ws = nullptr; unsigned *sk_flags = nullptr; unsigned sk_epoch = 0;
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };

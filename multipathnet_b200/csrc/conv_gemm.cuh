@@ -15,6 +15,8 @@ struct ConvProblem {
   DTensor res;                     // optional residual (split planes), same geometry as y
   DTensor y;                       // output: split planes (hi/lo) and/or f32; y.ld / f32_ld = pixel strides
   int64_t y_f32_ld = 0;
+  DTensor pool;                    // optional: 2x2/2 ceil max pool of y written by the epilogue (3x3 tcgen05 kernel only)
+  int pool_only = 0;               // 1: y itself is not written (nobody else reads it)
   void *dbg = nullptr;             // diagnostics: device buffer of 16 x u64 pipeline-wait counters (tools/engine_sweep.py)
 };
 
@@ -26,6 +28,7 @@ struct ConvPlan {
   int tn = 0, th = 0, tw = 0;      // 128 output pixels per M tile = tn*th*tw
   int tiles_img = 0, tiles_h = 0, tiles_w = 0, tiles_n = 0;
   int splitk = 1, kb_per_split = 0; // split-K over K blocks for tiny GEMMs (deterministic two-pass reduce)
+  int streamk = 0;                 // 3x3 kernel: contiguous (tile, step) ranges per CTA pair instead of whole tiles (no wave quantisation)
   int mode = 0;                    // 0 generic implicit GEMM, 1 = 3x3/s1/p1 A-reuse kernel (conv3x3_tc_kernel)
   int flat = 0;                    // 1: 1x1/s1/p0 => pixels treated as one flat axis
   int valid = 0;

@@ -58,11 +58,55 @@ struct TcParams {
   const __nv_bfloat16 *res_hi, *res_lo; long long res_ld;
   __nv_bfloat16 *out_hi, *out_lo; long long out_ld;
   float *out_f32; long long out_f32_ld;
+  __nv_bfloat16 *pool_hi, *pool_lo; long long pool_ld; int Hp, Wp;   // fused 2x2/2 max pool of the output (3x3 kernel only)
   int relu;
   int splitk, kb_per_split;      // split-K: unit = (tile, split); each split owns kb_per_split K blocks and writes raw fp32 partials
   long long split_stride;        // elements between the partial planes of consecutive splits (out_f32 is the workspace then)
   unsigned long long *dbg;       // optional (diagnostics): CTA 0 accumulates cycles spent in each pipeline wait
+  // stream-K (3x3 kernel): the (tile, step) space is cut into one contiguous range per CTA pair; a range that starts
+  // inside a tile writes its raw fp32 partial to sk_ws and raises sk_flags (= sk_epoch), the range that starts the tile
+  // adds the partials in pair order (fixed => deterministic) and runs the real epilogue.
+  int streamk; unsigned sk_epoch; float *sk_ws; unsigned *sk_flags;
 };
+
+// Work walk of one scheduling unit (CTA or CTA pair). Plain: tiles unit, unit + num_units, ... each with all S steps.
+// stream-K: the contiguous range [W*unit/num_units, W*(unit+1)/num_units) of the W = tiles*S (tile, step) space, visited
+// in ROTATED order: (1) the piece that continues a tile begun by the previous unit (its partial is published first, nobody
+// ever waits long for it), (2) the head piece of the tile the NEXT unit finishes (merging the partials then overlaps the
+// MMAs of what follows instead of sitting at the end of the kernel), (3) the whole tiles in between.
+struct SegWalk {
+  long long w, wend, cE, hS, w0, w1; int S, tile_step, phase; bool sk;
+  __device__ SegWalk(bool sk_, int unit, int num_units, int total_tiles, int S_) : S(S_), tile_step(num_units), phase(0), sk(sk_) {
+    if (sk) {
+      const long long W = (long long)total_tiles * S;
+      w0 = W * unit / num_units; w1 = W * (unit + 1) / num_units;
+      const long long te = (w0 / S + 1) * S;
+      cE = (w0 % S) ? (te < w1 ? te : w1) : w0;
+      const long long ts = (w1 / S) * S;
+      hS = ((w1 % S) && ts >= cE) ? ts : w1;
+      w = cE; wend = hS;
+    } else { w = unit; wend = total_tiles; }
+  }
+  __device__ bool emit(long long a, long long b, int &tile, int &s0, int &s1) {
+    tile = (int)(a / S); s0 = (int)(a - (long long)tile * S); s1 = s0 + (int)(b - a);
+    return true;
+  }
+  __device__ bool next(int &tile, int &s0, int &s1) {
+    if (!sk) {
+      if (w >= wend) return false;
+      tile = (int)w; s0 = 0; s1 = S; w += tile_step;
+      return true;
+    }
+    if (phase == 0) { phase = 1; if (cE > w0) return emit(w0, cE, tile, s0, s1); }
+    if (phase == 1) { phase = 2; if (hS < w1) return emit(hS, w1, tile, s0, s1); }
+    if (w >= wend) return false;
+    emit(w, w + S, tile, s0, s1); w += S;
+    return true;
+  }
+};
+// epilogue role of a segment
+struct EpiSk { int role = 0; float4 *part_out = nullptr; const float4 *part_in = nullptr; long long part_stride4 = 0; int ncont = 0; };
+enum { SK_FULL = 0, SK_WRITER = 1, SK_FINISHER = 2 };
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -215,7 +259,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 // warp q reads its 32 TMEM lanes 32 columns at a time; + bias (+ residual) (ReLU); re-split to bf16 hi/lo and/or fp32
 template <int BN>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tmem_base, int q, int a, int nt, bool row_ok,
-                                                 long long pix, float *out_f32, int ch_first) {
+                                                 long long pix, float *out_f32, int ch_first, long long ppix = -1,
+                                                 const EpiSk sk = EpiSk()) {
+  // fused 2x2/2 max pool (3x3 kernel: lane = (h & 3) * 8 + w of a 16 x 8 patch, so a window is lanes {l, l^1, l^8});
+  // ppix = pooled pixel this lane writes (its window's top-left lane), -1 otherwise. pool is warp-uniform.
+  const bool pool = (p.pool_hi != nullptr);
   // two warps share each TMEM lane quarter: this one takes chunks ch_first, ch_first + 2, ...
 #pragma unroll 1
   for (int ch = ch_first; ch < BN / 32; ch += 2) {
@@ -246,7 +294,29 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
     } else {
       tc_wait_ld();
     }
-    if (row_ok && col0 < p.Cout) {
+    if (sk.role != SK_FULL) {
+      // partial tiles live as [chunk][float4 j][128 rows] so that a warp's 32 rows are 512 contiguous bytes
+      const int r128 = q * 32 + (int)(threadIdx.x & 31);
+      if (sk.role == SK_WRITER) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sk.part_out[(ch * 8 + j) * 128 + r128] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        continue;
+      }
+      for (int t = 0; t < sk.ncont; ++t) {            // fixed order: pair u+1, u+2, ...
+        const float4 *pi = sk.part_in + (long long)t * sk.part_stride4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = __ldcg(pi + (ch * 8 + j) * 128 + r128);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x.w);
+        }
+      }
+    }
+    if ((row_ok || pool) && col0 < p.Cout) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {             // 8 output channels per group
         const int c = col0 + g * 8;
@@ -269,7 +339,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
             for (int e = 0; e < 8 && c + e < p.Cout; ++e) f[e] += __ldg(p.bias + c + e);
           }
         }
-        if (p.res_hi && full8) {
+        if (p.res_hi && full8 && row_ok) {
           const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + c);
           const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + c);
           const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
@@ -283,14 +353,31 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
         }
-        if (p.out_hi && full8) {
+        if (p.out_hi && full8 && row_ok) {
           uint32_t oh[4], ol[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) split_bf16x2(f[2 * t], f[2 * t + 1], oh[t], ol[t]);      // packed cvt.rn.bf16x2.f32
           *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
         }
-        if (out_f32) {
+        if (pool) {
+          // rows outside the image hold bias-only garbage: exclude them (ceil-mode windows at odd borders)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = row_ok ? f[e] : -INFINITY;
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+            x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+            f[e] = x;
+          }
+          if (ppix >= 0 && full8) {
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) split_bf16x2(f[2 * t], f[2 * t + 1], oh[t], ol[t]);
+            *reinterpret_cast<uint4 *>(p.pool_hi + ppix * p.pool_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            *reinterpret_cast<uint4 *>(p.pool_lo + ppix * p.pool_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+          }
+        }
+        if (out_f32 && row_ok) {
           float *o = out_f32 + pix * p.out_f32_ld + c;
           if (full8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
             reinterpret_cast<float4 *>(o)[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -361,6 +448,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+  // tail of the previous kernel in the stream; no global memory is touched before the previous grid has completed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop uniformly; one elected lane issues) =====================
@@ -557,6 +648,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+  // tail of the previous kernel in the stream; no global memory is touched before the previous grid has completed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const bool trace = (p.dbg != nullptr) && (blockIdx.x == 0);
   unsigned long long wc0 = 0ull, wc1 = 0ull, wc2 = 0ull;
@@ -566,13 +661,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     // (whole warp runs the loop uniformly; one elected lane issues)
     {
       uint32_t itA = 0, itB = 0;
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
+      SegWalk walk(p.streamk != 0, unit, num_units, total_tiles, 3 * p.cblocks);
+      int tile, s0, s1;
+      while (walk.next(tile, s0, s1)) {
         const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
         const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
         const int w0 = twi * 8, h0 = thi * 16, n0 = tni;
         const int b_row0 = nt * BN + (int)rank * (BN / CG);
-        for (int cb = 0; cb < p.cblocks; ++cb)
-          for (int kwi = 0; kwi < 3; ++kwi) {
+        for (int st = s0; st < s1; ++st) {            // step = (channel block, kw): one A box, three B tiles
+            const int cb = st / 3, kwi = st - cb * 3;
             {
               const int s = itA % SA; const uint32_t ph = (itA / SA) & 1u;
               mbar_wait_t(emptyA(s), ph ^ 1u, wc0, trace);
@@ -617,7 +714,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     uint32_t itA = 0, itB = 0, lt = 0;
-    for (int tile = unit; rank == 0 && tile < total_tiles; tile += num_units, ++lt) {
+    SegWalk walk(p.streamk != 0, unit, num_units, total_tiles, 3 * p.cblocks);
+    int tile, s0, s1;
+    for (; rank == 0 && walk.next(tile, s0, s1); ++lt) {
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       mbar_wait_t(tempty_bar(a), aph ^ 1u, wc2, trace);
       tc_fence_after();
@@ -627,8 +726,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const uint32_t d_hl = (NACC >= 2) ? d_base + BN : d_base;
       const uint32_t d_hh = (NACC == 3) ? d_base + 2 * BN : d_base;
       uint32_t first = 1u;
-      for (int cb = 0; cb < p.cblocks; ++cb)
-        for (int kwi = 0; kwi < 3; ++kwi, ++itA) {
+      for (int st = s0; st < s1; ++st, ++itA) {
           const int sA = itA % SA; const uint32_t phA = (itA / SA) & 1u;
           mbar_wait_t(fullA(sA), phA, wc0, trace);
           for (int khi = 0; khi < 3; ++khi, ++itB) {
@@ -656,7 +754,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   tc_mma_bf16(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
                 }
               }
-              const bool last = (cb == p.cblocks - 1) && (kwi == 2) && (khi == 2);
+              const bool last = (st == s1 - 1) && (khi == 2);
               if (CG == 2) {
                 tc_commit_2sm(emptyB(sB));
                 if (khi == 2) tc_commit_2sm(emptyA(sA));
@@ -678,17 +776,55 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int row = q * 32 + lane;
     const int wl = row & 7, hl = row >> 3;
     uint32_t lt = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++lt) {
+    const int S3 = 3 * p.cblocks;
+    SegWalk walk(p.streamk != 0, unit, num_units, total_tiles, S3);
+    int tile, s0, s1;
+    const long long slot4 = (long long)BN * 32;                 // float4 per CTA partial tile (128 rows x BN fp32)
+    for (; walk.next(tile, s0, s1); ++lt) {
       const int a = lt & 1; const uint32_t aph = (lt >> 1) & 1u;
       const int nt = tile % p.tiles_n, mt = (tile / p.tiles_n) * CG + (int)rank;
       const int twi = mt % p.tiles_w, thi = (mt / p.tiles_w) % p.tiles_h, tni = mt / (p.tiles_w * p.tiles_h);
       const int wo = twi * 8 + wl, ho = thi * 16 + hl, n = tni;
+      EpiSk sk;
+      if (p.streamk) {
+        float4 *ws4 = reinterpret_cast<float4 *>(p.sk_ws);
+        if (s0 > 0) {
+          sk.role = SK_WRITER; sk.part_out = ws4 + (long long)(unit * CG + (int)rank) * slot4;
+        } else if (s1 < S3) {
+          // the rest of this tile belongs to the following pairs (their FIRST segment, so it is long done or in flight)
+          sk.role = SK_FINISHER; sk.part_in = ws4 + (long long)((unit + 1) * CG + (int)rank) * slot4; sk.part_stride4 = CG * slot4;
+          const long long W = (long long)total_tiles * S3, tend = (long long)(tile + 1) * S3;
+          int nc = 0;
+          for (int v = unit + 1; v < num_units && W * v / num_units < tend; ++v) ++nc;
+          sk.ncont = nc;
+          if (lane == 0) {
+            for (int t = 0; t < nc; ++t) {
+              const unsigned *f = p.sk_flags + ((long long)((unit + 1 + t) * CG + (int)rank)) * EPI_WARPS + (warp - 2);
+              unsigned got, spins = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(got) : "l"(f) : "memory");
+                if (got != p.sk_epoch && ++spins == (1u << 24)) { printf("[mpn] stream-K flag wait timed out: block %d warp %d\n", (int)blockIdx.x, warp); __trap(); }
+              } while (got != p.sk_epoch);
+            }
+          }
+          __syncwarp();
+        }
+      }
       const bool row_ok = (wo < p.Wo) && (ho < p.Ho) && (n < p.N);
       const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
+      const long long ppix = (p.pool_hi && row_ok && !(lane & 9)) ? ((long long)n * p.Hp + (ho >> 1)) * p.Wp + (wo >> 1) : -1;
       mbar_wait_t(tfull_bar(a), aph, wc0, trace);
       tc_fence_after();
-      { const long long te = clock64(); tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2); if (trace) wc1 += (unsigned long long)(clock64() - te); }
+      { const long long te = clock64(); tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk); if (trace) wc1 += (unsigned long long)(clock64() - te); }
       tc_fence_before();
+      if (sk.role == SK_WRITER) {                  // publish the partial: data, fence, then the flag (release)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          unsigned *f = p.sk_flags + ((long long)(unit * CG + (int)rank)) * EPI_WARPS + (warp - 2);
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(p.sk_epoch) : "memory");
+        }
+      }
       __syncwarp();
       if (lane == 0) {
         if (CG == 2 && rank != 0) mbar_arrive_remote(tempty_bar(a), 0u);
@@ -766,6 +902,12 @@ int encode_map(mpn_ctx *ctx, CUtensorMap *tm, const void *base, int rank, const 
   return MPN_OK;
 }
 
+// MPN_TC_PDL=0 disables programmatic dependent launch (debug knob)
+inline bool tc_use_pdl() {
+  static const int on = [] { const char *e = getenv("MPN_TC_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+
 template <int BN, int CG>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + 1024 /*align*/ + 256 /*barriers*/;
@@ -779,10 +921,19 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   const int grid = std::min(units, ctx->sm_count / CG) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = (CG > 1) ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (tc_use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
@@ -798,13 +949,22 @@ int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   }
   const int tiles_m = pl.tiles_img * pl.tiles_h * pl.tiles_w;
   const int units = ((tiles_m + CG - 1) / CG) * pl.tiles_n;
-  const int grid = std::min(units, ctx->sm_count / CG) * CG;
+  const int grid = (pl.streamk ? ctx->sm_count / CG : std::min(units, ctx->sm_count / CG)) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = (CG > 1) ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CG > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CG; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (tc_use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr; cfg.numAttrs = na;
   MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
@@ -855,7 +1015,10 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     const char *env3 = getenv("MPN_TC_R3");
     const int max_mode = (r3_ok && !(env3 && env3[0] == '0')) ? 1 : 0;
     const int taps = p.kh * p.kw;
-    double best = 1e300; int best_bn = 64, best_cg = 1, best_mode = 0;
+    double best = 1e300; int best_bn = 64, best_cg = 1, best_mode = 0, best_sk = 0;
+    const double cblocks = (double)(p.x.C / BK);
+    const char *env4 = getenv("MPN_TC_STREAMK");
+    const bool allow_sk = !(env4 && env4[0] == '0');
     for (int mode = 0; mode <= max_mode; ++mode) {
       const long long tiles_m = mode ? r_tiles_m : g_tiles_m;
       for (int cg = 1; cg <= max_cg; ++cg) {
@@ -869,12 +1032,23 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
           const long long rounds = (units + slots - 1) / slots;
           const double rows = mode ? (3.0 * 144 + 9.0 * bn / cg) : (double)taps * (128 + bn / cg);
           const double cyc = std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
-          const double cost = (double)rounds * cyc;
-          if (cost < best * 0.999) { best = cost; best_bn = bn; best_cg = cg; best_mode = mode; }
+          double cost = (double)rounds * cyc * cblocks;
+          int sk = 0;
+          if (mode == 1 && allow_sk) {
+            // stream-K: no round quantisation, but one partial-tile exchange per pair (~6k cycles) and >= 4 steps per pair
+            // (measured: merging one partial costs the finisher ~40 cycles per accumulator column; it is hidden behind the
+            //  following tiles unless a pair's whole range is shorter than about two tiles)
+            const double S3 = 3.0 * cblocks, steps_per_unit = (double)units * S3 / (double)slots;
+            const double pieces = std::max(1.0, S3 / steps_per_unit);
+            const double exposed = (steps_per_unit < 2.0 * S3) ? 40.0 * bn * pieces : 3000.0;
+            const double cost_sk = (double)units * cyc * cblocks / (double)slots + 3000.0 + exposed;
+            if (steps_per_unit >= 4.0 && cost_sk < 0.95 * cost) { cost = cost_sk; sk = 1; }
+          }
+          if (cost < best * 0.999) { best = cost; best_bn = bn; best_cg = cg; best_mode = mode; best_sk = sk; }
         }
       }
     }
-    pl.BN = best_bn; pl.CG = best_cg; pl.mode = best_mode;
+    pl.BN = best_bn; pl.CG = best_cg; pl.mode = best_mode; pl.streamk = best_sk;
     pl.tiles_n = (p.Cout + pl.BN - 1) / pl.BN;
   }
   if (pl.flat) {
@@ -941,6 +1115,24 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.relu = p.relu;
   tp.splitk = pl.splitk; tp.kb_per_split = pl.kb_per_split; tp.split_stride = 0;
   tp.dbg = (unsigned long long *)p.dbg;
+  tp.pool_hi = tp.pool_lo = nullptr; tp.pool_ld = 0; tp.Hp = tp.Wp = 0;
+  tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
+  if (pl.streamk && pl.mode == 1) {
+    if (!ctx->sk_ws) {
+      MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_ws, (size_t)ctx->sm_count * 128 * 256 * sizeof(float)));
+      MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_flags, (size_t)ctx->sm_count * EPI_WARPS * sizeof(unsigned)));
+      MPN_CUDA(ctx, cudaMemsetAsync(ctx->sk_flags, 0, (size_t)ctx->sm_count * EPI_WARPS * sizeof(unsigned), ctx->stream));
+    }
+    tp.streamk = 1; tp.sk_epoch = ++ctx->sk_epoch; tp.sk_ws = ctx->sk_ws; tp.sk_flags = ctx->sk_flags;
+  }
+  if (p.pool.hi) {
+    // fused 2x2/2 (ceil) max pool: the 3x3 kernel's 16 x 8 patches start at even coordinates, so no window straddles tiles
+    MPN_CHECK_ARG(ctx, pl.mode == 1 && pl.splitk == 1 && !p.res.hi && p.Cout % 8 == 0 && p.pool.ld % 8 == 0,
+                  "conv_tc: fused pooling needs the 3x3 kernel, no residual, Cout multiple of 8");
+    MPN_CHECK_ARG(ctx, p.pool.H == (p.y.H + 1) / 2 && p.pool.W == (p.y.W + 1) / 2 && p.pool.N == p.y.N, "conv_tc: pooled geometry mismatch");
+    tp.pool_hi = p.pool.hi; tp.pool_lo = p.pool.lo; tp.pool_ld = p.pool.ld; tp.Hp = (int)p.pool.H; tp.Wp = (int)p.pool.W;
+    if (p.pool_only) { tp.out_hi = tp.out_lo = nullptr; tp.out_f32 = nullptr; }
+  }
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
   if (pl.splitk > 1) {
     // partial accumulators go to a dense fp32 workspace [split][pixel][Cout]; bias/residual/ReLU/output split move to the reduce

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <map>
 #include <memory>
+#include <set>
 
 // launchers defined in the other TUs
 int mpn_maxpool_launch(mpn_ctx *, const DTensor &, int, int, int, DTensor &);
@@ -59,6 +60,10 @@ struct LayerExec {
   ConvPlan plan;
   bool is_direct = false;  // Cin not a multiple of 64: CUDA-core direct conv from the NCHW fp32 image
   DTensor in, out;
+  // conv -> 2x2/2 max pool fusion (trunk): the conv's epilogue also writes the NEXT layer's (pool) output;
+  // pool_only: the full-resolution conv output has no other reader and is not written at all.
+  bool fused_pool = false, pool_only = false;
+  DTensor pool_out_t;
 };
 
 int pool_out(int in, int k, int s, int p, int ceil_mode) {
@@ -86,6 +91,7 @@ struct mpn_model {
   std::vector<LayerExec> trunk_exec;
   std::map<int, DTensor> trunk_slots; std::map<int, std::unique_ptr<SplitBuf>> trunk_bufs;
   DevBuf image_dev;
+  std::set<int> elided_slots;      // conv outputs the last trunk forward did not materialise (conv+pool fusion)
   double trunk_flops = 0, head_flops = 0;
   // max pyramids of the trunk slots that towers pool from (roi.cu): level k>=1 buffers per slot
   struct Pyramid { std::vector<std::unique_ptr<SplitBuf>> lv; int nlev = 1; };
@@ -215,6 +221,27 @@ int plan_trunk(mpn_model *m, int H, int W) {
     m->trunk_slots[L.out_slot] = out;
     m->trunk_exec.push_back(e);
   }
+  // conv(3x3 tcgen05 kernel) immediately followed by a 2x2/2 pad-0 max pool of its output: fuse the pool into the epilogue
+  {
+    const char *envf = getenv("MPN_TC_FUSE_POOL");
+    const bool allow = !(envf && envf[0] == '0');
+    for (size_t i = 0; allow && i + 1 < m->trunk_exec.size(); ++i) {
+      LayerExec &c = m->trunk_exec[i]; const LayerExec &q = m->trunk_exec[i + 1];
+      if (c.L.kind != MPN_LAYER_CONV || c.is_direct || q.L.kind != MPN_LAYER_MAXPOOL) continue;
+      if (q.L.in_slot != c.L.out_slot || q.L.kh != 2 || q.L.kw != 2 || q.L.stride != 2 || q.L.pad != 0) continue;
+      if (c.plan.mode != 1 || c.plan.splitk != 1 || c.L.residual_slot >= 0 || (c.L.cout % 8) != 0) continue;
+      if (q.out.H != (c.out.H + 1) / 2 || q.out.W != (c.out.W + 1) / 2) continue;      // floor-mode pools with odd sizes stay separate
+      bool other_reader = false;
+      for (size_t j = 0; j < m->trunk_exec.size(); ++j) {
+        if (j == i + 1) continue;
+        const mpn_layer &L2 = m->trunk_exec[j].L;
+        if (j > i && (L2.in_slot == c.L.out_slot || L2.residual_slot == c.L.out_slot)) other_reader = true;
+      }
+      for (const mpn_tower &T : m->towers)
+        for (int l = 0; l < T.n_levels; ++l) if (T.level_slot[l] == c.L.out_slot) other_reader = true;
+      c.fused_pool = true; c.pool_only = !other_reader; c.pool_out_t = q.out;
+    }
+  }
   // max pyramids for every slot a tower pools from: levels with 2^k <= min(H, W), at most ROI_MAX_LEVELS-1 extra copies
   for (const mpn_tower &T : m->towers)
     for (int l = 0; l < T.n_levels; ++l) {
@@ -237,8 +264,18 @@ int plan_trunk(mpn_model *m, int H, int W) {
 
 int run_trunk(mpn_model *m, const float *image_dev) {
   mpn_ctx *ctx = m->ctx;
-  for (LayerExec &e : m->trunk_exec) {
+  m->elided_slots.clear();
+  for (size_t li = 0; li < m->trunk_exec.size(); ++li) {
+    LayerExec &e = m->trunk_exec[li];
     const mpn_layer &L = e.L;
+    if (e.fused_pool && m->conv_impl == 0) {
+      ConvProblem pf = e.prob;
+      pf.pool = e.pool_out_t; pf.pool_only = e.pool_only ? 1 : 0;
+      MPN_TRY(conv_tc_launch(ctx, pf, e.plan));
+      if (e.pool_only) m->elided_slots.insert(L.out_slot);
+      ++li;                                  // the pool layer's output is already written
+      continue;
+    }
     if (L.kind == MPN_LAYER_CONV) {
       if (e.is_direct) {
         const float *bias = L.bias >= 0 ? (const float *)m->weights[L.bias]->f32.p : nullptr;
@@ -503,7 +540,7 @@ void mpn_model_destroy(mpn_model *m) {
 
 int mpn_model_set_conv_impl(mpn_model *m, int32_t impl) {
   if (!m) return MPN_ERR_ARG;
-  MPN_CHECK_ARG(m->ctx, impl == 0 || impl == 1, "impl must be 0 (tcgen05) or 1 (fp32 check kernel)");
+  MPN_CHECK_ARG(m->ctx, impl >= 0 && impl <= 2, "impl must be 0 (tcgen05), 1 (fp32 check kernel) or 2 (tcgen05 without conv+pool fusion)");
   m->conv_impl = impl;
   return MPN_OK;
 }
@@ -667,6 +704,8 @@ int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_
   mpn_ctx *ctx = m->ctx;
   MPN_CUDA(ctx, cudaSetDevice(ctx->device));
   MPN_CHECK_ARG(ctx, m->trunk_valid && slot > 0 && m->trunk_slots.count(slot), "unknown trunk slot or no trunk forward yet");
+  MPN_CHECK_ARG(ctx, !m->elided_slots.count(slot),
+                "trunk slot was fused into the following max pool and never written (mpn_model_set_conv_impl(m, 2) disables the fusion)");
   const DTensor &t = m->trunk_slots[slot];
   const int64_t n = t.N * t.C * t.H * t.W;
   if (C) *C = (int32_t)t.C; if (H) *H = (int32_t)t.H; if (W) *W = (int32_t)t.W;

@@ -186,7 +186,7 @@ constexpr int WARPK_THREADS = 256;
 
 struct WalkCtx {
   const unsigned long long *s_mask, *m; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
-  unsigned short *s_keep;
+  unsigned short *s_keep, *s_death, *s_qalt;
   int n, nwords, nwords_cap, use_smem_mask;
 };
 
@@ -218,7 +218,7 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
   }
   int nkeep = 0, hp = 0, replayed = 0;
   while (true) {
-    // ---- first live box in (score desc, row asc) order
+    // ---- first 64-row chunk (mask word cw) that still has a live box in (score desc, row asc) order
     unsigned ball = __ballot_sync(0xffffffffu, rem0 != ~0ull);
     int half = 0;
     if (!ball) {
@@ -227,13 +227,56 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
       if (!ball) break;
     }
     const int wl = __ffs(ball) - 1;
-    const unsigned long long aw = ~__shfl_sync(0xffffffffu, (TWO && half) ? rem1 : rem0, wl);
-    const int qb = __ffsll((long long)aw) - 1;
-    const int q = (wl + (TWO ? 32 * half : 0)) * 64 + qb;
+    const int cw = wl + (TWO ? 32 * half : 0);
+    const int row0 = cw * 64;
+    unsigned long long cur = __shfl_sync(0xffffffffu, (TWO && half) ? rem1 : rem0, wl);
+    const unsigned long long tw = TIE ? __shfl_sync(0xffffffffu, (TWO && half) ? tn1 : tn0, wl) : 0ull;
+    // ---- resolve the chunk's rows against each other. Every lane runs the SAME fully unrolled, branch-free chain on the
+    //      64 diagonal words (broadcast loads, no shuffles): ~15 cycles per row instead of one ~100-cycle round per kept box.
+    //      A live box whose score continues into the next row (tie) stops the chain: it takes the general round below.
+    unsigned long long kb = 0ull; int tie_b = -1;
+    {
+      unsigned long long dg[64];
+#pragma unroll
+      for (int b = 0; b < 64; ++b) dg[b] = mask_word(min(row0 + b, n - 1), cw);
+#pragma unroll
+      for (int b = 0; b < 64; ++b) {
+        const bool live = !((cur >> b) & 1ull) && (!TIE || tie_b < 0);
+        // tied with the next row; skipped when that row is already dead and the tie group ends there (the common pair case)
+        const bool pair_done = (b < 63) && ((cur >> ((b + 1) & 63)) & 1ull) && !((tw >> ((b + 1) & 63)) & 1ull);
+        const bool tie_here = TIE && live && ((tw >> b) & 1ull) && !pair_done;
+        if (tie_here) tie_b = b;
+        if (live && !tie_here) { kb |= 1ull << b; cur |= dg[b]; }
+      }
+    }
+    // ---- record the kept rows (emission order = ascending sorted position inside the chunk)
+    if ((kb >> lane) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << lane) - 1ull))] = (unsigned short)(row0 + lane);
+    if ((kb >> (lane + 32)) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << (lane + 32)) - 1ull))] = (unsigned short)(row0 + lane + 32);
+    nkeep += __popcll(kb);
+    // ---- deferred suppression: OR the kept rows into the words after cw (lane-parallel over words, loads batched by 8)
+    {
+      const bool on0 = (lane > cw) && (lane < nwords);
+      const bool on1 = TWO && (lane + 32 > cw) && (lane + 32 < nwords);
+      unsigned long long acc0 = 0ull, acc1 = 0ull;
+      if (kb) {
+#pragma unroll 8
+        for (int b = 0; b < 64; ++b) {
+          if ((kb >> b) & 1ull) {
+            if (on0) acc0 |= mask_word(row0 + b, lane);
+            if (on1) acc1 |= mask_word(row0 + b, lane + 32);
+          }
+        }
+      }
+      rem0 |= acc0; if (TWO) rem1 |= acc1;
+      if (lane == wl) { if (TWO && half) rem1 = cur; else rem0 = cur; }
+    }
+    if (!TIE || tie_b < 0) continue;
+    // ---- general round for a candidate with a tied successor (rare)
+    const int qb = tie_b;
+    const int q = row0 + qb;
     int pb = q;
     if (TIE) {
-      const unsigned long long tw = __shfl_sync(0xffffffffu, (TWO && half) ? tn1 : tn0, wl);
-      if ((tw >> qb) & 1ull) {           // q's score continues into q+1: is a tied box still alive? (rare path)
+      {                                  // q's score continues into q+1: is a tied box still alive?
         // publish the current removed-set so any lane can test liveness
         c.s_rrem[lane] = rem0; if (TWO) c.s_rrem[lane + 32] = rem1;
         __syncwarp();
@@ -244,42 +287,47 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
             if (!((c.s_rrem[r >> 6] >> (r & 63)) & 1ull)) { need = 1; break; }
         need = __shfl_sync(0xffffffffu, need, 0);
         if (need) {
-          // ---- replay rounds [replayed, nkeep): nms.c:83-86 moves the head (live occupant of the first live slot)
-          //      into the selected box's slot, every round
+          // ---- replay rounds [replayed, nkeep). (a) death round of every box removed in those rounds: the same mask rows
+          //      as the forward pass, word-parallel over lanes, recording the round that first sets each bit
           for (int tt = replayed; tt < nkeep; ++tt) {
-            const int pbt = c.s_keep[tt];
-            __syncwarp();
-            c.s_rrem[lane] = rr0; if (TWO) c.s_rrem[lane + 32] = rr1;
-            __syncwarp();
-            int head = -1;
-            while (true) {                                   // warp-parallel scan, 32 slots per step, monotone pointer
-              const int sl = hp + lane;
-              const int e = (sl < n) ? c.s_owner[sl] : -1;
-              const bool ok = (e >= 0) && !((c.s_rrem[e >> 6] >> (e & 63)) & 1ull);
-              const unsigned hb = __ballot_sync(0xffffffffu, ok);
-              if (hb) { const int first = __ffs(hb) - 1; head = __shfl_sync(0xffffffffu, e, first); hp += first; break; }
-              hp += 32;
-              if (hp >= n) break;
-            }
-            if (lane == 0 && head >= 0) {
-              const int lb = c.s_label[pbt];
-              if (head != pbt) { c.s_owner[lb] = head; c.s_label[head] = lb; }
-              c.s_owner[hp] = -1;
-            }
-            // first live box of that round (start of its tie group), then apply the round's suppression to the replay set
-            unsigned rb = __ballot_sync(0xffffffffu, rr0 != ~0ull); int rh = 0;
-            if (!rb && TWO) { rb = __ballot_sync(0xffffffffu, rr1 != ~0ull); rh = 1; }
-            const int rwl = __ffs(rb) - 1;
-            const unsigned long long raw = ~__shfl_sync(0xffffffffu, (TWO && rh) ? rr1 : rr0, rwl);
-            const int qt = (rwl + (TWO ? 32 * rh : 0)) * 64 + __ffsll((long long)raw) - 1;
+            const int kt = c.s_keep[tt];
+            const int pbt = kt & 0x7fff;
             const int wbt = pbt >> 6;
-            if (lane >= wbt && lane < nwords) rr0 |= mask_word(pbt, lane);
-            if (TWO && lane + 32 >= wbt && lane + 32 < nwords) rr1 |= mask_word(pbt, lane + 32);
-            for (int e = qt; e < pbt; ++e)
-              if ((mask_word(e, wbt) >> (pbt & 63)) & 1ull) {
-                if (lane == (e >> 6)) rr0 |= 1ull << (e & 63);
-                if (TWO && lane + 32 == (e >> 6)) rr1 |= 1ull << (e & 63);
-              }
+            if (lane >= wbt && lane < nwords) {
+              const unsigned long long mw = mask_word(pbt, lane);
+              unsigned long long nb = mw & ~rr0; rr0 |= mw;
+              while (nb) { const int bb = __ffsll((long long)nb) - 1; nb &= nb - 1ull; c.s_death[lane * 64 + bb] = (unsigned short)tt; }
+            }
+            if (TWO && lane + 32 >= wbt && lane + 32 < nwords) {
+              const unsigned long long mw = mask_word(pbt, lane + 32);
+              unsigned long long nb = mw & ~rr1; rr1 |= mw;
+              while (nb) { const int bb = __ffsll((long long)nb) - 1; nb &= nb - 1ull; c.s_death[(lane + 32) * 64 + bb] = (unsigned short)tt; }
+            }
+            if (kt & 0x8000) {                   // a tie round that did not pick the first live box: symmetric suppression of [q, pb)
+              const int qt = c.s_qalt[tt];
+              for (int e = qt; e < pbt; ++e)
+                if ((mask_word(e, wbt) >> (pbt & 63)) & 1ull) {
+                  if (lane == (e >> 6) && !((rr0 >> (e & 63)) & 1ull)) { rr0 |= 1ull << (e & 63); c.s_death[e] = (unsigned short)tt; }
+                  if (TWO && lane + 32 == (e >> 6) && !((rr1 >> (e & 63)) & 1ull)) { rr1 |= 1ull << (e & 63); c.s_death[e] = (unsigned short)tt; }
+                }
+            }
+          }
+          __syncwarp();
+          // (b) nms.c:83-86, every round: the head (live occupant of the first live slot) moves into the selected box's
+          //     slot. The head slot only moves forward. Every lane runs the same scalar walk and stores the same values
+          //     (later rounds never write what an earlier round reads), so no warp collective sits on this chain.
+          for (int tt = replayed; tt < nkeep; ++tt) {
+            const int pbt = c.s_keep[tt] & 0x7fff;
+            int head = -1;
+            while (hp < n) {
+              const int e = c.s_owner[hp];
+              if (e >= 0 && (int)c.s_death[e] >= tt) { head = e; break; }      // alive at the start of round tt
+              ++hp;
+            }
+            if (head < 0) break;
+            const int lb = c.s_label[pbt];
+            if (head != pbt) { c.s_owner[lb] = head; c.s_label[head] = lb; }
+            c.s_owner[hp] = -1;
           }
           replayed = nkeep;
           __syncwarp();
@@ -295,7 +343,10 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
         }
       }
     }
-    if (lane == 0) c.s_keep[nkeep] = (unsigned short)pb;       // no global access on the serial chain
+    if (lane == 0) {                                            // no global access on the serial chain
+      c.s_keep[nkeep] = (unsigned short)(pb | ((TIE && pb != q) ? 0x8000 : 0));
+      if (TIE && pb != q) c.s_qalt[nkeep] = (unsigned short)q;
+    }
     // ---- suppress: removed |= mask row of pb (upper triangle incl. the diagonal bit = pb itself)
     const int wb = pb >> 6;
     if (lane >= wb && lane < nwords) rem0 |= mask_word(pb, lane);
@@ -325,17 +376,19 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   if (n <= 0) { if (threadIdx.x == 0) keep_counts[seg] = 0; return; }
   const int nwords = (n + 63) >> 6;
   const bool tie = tie_flag[seg] != 0;
-  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap] [keep u16 cap]
+  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap] [keep u16 cap] [death u16 cap] [qalt u16 cap]
   unsigned long long *s_mask = s_dyn;
   unsigned long long *s_rrem = s_dyn + (use_smem_mask ? (size_t)cap * nwords_cap : 0);
   float *s_score = reinterpret_cast<float *>(s_rrem + 64);
   int *s_label = reinterpret_cast<int *>(s_score + cap);
   int *s_owner = s_label + cap;
   unsigned short *s_keep = reinterpret_cast<unsigned short *>(s_owner + cap);
+  unsigned short *s_death = s_keep + cap;      // round in which a box was removed (0xffff = alive); filled lazily by the tie replay
+  unsigned short *s_qalt = s_death + cap;
   const unsigned long long *m = mask + (size_t)seg * cap * nwords_cap;
   const int32_t *ord = order + (size_t)seg * cap;
   if (use_smem_mask) {
-#pragma unroll 4
+#pragma unroll 8
     for (int i = threadIdx.x; i < n * nwords; i += WARPK_THREADS) {
       const int r = i / nwords, w = i - r * nwords;
       s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;   // only the upper triangle was computed
@@ -348,18 +401,19 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
       s_score[p] = seg_sb[(size_t)o * 5 + 4];
       s_label[p] = o;            // slot label = position in the reference's pointer array
       s_owner[o] = p;            // slot -> sorted position of its occupant
+      s_death[p] = 0xffffu;
     }
   }
   __syncthreads();
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   int nkeep;
-  const WalkCtx wc{s_mask, m, s_score, s_label, s_owner, s_rrem, s_keep, n, nwords, nwords_cap, use_smem_mask};
+  const WalkCtx wc{s_mask, m, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
   if (tie) nkeep = (nwords > 32) ? nms_walk<true, true>(wc, lane) : nms_walk<true, false>(wc, lane);
   else nkeep = (nwords > 32) ? nms_walk<false, true>(wc, lane) : nms_walk<false, false>(wc, lane);
   __syncwarp();
   for (int k = lane; k < nkeep; k += 32) {
-    const int o = ord[s_keep[k]];
+    const int o = ord[s_keep[k] & 0x7fff];
     keep_idx[(size_t)seg * cap + k] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
   }
   if (lane == 0) keep_counts[seg] = nkeep;
@@ -476,17 +530,17 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   int32_t *tie = (int32_t *)(ws + o_tie);
   unsigned long long *mask = (unsigned long long *)(ws + o_mask);
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
-  MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));
+  const bool small = cap <= WARP_CAP;
+  if (!small) MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));   // the warp kernel writes every count
   dim3 g1((cap + RANK_THREADS - 1) / RANK_THREADS, nseg);
   nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
-  const bool small = cap <= WARP_CAP;
   nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, small ? 0 : 1, thr, mask);
   MPN_LAUNCHED(ctx);
   if (small) {
     const int use_smem_mask = cap <= WARP_SMEM_MASK_CAP ? 1 : 0;
-    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 14 + 64 * 8 + 64;
+    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 18 + 64 * 8 + 64;
     if (smem > 48 * 1024)
       MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nms_scan_warp_kernel<<<nseg, WARPK_THREADS, smem, ctx->stream>>>(mask, order, sb_dev, cap, nwords, use_smem_mask, counts_dev,

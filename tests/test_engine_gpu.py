@@ -79,3 +79,26 @@ def test_first_layer_direct_conv(ctx, Cin, Cout, k, s, p, H, W):
     ref = F.relu(F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=s, padding=p)).numpy()
     got = ctx.conv_check(x, w, b, stride=s, pad=p, relu=True, impl=2)
     assert rel_err(got, ref) < TOL
+
+
+@pytest.mark.parametrize("Cin,H,W,Cout", [(512, 38, 50, 512), (256, 150, 200, 256), (128, 75, 100, 256)])
+def test_streamk_schedule(ctx, Cin, H, W, Cout, monkeypatch):
+    """stream-K (contiguous (tile, step) ranges per CTA pair, partial tiles exchanged through L2 and summed in pair order):
+    chosen for these wave-quantised shapes, deterministic across launches, and equal to the whole-tile schedule up to
+    fp32 summation order."""
+    rng = np.random.default_rng(Cin + H)
+    x = rng.standard_normal((1, Cin, H, W)).astype(np.float32)
+    w = (rng.standard_normal((Cout, Cin, 3, 3)) / np.sqrt(Cin * 9)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    _, _, _, mode, _ = ctx.conv_bench(1, Cin, H, W, Cout, 3, 1, 1, 1)
+    assert mode & 16, "planner did not pick stream-K for a wave-quantised layer"
+    a1 = ctx.conv_check(x, w, b, stride=1, pad=1, relu=True, impl=0)
+    a2 = ctx.conv_check(x, w, b, stride=1, pad=1, relu=True, impl=0)
+    assert np.array_equal(a1, a2)
+    monkeypatch.setenv("MPN_TC_STREAMK", "0")
+    _, _, _, mode0, _ = ctx.conv_bench(1, Cin, H, W, Cout, 3, 1, 1, 1)
+    assert not (mode0 & 16)
+    a0 = ctx.conv_check(x, w, b, stride=1, pad=1, relu=True, impl=0)
+    assert rel_err(a1, a0) < 2e-5      # another BN => another accumulator grouping
+    ref = F.relu(F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=1)).float().numpy()
+    assert rel_err(a1, ref) < TOL

@@ -27,18 +27,35 @@ def small_vgg(ctx):
     m.close()
 
 
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 2, 0])
 def test_vgg_trunk_features(ctx, small_vgg, impl):
+    """impl 1 = fp32 check kernel, 2 = tcgen05 with every slot materialised, 0 = product (conv+pool fused:
+    conv3_3 / conv4_3 have no other reader in Fast R-CNN and are never written)."""
     spec, m = small_vgg
     m.set_conv_impl(impl)
     img, _ = _inputs(spec, 150, 203, 1, 1)
     m.trunk(img)
     ts = G.trunk_forward(spec, img)
     for name, slot in spec.taps.items():
+        if impl == 0 and name != "conv5":
+            with pytest.raises(RuntimeError, match="fused"):
+                m.trunk_slot(slot)
+            continue
         got, ref = m.trunk_slot(slot), ts[slot].numpy()
         assert got.shape == ref.shape, name
         assert rel_err(got, ref) < 2e-4, name
     m.set_conv_impl(0)
+
+
+def test_fused_pool_matches_separate_pool(ctx, small_vgg):
+    """conv epilogue pooling vs conv then maxpool_split_kernel (odd sizes exercise the ceil-mode borders). Not bit-identical:
+    the separate kernel re-splits hi+lo, which may pick another (hi, lo) pair for the same value when lo is exactly half an
+    ulp of hi, and the next conv's dropped lo*lo term differs at the 2^-17 level; a border bug would be O(1)."""
+    spec, m = small_vgg
+    img, _ = _inputs(spec, 150, 203, 1, 1)
+    m.set_conv_impl(2); m.trunk(img); a = m.trunk_slot(spec.taps["conv5"]).copy()
+    m.set_conv_impl(0); m.trunk(img); b = m.trunk_slot(spec.taps["conv5"])
+    assert rel_err(b, a) < 5e-5
 
 
 @pytest.mark.parametrize("impl", [1, 0])

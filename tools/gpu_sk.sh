@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
-python tools/conv_trace.py 2>&1 | cut -c1-400 | tee gpurun_out/conv_trace.log
-for f in test_engine_gpu test_model_gpu; do
+python tools/conv_trace.py 2>&1 | cut -c1-330 | tee gpurun_out/conv_trace.log
+MPN_TC_STREAMK=0 python tools/conv_trace.py 2>&1 | cut -c1-60 | tee gpurun_out/conv_trace_nosk.log
+for f in test_nms_gpu test_engine_gpu test_model_gpu; do
   timeout 1200 python -m pytest tests/$f.py -q -m gpu -p no:cacheprovider -x > gpurun_out/$f.log 2>&1
   echo "$f exit $?" >> gpurun_out/summary.txt; tail -6 gpurun_out/$f.log
 done
@@ -9,12 +10,9 @@ cat gpurun_out/summary.txt
 python bench.py --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"
 python - <<'PY'
 import json
-for c in ('n1',):
-    try:
-        d=json.load(open(f'gpurun_out/bench_{c}.json'))
-        print(c,'value',round(d['value']),'e2e',round(d['e2e']['value']),'ms/step',round(d['ms_per_step'],3))
-        print('  ',{k:round(v,4) for k,v in d['roofline']['by_category_ms_per_step'].items()}, 'issued',round(d['roofline']['issued_frac'],3))
-    except Exception as e: print(c,'ERR',e)
+d=json.load(open('gpurun_out/bench_n1.json'))
+print('value',round(d['value']),'e2e',round(d['e2e']['value']),'ms/step',round(d['ms_per_step'],3))
+print('  ',{k:round(v,4) for k,v in d['roofline']['by_category_ms_per_step'].items()}, 'issued',round(d['roofline']['issued_frac'],3))
 PY
 tail -n 3 gpurun_out/bench_n1.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 201 -c 48 --csv --log-file gpurun_out/launches.csv \
