@@ -54,14 +54,18 @@ __global__ void bbox_norm_kernel(float *__restrict__ d, int64_t n4, float4 mean,
 
 // ---- utils.convertFrom per class block (utils.lua:226-246, ImageDetect.lua:183-185) ----
 // optional clamp of Tester_FRCNN.lua:75-78 (x to [1,W0], y to [1,H0]).
-__global__ void bbox_decode_kernel(const float *__restrict__ deltas, const float *__restrict__ boxes,
-                                   int64_t R, int C, int do_clamp, float W0, float H0,
-                                   float *__restrict__ out) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// has_norm: apply nn.BBoxNorm (BBoxNorm.lua: y*std + mean, same op order as bbox_norm_kernel) to the raw deltas first
+__device__ __forceinline__ void bbox_decode_body(int64_t idx, const float *__restrict__ deltas, const float *__restrict__ boxes,
+                                                 int64_t R, int C, int do_clamp, float W0, float H0, float *__restrict__ out,
+                                                 int has_norm, float4 mean, float4 stdv) {
   if (idx >= R * C) return;
   int64_t i = idx / C;
   float4 b = reinterpret_cast<const float4 *>(boxes)[i];
   float4 y = reinterpret_cast<const float4 *>(deltas)[idx];
+  if (has_norm) {
+    y.x = __fadd_rn(__fmul_rn(y.x, stdv.x), mean.x); y.y = __fadd_rn(__fmul_rn(y.y, stdv.y), mean.y);
+    y.z = __fadd_rn(__fmul_rn(y.z, stdv.z), mean.z); y.w = __fadd_rn(__fmul_rn(y.w, stdv.w), mean.w);
+  }
   float xc = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f), yc = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
   float w = __fsub_rn(b.z, b.x), h = __fsub_rn(b.w, b.y);
   float xtc = __fadd_rn(xc, __fmul_rn(y.x, w)), ytc = __fadd_rn(yc, __fmul_rn(y.y, h));
@@ -76,14 +80,20 @@ __global__ void bbox_decode_kernel(const float *__restrict__ deltas, const float
   }
   reinterpret_cast<float4 *>(out)[idx] = o;
 }
+__global__ void bbox_decode_kernel(const float *__restrict__ deltas, const float *__restrict__ boxes,
+                                   int64_t R, int C, int do_clamp, float W0, float H0,
+                                   float *__restrict__ out) {
+  bbox_decode_body((int64_t)blockIdx.x * blockDim.x + threadIdx.x, deltas, boxes, R, C, do_clamp, W0, H0, out, 0,
+                   make_float4(0, 0, 0, 0), make_float4(1, 1, 1, 1));
+}
 
 // ---- nn.SoftMax over classes; with K>1 heads: mean over K of the K softmaxes ------------
 // (ImageDetect.lua:189-191; integral eval branch model_utils.lua:296-313). One warp per ROI.
 // logits laid out [K][R][C]. do_softmax=0 copies head 0 (model.noSoftMax with a single head).
-__global__ void softmax_mean_kernel(const float *__restrict__ logits, int64_t R, int C, int K,
-                                    int do_softmax, float *__restrict__ out) {
-  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+__device__ __forceinline__ void softmax_mean_body(int64_t tid, const float *__restrict__ logits, int64_t R, int C, int K,
+                                                  int do_softmax, float *__restrict__ out) {
+  int64_t row = tid >> 5;
+  int lane = (int)(tid & 31);
   if (row >= R) return;
   if (!do_softmax) {
     for (int c = lane; c < C; c += 32) out[row * C + c] = logits[row * C + c];
@@ -106,6 +116,18 @@ __global__ void softmax_mean_kernel(const float *__restrict__ logits, int64_t R,
     }
     if (c < C) out[row * C + c] = (K > 1) ? acc / (float)K : acc;
   }
+}
+__global__ void softmax_mean_kernel(const float *__restrict__ logits, int64_t R, int C, int K,
+                                    int do_softmax, float *__restrict__ out) {
+  softmax_mean_body((int64_t)blockIdx.x * blockDim.x + threadIdx.x, logits, R, C, K, do_softmax, out);
+}
+// detect tail in ONE launch: blocks [0, nb_sm) = class_values (softmax / mean of softmaxes), the rest = BBoxNorm + decode (+clamp)
+__global__ void __launch_bounds__(256)
+detect_tail_kernel(const float *__restrict__ logits, int64_t R, int C, int K, int do_softmax, float *__restrict__ scores,
+                   int nb_sm, const float *__restrict__ deltas, const float *__restrict__ boxes, int do_clamp, float W0,
+                   float H0, float *__restrict__ bboxes, int has_norm, float4 mean, float4 stdv) {
+  if ((int)blockIdx.x < nb_sm) softmax_mean_body((int64_t)blockIdx.x * 256 + threadIdx.x, logits, R, C, K, do_softmax, scores);
+  else bbox_decode_body((int64_t)(blockIdx.x - nb_sm) * 256 + threadIdx.x, deltas, boxes, R, C, do_clamp, W0, H0, bboxes, has_norm, mean, stdv);
 }
 
 // ---- Tester_FRCNN.lua:106-116: per foreground class j gather rows with score > thresh ----
@@ -300,6 +322,18 @@ int mpn_bbox_decode_launch(mpn_ctx *ctx, const float *deltas_dev, const float *b
   MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R * C <= 0) return MPN_OK;
   bbox_decode_kernel<<<nblk(R * C, 256), 256, 0, ctx->stream>>>(deltas_dev, boxes_dev, R, C, do_clamp, W0, H0, out_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+int mpn_detect_tail_launch(mpn_ctx *ctx, const float *logits_dev, int64_t R, int C, int K, int do_softmax, float *scores_dev,
+                           const float *deltas_dev, const float *boxes_dev, int do_clamp, float W0, float H0,
+                           float *bboxes_dev, int has_norm, const float *mean4, const float *std4) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
+  if (R <= 0) return MPN_OK;
+  const int nb_sm = (int)nblk(R * 32, 256), nb_dec = (int)nblk(R * C, 256);
+  detect_tail_kernel<<<nb_sm + nb_dec, 256, 0, ctx->stream>>>(
+      logits_dev, R, C, K, do_softmax, scores_dev, nb_sm, deltas_dev, boxes_dev, do_clamp, W0, H0, bboxes_dev, has_norm,
+      make_float4(mean4[0], mean4[1], mean4[2], mean4[3]), make_float4(std4[0], std4[1], std4[2], std4[3]));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }

@@ -23,6 +23,8 @@ int mpn_project_rois_launch(mpn_ctx *, const float *, int64_t, float, float *);
 int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
 int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
 int mpn_softmax_mean_launch(mpn_ctx *, const float *, int64_t, int, int, int, float *);
+int mpn_detect_tail_launch(mpn_ctx *, const float *, int64_t, int, int, int, float *, const float *, const float *, int, float, float,
+                           float *, int, const float *, const float *);
 int mpn_gather_scored_launch(mpn_ctx *, const float *, const float *, int, int, float, float *, int32_t *, int32_t *);
 int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
 
@@ -459,7 +461,7 @@ int plan_heads(mpn_model *m, int64_t R) {
   return MPN_OK;
 }
 
-int run_heads(mpn_model *m, const float *rois_dev, int64_t R) {
+int run_heads(mpn_model *m, const float *rois_dev, int64_t R, bool apply_bbox_norm = true) {
   mpn_ctx *ctx = m->ctx;
   const mpn_tower &T0 = m->towers[0];
   MPN_TRY(mpn_roi_pool_fused_launch(ctx, m->jobs, rois_dev, R, T0.pooled_w, T0.pooled_h, m->d.roi_variant));
@@ -475,7 +477,7 @@ int run_heads(mpn_model *m, const float *rois_dev, int64_t R) {
     }
   }
   for (LayerExec &e : m->head_exec) MPN_TRY(run_conv(m, e));
-  if (m->d.has_bbox_norm)
+  if (m->d.has_bbox_norm && apply_bbox_norm)
     MPN_TRY(mpn_bbox_norm_launch(ctx, (float *)m->bbox_raw.p, R, 4 * m->d.num_classes, m->d.bbox_mean, m->d.bbox_std));
   return MPN_OK;
 }
@@ -618,11 +620,13 @@ static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, floa
   MPN_TRY(ensure_heads(m, R));
   MPN_TRY(m->rois_dev.ensure(ctx, sizeof(float) * 5 * (size_t)R));
   MPN_TRY(mpn_project_rois_launch(ctx, boxes_dev, R, im_scale, (float *)m->rois_dev.p));
-  MPN_TRY(run_heads(m, (const float *)m->rois_dev.p, R));
-  // class_values: softmax unless model.noSoftMax; an integral head IS its mean of softmaxes (noSoftMax=true)
+  MPN_TRY(run_heads(m, (const float *)m->rois_dev.p, R, /*apply_bbox_norm=*/false));
+  // class_values: softmax unless model.noSoftMax; an integral head IS its mean of softmaxes (noSoftMax=true).
+  // One launch: softmax (+mean) | BBoxNorm + decode (+ clamp to the image for the NMS path, Tester_FRCNN.lua:75-78)
   const int do_softmax = (K > 1) ? 1 : (m->d.no_softmax ? 0 : 1);
-  MPN_TRY(mpn_softmax_mean_launch(ctx, (const float *)m->cls_logits.p, R, C, K, do_softmax, (float *)m->scores_dev.p));
-  MPN_TRY(mpn_bbox_decode_launch(ctx, (const float *)m->bbox_raw.p, boxes_dev, R, C, do_nms, W0, H0, (float *)m->bboxes_dev.p));
+  MPN_TRY(mpn_detect_tail_launch(ctx, (const float *)m->cls_logits.p, R, C, K, do_softmax, (float *)m->scores_dev.p,
+                                 (const float *)m->bbox_raw.p, boxes_dev, do_nms, W0, H0, (float *)m->bboxes_dev.p,
+                                 m->d.has_bbox_norm ? 1 : 0, m->d.bbox_mean, m->d.bbox_std));
   if (do_nms) {
     MPN_TRY(mpn_gather_scored_launch(ctx, (const float *)m->scores_dev.p, (const float *)m->bboxes_dev.p, (int)R, C,
                                      score_thresh, (float *)m->sb_dev.p, (int32_t *)m->src_idx_dev.p, (int32_t *)m->counts_dev.p));

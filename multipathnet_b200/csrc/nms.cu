@@ -37,43 +37,53 @@ __device__ __forceinline__ float iou_ref(float ax1, float ay1, float ax2, float 
 }
 
 constexpr int RANK_THREADS = 256;
+constexpr int RANK_ELEMS = 64;            // rows ranked per block; 4 threads per row, each scanning a quarter of every tile
 
-// grid (ceil(cap/256), nseg). rank[i] = #{j: s_j > s_i or (s_j == s_i and j < i)}.
+// grid (ceil(cap/64), nseg). rank[i] = #{j: s_j > s_i or (s_j == s_i and j < i)}.
 __global__ void __launch_bounds__(RANK_THREADS)
 nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict__ counts,
                 int32_t *__restrict__ order, float4 *__restrict__ sorted_boxes,
                 int32_t *__restrict__ tie_flag) {
   const int seg = blockIdx.y;
   const int n = counts ? counts[seg] : cap;
-  if ((int)blockIdx.x * RANK_THREADS >= n) return;
+  if ((int)blockIdx.x * RANK_ELEMS >= n) return;
   const float *seg_sb = sb + (size_t)seg * cap * 5;
-  __shared__ float s_tile[RANK_THREADS];
-  const int i = blockIdx.x * RANK_THREADS + threadIdx.x;
+  constexpr int TILE = 1024;
+  __shared__ float s_tile[TILE];
+  __shared__ int s_rank[RANK_ELEMS], s_tied[RANK_ELEMS];
+  const int el = threadIdx.x & (RANK_ELEMS - 1), part = threadIdx.x / RANK_ELEMS;
+  const int i = blockIdx.x * RANK_ELEMS + el;
   const bool valid = i < n;
   const float si = valid ? seg_sb[(size_t)i * 5 + 4] : 0.0f;
+  if (threadIdx.x < RANK_ELEMS) { s_rank[threadIdx.x] = 0; s_tied[threadIdx.x] = 0; }
   int rank = 0; int tied = 0;
-  for (int base = 0; base < n; base += RANK_THREADS) {
-    int j = base + threadIdx.x;
-    s_tile[threadIdx.x] = (j < n) ? seg_sb[(size_t)j * 5 + 4] : 0.0f;
+  for (int base = 0; base < n; base += TILE) {
+    for (int t = threadIdx.x; t < TILE; t += RANK_THREADS) {
+      const int j = base + t;
+      s_tile[t] = (j < n) ? seg_sb[(size_t)j * 5 + 4] : 0.0f;
+    }
     __syncthreads();
-    int lim = min(RANK_THREADS, n - base);
+    const int t0 = part * (TILE / 4), lim = min(TILE / 4, n - base - t0);
     if (valid) {
 #pragma unroll 8
       for (int t = 0; t < lim; ++t) {
-        float sj = s_tile[t];
-        int jj = base + t;
-        bool eq = (sj == si);
+        const float sj = s_tile[t0 + t];
+        const int jj = base + t0 + t;
+        const bool eq = (sj == si);
         rank += (sj > si) || (eq && jj < i);
         tied |= (eq && jj != i);
       }
     }
     __syncthreads();
   }
-  if (valid) {
-    order[(size_t)seg * cap + rank] = i;
+  if (valid) { atomicAdd(&s_rank[el], rank); if (tied) atomicOr(&s_tied[el], 1); }
+  __syncthreads();
+  if (valid && part == 0) {
+    const int r = s_rank[el];
+    order[(size_t)seg * cap + r] = i;
     const float *b = seg_sb + (size_t)i * 5;
-    sorted_boxes[(size_t)seg * cap + rank] = make_float4(b[0], b[1], b[2], b[3]);
-    if (tied) atomicOr(&tie_flag[seg], 1);
+    sorted_boxes[(size_t)seg * cap + r] = make_float4(b[0], b[1], b[2], b[3]);
+    if (s_tied[el]) atomicOr(&tie_flag[seg], 1);
   }
 }
 
@@ -532,7 +542,7 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
   const bool small = cap <= WARP_CAP;
   if (!small) MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));   // the warp kernel writes every count
-  dim3 g1((cap + RANK_THREADS - 1) / RANK_THREADS, nseg);
+  dim3 g1((cap + RANK_ELEMS - 1) / RANK_ELEMS, nseg);
   nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
@@ -615,7 +625,7 @@ int mpn_nms_dense_launch(mpn_ctx *ctx, const float *sb_dev, int n, float thr, in
   unsigned long long *mask = (unsigned long long *)(ws + o_mask);
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * 2, ctx->stream));
   MPN_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int32_t), ctx->stream));
-  dim3 g1((n + RANK_THREADS - 1) / RANK_THREADS, 1);
+  dim3 g1((n + RANK_ELEMS - 1) / RANK_ELEMS, 1);
   nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, n, nullptr, order, sorted, tie);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, 1);
