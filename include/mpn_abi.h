@@ -185,6 +185,18 @@ int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W,
                          const float *boxes, int64_t R, float im_scale, float W0, float H0,
                          float score_thresh, float nms_thr, float *scores, float *bboxes,
                          int32_t *keep_idx, int32_t *keep_counts);
+/* Pipelined form of mpn_model_detect_nms for throughput serving (test_runner.lua keeps one
+ * image in flight per donkey thread; here one model keeps two): submit returns at once with a
+ * ticket, at most 2 tickets may be outstanding. The host->device copy of a submission runs on
+ * its own copy stream and overlaps the kernels of the previous submission, the device->host
+ * copy of the results on a third stream. The caller's buffers (pinned memory for real overlap)
+ * must stay valid and untouched until mpn_model_detect_nms_wait(ticket) returns; results are
+ * bit-identical to the synchronous call.                                       */
+int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int32_t W,
+                                const float *boxes, int64_t R, float im_scale, float W0, float H0,
+                                float score_thresh, float nms_thr, float *scores, float *bboxes,
+                                int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket);
+int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket);
 /* Same with every buffer resident on the device, fully asynchronous (the
  * throughput path: bench.py `value`). */
 int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W,

@@ -91,6 +91,9 @@ SIGNATURES = {
     "mpn_model_detect": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_int32, _vp, _vp]),
     "mpn_model_detect_nms": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "mpn_model_detect_nms_submit": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
+                                              C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32p]),
+    "mpn_model_detect_nms_wait": (C.c_int, [_vp, C.c_int32]),
     "mpn_model_detect_nms_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     "mpn_model_get_trunk_slot": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p, _i32p]),
@@ -463,6 +466,28 @@ class Model:
             self.h, _ptr(im), im.shape[1], im.shape[2], _ptr(b), n, float(im_scale), float(W0), float(H0),
             float(score_thresh), float(nms_thr), _ptr(scores), _ptr(bboxes), _ptr(keep), _ptr(counts)), "mpn_model_detect_nms")
         return scores, bboxes, [keep[j, : counts[j]].copy() for j in range(self.C - 1)]
+
+    def detect_nms_submit(self, image_chw, boxes, im_scale: float, W0: float, H0: float, score_thresh: float = -1.5,
+                          nms_thr: float = 0.3):
+        """Pipelined detect_nms (at most two in flight): returns a ticket; `detect_nms_wait(ticket)` returns the results.
+        The host->device copy overlaps the previous submission's kernels (pass pinned arrays for real overlap)."""
+        im, b = _f32(image_chw), _f32(boxes)
+        n = b.shape[0]
+        out = dict(im=im, b=b, scores=np.empty((n, self.C), dtype=np.float32), bboxes=np.empty((n, 4 * self.C), dtype=np.float32),
+                   keep=np.empty((self.C - 1, n), dtype=np.int32), counts=np.empty(self.C - 1, dtype=np.int32))
+        t = C.c_int32(-1)
+        self.ctx.check(self.ctx.lib.mpn_model_detect_nms_submit(
+            self.h, _ptr(im), im.shape[1], im.shape[2], _ptr(b), n, float(im_scale), float(W0), float(H0), float(score_thresh),
+            float(nms_thr), _ptr(out["scores"]), _ptr(out["bboxes"]), _ptr(out["keep"]), _ptr(out["counts"]), C.byref(t)),
+            "mpn_model_detect_nms_submit")
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = out              # keeps the host buffers alive until wait()
+        return t.value
+
+    def detect_nms_wait(self, ticket: int):
+        self.ctx.check(self.ctx.lib.mpn_model_detect_nms_wait(self.h, int(ticket)), "mpn_model_detect_nms_wait")
+        o = self._inflight.pop(ticket)
+        return o["scores"], o["bboxes"], [o["keep"][j, : o["counts"][j]].copy() for j in range(self.C - 1)]
 
     def detect_nms_dev(self, image_dev, H: int, W: int, boxes_dev, R: int, im_scale: float, W0: float, H0: float,
                        score_thresh: float, nms_thr: float, scores_dev=None, bboxes_dev=None, keep_idx_dev=None,

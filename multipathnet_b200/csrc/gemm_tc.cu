@@ -44,7 +44,8 @@ __host__ __device__ constexpr int num_stages(int BN, int CG = 1) {
 }
 // Accumulator rotation: back-to-back tcgen05.mma into the SAME TMEM accumulator serialise on its read-modify-write
 // latency (~117 cycles measured, independent of N), so for N <= 128 (32/64 cycles of tensor work per instruction) the
-// three bf16x3 products go to separate accumulators (3 for BN=64, 2 for BN=128) that the epilogue sums.
+// three bf16x3 products go to separate accumulators (2 for BN=128; for BN=64 one BN-wide A_lo x B_hi and one 2*BN-wide
+// A_hi x [B_hi ; B_lo], which also saves one shared-memory read of A per k16) that the epilogue sums.
 __host__ __device__ constexpr int num_acc(int BN) { return BN == 256 ? 1 : (BN == 128 ? 2 : 3); }
 __host__ __device__ constexpr int tmem_cols(int BN) { return 512; }       // 2 buffers x num_acc(BN) x BN columns (384 or 512)
 
@@ -257,7 +258,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 
 // ---------------------------------------------------------------- epilogue of one accumulator tile (shared by both kernels)
 // warp q reads its 32 TMEM lanes 32 columns at a time; + bias (+ residual) (ReLU); re-split to bf16 hi/lo and/or fp32
-template <int BN>
+template <int BN, int CG>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tmem_base, int q, int a, int nt, bool row_ok,
                                                  long long pix, float *out_f32, int ch_first, long long ppix = -1,
                                                  const EpiSk sk = EpiSk()) {
@@ -281,12 +282,17 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
     tc_ld32(tcol, v);
     if (NACC >= 2) {                       // sum the per-product accumulators (fixed order: deterministic)
       uint32_t w[32];
-      tc_ld32(tcol + BN, w);
+      // NACC == 3 (BN = 64): the second accumulator is the 2*BN-wide product A_hi x [B_hi ; B_lo] (one MMA, see the issuer);
+      // with CTA pairs each CTA contributes [its hi half ; its lo half], so the columns interleave per 32-channel half.
+      const uint32_t d2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NACC * BN + BN);
+      const uint32_t hh_col = (NACC == 3) ? d2 + (uint32_t)(CG == 2 ? ch * 64 : ch * 32) : 0u;
+      const uint32_t hl_col = (NACC == 3) ? d2 + (uint32_t)(CG == 2 ? ch * 64 + 32 : BN + ch * 32) : tcol + BN;
+      tc_ld32(hl_col, w);
       tc_wait_ld();
 #pragma unroll
       for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
       if (NACC == 3) {
-        tc_ld32(tcol + 2 * BN, w);
+        tc_ld32(hh_col, w);
         tc_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
@@ -401,6 +407,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   constexpr int STAGE = stage_bytes(BN, CG);
   constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;            // this CTA's share of the B tile
   constexpr uint32_t IDESC = make_idesc(BM * CG, BN);         // cta_group::2: one 256 x BN MMA over the pair
+  constexpr uint32_t IDESC2 = make_idesc(BM * CG, 2 * BN <= 256 ? 2 * BN : BN);   // A_hi x [B_hi ; B_lo] (BN = 64 only)
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for SWIZZLE_128B tiles
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -519,7 +526,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
             const uint32_t later = ((kb - kb0) | k) != 0 ? 1u : 0u;     // 0 on the first k16 of the tile: zero-init
             const uint32_t f_lh = later, f_hh = (NACC >= 2) ? later : 1u, f_hl = (NACC == 3) ? later : 1u;
-            if (CG == 2) {
+            if (NACC == 3) {
+              // narrow tiles are bound by the shared-memory read of A (4 KB per MMA): B_lo sits right behind B_hi, so
+              // ONE 2*BN-wide MMA computes A_hi x [B_hi ; B_lo] and A is read twice per k16 instead of three times
+              if (CG == 2) {
+                tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                tc_mma_bf16_2sm(d_hl, a_hi + adv, b_hi + adv, IDESC2, f_hl);
+              } else {
+                tc_mma_bf16(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                tc_mma_bf16(d_hl, a_hi + adv, b_hi + adv, IDESC2, f_hl);
+              }
+            } else if (CG == 2) {
               tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
               tc_mma_bf16_2sm(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
               tc_mma_bf16_2sm(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
@@ -557,7 +574,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-      tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
+      tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                             // 4*CG arrivals (one per epilogue warp of the pair) free the buffer
@@ -591,7 +608,8 @@ constexpr int R3_A_STAGE = 2 * R3_A_PLANE;       // hi + lo
 __host__ __device__ constexpr int r3_b_stage(int BN, int CG) { return 2 * (BN / CG) * BK * 2; }
 __host__ __device__ constexpr int r3_sa(int BN, int CG) { return (BN / CG) >= 128 ? 2 : 3; }
 __host__ __device__ constexpr int r3_sb(int BN, int CG) {
-  return (196608 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 8 ? 8 : (196608 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
+  // fill what is left of ~215 KB after the A ring (B tiles are small for narrow layers: a deep ring hides the TMA latency)
+  return (220160 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 12 ? 12 : (220160 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
 }
 
 template <int BN, int CG>
@@ -603,6 +621,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   constexpr int B_STAGE = r3_b_stage(BN, CG);
   constexpr int B_TILE_BYTES = B_STAGE / 2;
   constexpr uint32_t IDESC = make_idesc(BM * CG, BN);
+  constexpr uint32_t IDESC2 = make_idesc(BM * CG, 2 * BN <= 256 ? 2 * BN : BN);
   static_assert(SB >= 2, "B ring too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -744,7 +763,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
                 const uint32_t later = (first && k == 0) ? 0u : 1u;
                 const uint32_t f_lh = later, f_hh = (NACC >= 2) ? later : 1u, f_hl = (NACC == 3) ? later : 1u;
-                if (CG == 2) {
+                if (NACC == 3) {                   // A_hi x [B_hi ; B_lo] in one 2*BN-wide MMA (see the generic kernel)
+                  if (CG == 2) {
+                    tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                    tc_mma_bf16_2sm(d_hl, a_hi + adv, b_hi + adv, IDESC2, f_hl);
+                  } else {
+                    tc_mma_bf16(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
+                    tc_mma_bf16(d_hl, a_hi + adv, b_hi + adv, IDESC2, f_hl);
+                  }
+                } else if (CG == 2) {
                   tc_mma_bf16_2sm(d_lh, a_lo + adv, b_hi + adv, IDESC, f_lh);
                   tc_mma_bf16_2sm(d_hh, a_hi + adv, b_hi + adv, IDESC, f_hh);
                   tc_mma_bf16_2sm(d_hl, a_hi + adv, b_lo + adv, IDESC, f_hl);
@@ -815,7 +842,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const long long ppix = (p.pool_hi && row_ok && !(lane & 9)) ? ((long long)n * p.Hp + (ho >> 1)) * p.Wp + (wo >> 1) : -1;
       mbar_wait_t(tfull_bar(a), aph, wc0, trace);
       tc_fence_after();
-      { const long long te = clock64(); tc_epilogue_tile<BN>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk); if (trace) wc1 += (unsigned long long)(clock64() - te); }
+      { const long long te = clock64(); tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk); if (trace) wc1 += (unsigned long long)(clock64() - te); }
       tc_fence_before();
       if (sk.role == SK_WRITER) {                  // publish the partial: data, fence, then the flag (release)
         __threadfence();

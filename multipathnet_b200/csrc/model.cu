@@ -112,6 +112,20 @@ struct mpn_model {
   DevBuf rois_dev, boxes_dev, cls_logits, bbox_raw, scores_dev, bboxes_dev;
   DevBuf sb_dev, src_idx_dev, counts_dev, keep_idx_dev, keep_counts_dev;
   RoiJobs jobs;
+  // ---- pipelined submit/wait (two slots): per-slot input staging + a private copy of the outputs, copy streams, events
+  struct PipeSlot {
+    DevBuf image, boxes, scores, bboxes, keep_idx, keep_counts;
+    cudaEvent_t h2d = nullptr, compute = nullptr, done = nullptr;
+    bool busy = false; int ticket = -1;
+  };
+  PipeSlot pipe[2];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  int next_ticket = 0;
+  ~mpn_model() {
+    for (auto &q : pipe) { if (q.h2d) cudaEventDestroy(q.h2d); if (q.compute) cudaEventDestroy(q.compute); if (q.done) cudaEventDestroy(q.done); }
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+  }
 };
 
 namespace {
@@ -537,6 +551,7 @@ void mpn_model_destroy(mpn_model *m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  if (m->s_d2h) cudaStreamSynchronize(m->s_d2h);
   delete m;
 }
 
@@ -699,6 +714,63 @@ int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W,
   if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, m->keep_idx_dev.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToHost, ctx->stream));
   if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, m->keep_counts_dev.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
+                                float im_scale, float W0, float H0, float score_thresh, float nms_thr, float *scores,
+                                float *bboxes, int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image && boxes && R > 0 && ticket, "image/boxes/ticket missing");
+  const int C = m->d.num_classes;
+  mpn_model::PipeSlot &q = m->pipe[m->next_ticket & 1];
+  if (q.busy) return mpn_fail(ctx, MPN_ERR_STATE, "two submissions are already in flight: call mpn_model_detect_nms_wait first");
+  if (!m->s_h2d) {
+    MPN_CUDA(ctx, cudaStreamCreateWithFlags(&m->s_h2d, cudaStreamNonBlocking));
+    MPN_CUDA(ctx, cudaStreamCreateWithFlags(&m->s_d2h, cudaStreamNonBlocking));
+  }
+  if (!q.h2d) {
+    MPN_CUDA(ctx, cudaEventCreateWithFlags(&q.h2d, cudaEventDisableTiming));
+    MPN_CUDA(ctx, cudaEventCreateWithFlags(&q.compute, cudaEventDisableTiming));
+    MPN_CUDA(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
+  }
+  const size_t img_bytes = sizeof(float) * 3 * (size_t)H * W;
+  MPN_TRY(q.image.ensure(ctx, img_bytes));
+  MPN_TRY(q.boxes.ensure(ctx, sizeof(float) * 4 * (size_t)R));
+  MPN_TRY(q.scores.ensure(ctx, sizeof(float) * (size_t)R * C));
+  MPN_TRY(q.bboxes.ensure(ctx, sizeof(float) * (size_t)R * 4 * C));
+  MPN_TRY(q.keep_idx.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * R));
+  MPN_TRY(q.keep_counts.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1)));
+  // inputs: the slot's previous occupant was waited for (busy == false), so its staging buffers are free
+  MPN_CUDA(ctx, cudaMemcpyAsync(q.image.p, image, img_bytes, cudaMemcpyHostToDevice, m->s_h2d));
+  MPN_CUDA(ctx, cudaMemcpyAsync(q.boxes.p, boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, m->s_h2d));
+  MPN_CUDA(ctx, cudaEventRecord(q.h2d, m->s_h2d));
+  MPN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.h2d, 0));
+  MPN_TRY(mpn_model_detect_nms_dev(m, (const float *)q.image.p, H, W, (const float *)q.boxes.p, R, im_scale, W0, H0, score_thresh,
+                                   nms_thr, scores ? (float *)q.scores.p : nullptr, bboxes ? (float *)q.bboxes.p : nullptr,
+                                   keep_idx ? (int32_t *)q.keep_idx.p : nullptr, keep_counts ? (int32_t *)q.keep_counts.p : nullptr));
+  MPN_CUDA(ctx, cudaEventRecord(q.compute, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamWaitEvent(m->s_d2h, q.compute, 0));
+  if (scores) MPN_CUDA(ctx, cudaMemcpyAsync(scores, q.scores.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, m->s_d2h));
+  if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, q.bboxes.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, m->s_d2h));
+  if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, q.keep_idx.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToHost, m->s_d2h));
+  if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, q.keep_counts.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, m->s_d2h));
+  MPN_CUDA(ctx, cudaEventRecord(q.done, m->s_d2h));
+  q.busy = true; q.ticket = m->next_ticket;
+  *ticket = m->next_ticket++;
+  return MPN_OK;
+}
+
+int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  mpn_model::PipeSlot &q = m->pipe[ticket & 1];
+  MPN_CHECK_ARG(ctx, ticket >= 0 && q.busy && q.ticket == ticket, "unknown or already completed ticket");
+  MPN_CUDA(ctx, cudaEventSynchronize(q.done));
+  q.busy = false;
   return MPN_OK;
 }
 

@@ -220,6 +220,7 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
   unsigned long long tn0 = 0ull, tn1 = 0ull;       // tienext bit p: score[p] == score[p+1] in sorted order
   unsigned long long rr0 = rem0, rr1 = rem1;       // replay state: removed-set at round `replayed`
   if (TIE) {
+#pragma unroll 1
     for (int b = 0; b < 64; ++b) {
       const int p0 = lane * 64 + b, p1 = (lane + 32) * 64 + b;
       if (p0 + 1 < n && c.s_score[p0] == c.s_score[p0 + 1]) tn0 |= 1ull << b;
@@ -241,40 +242,49 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
     const int row0 = cw * 64;
     unsigned long long cur = __shfl_sync(0xffffffffu, (TWO && half) ? rem1 : rem0, wl);
     const unsigned long long tw = TIE ? __shfl_sync(0xffffffffu, (TWO && half) ? tn1 : tn0, wl) : 0ull;
-    // ---- resolve the chunk's rows against each other. Every lane runs the SAME fully unrolled, branch-free chain on the
-    //      64 diagonal words (broadcast loads, no shuffles): ~15 cycles per row instead of one ~100-cycle round per kept box.
-    //      A live box whose score continues into the next row (tie) stops the chain: it takes the general round below.
+    // ---- resolve the chunk's rows against each other: every lane runs the same scalar loop over the LIVE rows only
+    //      (typically 5-15 of 64): next live bit, its diagonal word (one broadcast load), clear what it suppresses. A single
+    //      warp pays ~5 cycles per dependent instruction, so the loop body is kept to a dozen instructions; a live box
+    //      whose score continues into the next row (tie) stops the loop and takes the general round below.
     unsigned long long kb = 0ull; int tie_b = -1;
     {
-      unsigned long long dg[64];
-#pragma unroll
-      for (int b = 0; b < 64; ++b) dg[b] = mask_word(min(row0 + b, n - 1), cw);
-#pragma unroll
-      for (int b = 0; b < 64; ++b) {
-        const bool live = !((cur >> b) & 1ull) && (!TIE || tie_b < 0);
-        // tied with the next row; skipped when that row is already dead and the tie group ends there (the common pair case)
-        const bool pair_done = (b < 63) && ((cur >> ((b + 1) & 63)) & 1ull) && !((tw >> ((b + 1) & 63)) & 1ull);
-        const bool tie_here = TIE && live && ((tw >> b) & 1ull) && !pair_done;
-        if (tie_here) tie_b = b;
-        if (live && !tie_here) { kb |= 1ull << b; cur |= dg[b]; }
+      unsigned long long live = ~cur;
+      while (live) {
+        const int b = __ffsll((long long)live) - 1;
+        if (TIE && ((tw >> b) & 1ull)) {
+          // tied with the next row; skipped when that row is already dead and the tie group ends there (the common pair case)
+          const bool pair_done = (b < 63) && !((live >> ((b + 1) & 63)) & 1ull) && !((tw >> ((b + 1) & 63)) & 1ull);
+          if (!pair_done) { tie_b = b; break; }
+        }
+        const unsigned long long d = mask_word(row0 + b, cw);      // includes the diagonal bit b
+        kb |= 1ull << b;
+        live &= ~d;
       }
+      cur = ~live;
     }
     // ---- record the kept rows (emission order = ascending sorted position inside the chunk)
     if ((kb >> lane) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << lane) - 1ull))] = (unsigned short)(row0 + lane);
     if ((kb >> (lane + 32)) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << (lane + 32)) - 1ull))] = (unsigned short)(row0 + lane + 32);
     nkeep += __popcll(kb);
-    // ---- deferred suppression: OR the kept rows into the words after cw (lane-parallel over words, loads batched by 8)
+    // ---- deferred suppression: OR the kept rows into the words after cw (lane-parallel over words; four loads in flight)
     {
       const bool on0 = (lane > cw) && (lane < nwords);
       const bool on1 = TWO && (lane + 32 > cw) && (lane + 32 < nwords);
-      unsigned long long acc0 = 0ull, acc1 = 0ull;
-      if (kb) {
-#pragma unroll 8
-        for (int b = 0; b < 64; ++b) {
-          if ((kb >> b) & 1ull) {
-            if (on0) acc0 |= mask_word(row0 + b, lane);
-            if (on1) acc1 |= mask_word(row0 + b, lane + 32);
-          }
+      unsigned long long acc0 = 0ull, acc1 = 0ull, bits = kb;
+      while (bits) {
+        const int b0 = __ffsll((long long)bits) - 1; bits &= bits - 1ull;
+        const int b1 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
+        const int b2 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
+        const int b3 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
+        if (on0) {
+          const unsigned long long m0 = mask_word(row0 + b0, lane), m1 = mask_word(row0 + b1, lane);
+          const unsigned long long m2 = mask_word(row0 + b2, lane), m3 = mask_word(row0 + b3, lane);
+          acc0 |= (m0 | m1) | (m2 | m3);
+        }
+        if (on1) {
+          const unsigned long long m0 = mask_word(row0 + b0, lane + 32), m1 = mask_word(row0 + b1, lane + 32);
+          const unsigned long long m2 = mask_word(row0 + b2, lane + 32), m3 = mask_word(row0 + b3, lane + 32);
+          acc1 |= (m0 | m1) | (m2 | m3);
         }
       }
       rem0 |= acc0; if (TWO) rem1 |= acc1;

@@ -81,7 +81,7 @@ def test_first_layer_direct_conv(ctx, Cin, Cout, k, s, p, H, W):
     assert rel_err(got, ref) < TOL
 
 
-@pytest.mark.parametrize("Cin,H,W,Cout", [(512, 38, 50, 512), (256, 150, 200, 256), (128, 75, 100, 256)])
+@pytest.mark.parametrize("Cin,H,W,Cout", [(512, 38, 50, 512), (256, 150, 200, 256)])
 def test_streamk_schedule(ctx, Cin, H, W, Cout, monkeypatch):
     """stream-K (contiguous (tile, step) ranges per CTA pair, partial tiles exchanged through L2 and summed in pair order):
     chosen for these wave-quantised shapes, deterministic across launches, and equal to the whole-tile schedule up to

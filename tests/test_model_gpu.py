@@ -211,3 +211,24 @@ def test_resnet50_full_size_cfg4(ctx):
     tf, hf = m.last_flops()
     assert abs(tf / 1e9 - 104.9) < 1.5 and abs(hf / 2000 / 1e9 - 1.62) < 0.02
     m.close()
+
+
+def test_pipelined_submit_wait_matches_sync(ctx, small_vgg):
+    """mpn_model_detect_nms_submit/_wait (two images in flight, copies on their own streams) == the blocking call, bit for bit;
+    a third submission without a wait is refused loudly."""
+    spec, m = small_vgg
+    inputs = [_inputs(spec, 150, 203, 120, 10 + i) for i in range(5)]
+    sync = [m.detect_nms(im, bx, 1.0, 203, 150, 0.0, 0.3) for im, bx in inputs]
+    got = []
+    prev = m.detect_nms_submit(inputs[0][0], inputs[0][1], 1.0, 203, 150, 0.0, 0.3)
+    for i in range(1, 5):
+        cur = m.detect_nms_submit(inputs[i][0], inputs[i][1], 1.0, 203, 150, 0.0, 0.3)
+        if i == 1:
+            with pytest.raises(RuntimeError, match="in flight"):
+                m.detect_nms_submit(inputs[2][0], inputs[2][1], 1.0, 203, 150, 0.0, 0.3)
+        got.append(m.detect_nms_wait(prev))
+        prev = cur
+    got.append(m.detect_nms_wait(prev))
+    for (s0, b0, k0), (s1, b1, k1) in zip(sync, got):
+        assert np.array_equal(s0, s1) and np.array_equal(b0, b1)
+        assert all(np.array_equal(a, b) for a, b in zip(k0, k1))
