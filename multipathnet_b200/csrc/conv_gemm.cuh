@@ -41,4 +41,7 @@ int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p);           // CUDA-core 
 int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, int H, int W, const float *w,
                             const float *bias, int Cout, int kh, int kw, int stride, int pad, int relu,
                             DTensor &y, const float *w_host = nullptr, const float *bias_host = nullptr);
+// first layer (3x3/1/1, Cin 3, Cout 64) on tcgen05: x NCHW fp32, w fp32 [64][27] (Torch layout), y NHWC split planes
+int conv1_tc_launch(mpn_ctx *ctx, const float *x_nchw, int N, int H, int W, const float *w_dev, const float *bias_dev, int relu,
+                    DTensor &y);
 double conv_flops(const ConvProblem &p);

@@ -7,6 +7,7 @@
 //    split-bf16 operands as the tcgen05 engine. Verification/debug only (mpn_model_set_conv_impl
 //    = 1, mpn_*_check impl=1): it lets tests separate "tensor-core engine bug" from "graph bug".
 #include "conv_gemm.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -235,6 +236,10 @@ int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, i
   const size_t smem = sizeof(float) * DC_CO * Cin * kh * kw;
   MPN_CHECK_ARG(ctx, smem <= 48 * 1024, "conv_direct: filter too large");
   dim3 grid((unsigned)((pixels + 255) / 256), (unsigned)((Cout + DC_CO - 1) / DC_CO));
+  if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout == 64 && y.ld % 8 == 0 && bias) {
+    const char *e = getenv("MPN_CONV1_TC");           // debug knob: 0 = CUDA-core kernels below
+    if (!(e && e[0] == '0')) return conv1_tc_launch(ctx, x_nchw, N, H, W, w, bias, relu, y);
+  }
   if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout == 64 && w_host && y.ld % 8 == 0) {
     Conv1Params cp;
     memcpy(cp.w, w_host, sizeof(cp.w));

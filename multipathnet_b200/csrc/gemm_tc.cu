@@ -26,6 +26,7 @@
 #include "conv_gemm.cuh"
 #include <algorithm>
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -878,6 +879,160 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------- first layer: 3x3 / pad 1 / Cin = 3 / Cout = 64 on tcgen05
+// K = 27 cannot come through TMA (NCHW fp32 image, 3 channels), so four builder warps do the im2col themselves: thread
+// = one pixel of the 128-pixel tile, 27 loads, split to bf16 hi/lo and written straight into the canonical K-major
+// SWIZZLE_128B layout (row = 128 B, only k < 32 populated; the MMAs read two k16 steps), then fence.proxy.async + one
+// mbarrier arrive per warp. The 64 x 27 filter bank is split once per CTA into a resident B tile ([B_hi ; B_lo]).
+// Per tile: A_lo x B_hi (N = 64) and A_hi x [B_hi ; B_lo] (N = 128) for each k16 = 4 MMAs; the accumulator layout is the
+// BN = 64 layout of the generic kernel, so its epilogue (bias, ReLU, split, 16-byte stores) is reused unchanged.
+__device__ __forceinline__ int c1_chunk_first(int warp) { return ((warp - 5) >> 2) & 1; }
+constexpr int C1_BUILD_WARPS = 4, C1_THREADS = 32 * (1 + C1_BUILD_WARPS + EPI_WARPS);
+constexpr int C1_A_STAGE = 2 * A_TILE_BYTES, C1_STAGES = 2, C1_B_BYTES = 2 * 64 * 128;
+
+__global__ void __launch_bounds__(C1_THREADS, 1)
+conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *__restrict__ w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sB = smem + C1_STAGES * C1_A_STAGE;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + C1_B_BYTES);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  const uint32_t a_base = smem_u32(smem), b_base = smem_u32(sB), bar_base = smem_u32(bars);
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (4 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (6 + a); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long pixels = (long long)N * H * W;
+  const int total_tiles = (int)((pixels + BM - 1) / BM);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C1_STAGES; ++s) { mbar_init(fullA(s), C1_BUILD_WARPS); mbar_init(emptyA(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // resident B tile: row = output channel, 128 B per row (k < 32 used), 16-byte chunk j stored at j ^ (row & 7)
+  for (int i = threadIdx.x; i < 64 * 4; i += C1_THREADS) {
+    const int row = i >> 2, j = i & 3;
+    uint32_t hh[4], ll[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k0 = j * 8 + 2 * t;
+      const float v0 = (k0 < 27) ? __ldg(w + row * 27 + k0) : 0.f, v1 = (k0 + 1 < 27) ? __ldg(w + row * 27 + k0 + 1) : 0.f;
+      split_bf16x2(v0, v1, hh[t], ll[t]);
+    }
+    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) * 16);
+    *reinterpret_cast<uint4 *>(sB + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    *reinterpret_cast<uint4 *>(sB + 64 * 128 + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t IDESC_N64 = make_idesc(BM, 64), IDESC_N128 = make_idesc(BM, 128);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1, a = it & 1; const uint32_t ph = (it >> 1) & 1u;
+      mbar_wait(tempty_bar(a), ph ^ 1u);
+      mbar_wait(fullA(s), ph);
+      tc_fence_after();
+      const uint32_t d1 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(a * 192), 0);
+      const uint32_t sa = __shfl_sync(0xffffffffu, a_base + (uint32_t)s * C1_A_STAGE, 0);
+      const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES), b_hi = make_smem_desc(b_base);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+          tc_mma_bf16(d1, a_lo + adv, b_hi + adv, IDESC_N64, k ? 1u : 0u);
+          tc_mma_bf16(d1 + 64, a_hi + adv, b_hi + adv, IDESC_N128, k ? 1u : 0u);
+        }
+        tc_commit(emptyA(s));
+        tc_commit(tfull_bar(a));
+      }
+      __syncwarp();
+    }
+  } else if (warp <= C1_BUILD_WARPS) {
+    // ===================== im2col builders: one pixel (= one A row) per thread =====================
+    const int row = (warp - 1) * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int s = it & 1; const uint32_t ph = (it >> 1) & 1u;
+      const long long pix = (long long)tile * BM + row;
+      float in[32];
+#pragma unroll
+      for (int k = 27; k < 32; ++k) in[k] = 0.f;
+      if (pix < pixels) {
+        const int wo = (int)(pix % W), ho = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+        const float *xn = x + (size_t)n * 3 * H * W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int hi = ho + r - 1;
+            const bool hok = (hi >= 0) && (hi < H);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int wi = wo + q - 1;
+              const bool ok = hok && (wi >= 0) && (wi < W);
+              in[(ci * 3 + r) * 3 + q] = ok ? __ldg(xn + ((size_t)ci * H + hi) * W + wi) : 0.f;
+            }
+          }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 27; ++k) in[k] = 0.f;
+      }
+      mbar_wait(emptyA(s), ph ^ 1u);
+      uint8_t *pa = smem + (size_t)s * C1_A_STAGE + (size_t)row * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) split_bf16x2(in[j * 8 + 2 * t], in[j * 8 + 2 * t + 1], hh[t], ll[t]);
+        const int pj = (j ^ (row & 7)) * 16;
+        *reinterpret_cast<uint4 *>(pa + pj) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<uint4 *>(pa + A_TILE_BYTES + pj) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(fullA(s));
+    }
+  } else {
+    // ===================== epilogue: the generic kernel's, BN = 64 accumulator layout =====================
+    const int ew = warp - 1 - C1_BUILD_WARPS;          // 0..7
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1; const uint32_t ph = (it >> 1) & 1u;
+      const long long pix = (long long)tile * BM + row;
+      mbar_wait(tfull_bar(a), ph);
+      tc_fence_after();
+      // two warps share each TMEM lane quarter: the chunk parity comes from which of them this is
+      tc_epilogue_tile<64, 1>(p, tmem_base, q, a, 0, pix < pixels, pix, nullptr, c1_chunk_first(warp));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(a));
+      (void)ew;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // split-K second pass: out = epilogue(sum over splits in FIXED order) — deterministic (no atomics), so the
 // row-chunk invariance the reference asserts (modules/test.lua:85-98) still holds bit for bit.
 struct ReduceParams {
@@ -998,6 +1153,34 @@ int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
 }
 
 }  // namespace
+
+// first layer on the tensor cores (see conv1_tc_kernel); y: NHWC split planes with 64 channels
+int conv1_tc_launch(mpn_ctx *ctx, const float *x_nchw, int N, int H, int W, const float *w_dev, const float *bias_dev, int relu,
+                    DTensor &y) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_DIRECT);
+  MPN_CHECK_ARG(ctx, y.hi && y.lo && y.C == 64 && y.ld % 8 == 0, "conv1_tc: output must be 64-channel split planes");
+  TcParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.N = N; tp.Ho = H; tp.Wo = W; tp.Cout = 64; tp.bias = bias_dev; tp.relu = relu;
+  tp.out_hi = y.hi; tp.out_lo = y.lo; tp.out_ld = y.ld;
+  const int smem = C1_STAGES * C1_A_STAGE + C1_B_BYTES + 1024 + 256;
+  static int attr_set = 0;
+  if (!attr_set) {
+    MPN_CUDA(ctx, cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = 1;
+  }
+  const long long tiles = ((long long)N * H * W + BM - 1) / BM;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)std::min<long long>(tiles, ctx->sm_count)); cfg.blockDim = dim3(C1_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  int na = 0;
+  if (tc_use_pdl()) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+  cfg.attrs = attr; cfg.numAttrs = na;
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv1_tc_kernel, x_nchw, N, H, W, w_dev, tp));
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
 
 double conv_flops(const ConvProblem &p) {
   const double Ho = (double)p.y.H, Wo = (double)p.y.W;

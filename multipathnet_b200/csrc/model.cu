@@ -96,7 +96,7 @@ struct mpn_model {
   std::set<int> elided_slots;      // conv outputs the last trunk forward did not materialise (conv+pool fusion)
   double trunk_flops = 0, head_flops = 0;
   // max pyramids of the trunk slots that towers pool from (roi.cu): level k>=1 buffers per slot
-  struct Pyramid { std::vector<std::unique_ptr<SplitBuf>> lv; int nlev = 1; };
+  struct Pyramid { std::vector<std::unique_ptr<DevBuf>> lv; int nlev = 1; };   // fp32 levels 0..nlev-1
   std::map<int, Pyramid> pyramids;
 
   // ---- heads state
@@ -269,9 +269,9 @@ int plan_trunk(mpn_model *m, int H, int W) {
       while (nlev < ROI_MAX_LEVELS && (1 << nlev) <= std::min(f.H, f.W)) ++nlev;
       P.nlev = nlev;
       P.lv.resize(nlev);
-      for (int k = 1; k < nlev; ++k) {
-        if (!P.lv[k]) P.lv[k].reset(new SplitBuf());
-        MPN_TRY(P.lv[k]->ensure(ctx, (size_t)(f.N * f.H * f.W * f.C)));
+      for (int k = 0; k < nlev; ++k) {
+        if (!P.lv[k]) P.lv[k].reset(new DevBuf());
+        MPN_TRY(P.lv[k]->ensure(ctx, sizeof(float) * (size_t)(f.N * f.H * f.W * f.C) + 256));
       }
     }
   m->tH = H; m->tW = W; m->trunk_valid = false; m->heads_planned = false;
@@ -309,13 +309,14 @@ int run_trunk(mpn_model *m, const float *image_dev) {
   }
   for (auto &kv : m->pyramids) {
     const DTensor &f = m->trunk_slots[kv.first];
-    const __nv_bfloat16 *ph = f.hi, *pl = f.lo; long long ld = f.ld;
-    for (int k = 1; k < kv.second.nlev; ++k) {
-      SplitBuf &b = *kv.second.lv[k];
-      MPN_TRY(mpn_maxpyr_launch(ctx, ph, pl, (int)f.N, (int)f.H, (int)f.W, (int)f.C, ld, 1 << (k - 1), (__nv_bfloat16 *)b.hi.p,
-                                (__nv_bfloat16 *)b.lo.p));
-      ph = (const __nv_bfloat16 *)b.hi.p; pl = (const __nv_bfloat16 *)b.lo.p; ld = f.C;
-    }
+    float *lv[ROI_MAX_LEVELS] = {nullptr};
+    for (int k = 0; k < kv.second.nlev; ++k) lv[k] = (float *)kv.second.lv[k]->p;
+    int too_big = 0;       // small maps (conv5): every level in one launch
+    MPN_TRY(mpn_maxpyr_all_launch(ctx, f.hi, f.lo, (int)f.N, (int)f.H, (int)f.W, (int)f.C, f.ld, kv.second.nlev, lv, &too_big));
+    if (!too_big) continue;
+    MPN_TRY(mpn_pyr_level0_launch(ctx, f.hi, f.lo, (int)f.N, (int)f.H, (int)f.W, (int)f.C, f.ld, lv[0]));
+    for (int k = 1; k < kv.second.nlev; ++k)
+      MPN_TRY(mpn_maxpyr_launch(ctx, lv[k - 1], (int)f.N, (int)f.H, (int)f.W, (int)f.C, 1 << (k - 1), lv[k]));
   }
   m->trunk_valid = true;
   return MPN_OK;
@@ -360,13 +361,12 @@ int plan_heads(mpn_model *m, int64_t R) {
       MPN_CHECK_ARG(ctx, m->jobs.n < MAX_ROI_JOBS, "too many (tower, level) ROI jobs");
       const DTensor &f = m->trunk_slots[T.level_slot[l]];
       RoiJob &j = m->jobs.j[m->jobs.n++];
-      j.hi = f.hi; j.lo = f.lo; j.H = (int)f.H; j.W = (int)f.W; j.C = (int)f.C; j.ld = f.ld; j.scale = T.level_scale[l];
+      j.H = (int)f.H; j.W = (int)f.W; j.C = (int)f.C; j.scale = T.level_scale[l];
       j.region = T.region; j.out_hi = X.pooled.hi; j.out_lo = X.pooled.lo; j.out_ld = X.ctot; j.out_ch_off = ch_off;
       j.normalize = T.normalize;
       const mpn_model::Pyramid &P = m->pyramids[T.level_slot[l]];
       j.nlev = P.nlev;
-      for (int k = 0; k < ROI_MAX_LEVELS; ++k) { j.hi_lv[k] = f.hi; j.lo_lv[k] = f.lo; }
-      for (int k = 1; k < P.nlev; ++k) { j.hi_lv[k] = (const __nv_bfloat16 *)P.lv[k]->hi.p; j.lo_lv[k] = (const __nv_bfloat16 *)P.lv[k]->lo.p; }
+      for (int k = 0; k < ROI_MAX_LEVELS; ++k) j.lv[k] = (const float *)P.lv[std::min(k, P.nlev - 1)]->p;
       ch_off += (int)f.C;
     }
     // shape walk

@@ -43,7 +43,7 @@ constexpr int RANK_ELEMS = 64;            // rows ranked per block; 4 threads pe
 __global__ void __launch_bounds__(RANK_THREADS)
 nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict__ counts,
                 int32_t *__restrict__ order, float4 *__restrict__ sorted_boxes,
-                int32_t *__restrict__ tie_flag) {
+                int32_t *__restrict__ tie_flag, float *__restrict__ sorted_score) {
   const int seg = blockIdx.y;
   const int n = counts ? counts[seg] : cap;
   if ((int)blockIdx.x * RANK_ELEMS >= n) return;
@@ -83,6 +83,7 @@ nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict
     order[(size_t)seg * cap + r] = i;
     const float *b = seg_sb + (size_t)i * 5;
     sorted_boxes[(size_t)seg * cap + r] = make_float4(b[0], b[1], b[2], b[3]);
+    if (sorted_score) sorted_score[(size_t)seg * cap + r] = si;
     if (s_tied[el]) atomicOr(&tie_flag[seg], 1);
   }
 }
@@ -195,7 +196,7 @@ constexpr int WARP_SMEM_MASK_CAP = 1024;
 constexpr int WARPK_THREADS = 256;
 
 struct WalkCtx {
-  const unsigned long long *s_mask, *m; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
+  const unsigned long long *s_mask, *m, *s_tn; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
   unsigned short *s_keep, *s_death, *s_qalt;
   int n, nwords, nwords_cap, use_smem_mask;
 };
@@ -217,16 +218,9 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
     return c.use_smem_mask ? c.s_mask[row * nwords + w] : __ldg(c.m + (size_t)row * c.nwords_cap + w);
   };
   unsigned long long rem0 = init_word(lane), rem1 = TWO ? init_word(lane + 32) : ~0ull;
-  unsigned long long tn0 = 0ull, tn1 = 0ull;       // tienext bit p: score[p] == score[p+1] in sorted order
+  // tienext bit p: score[p] == score[p+1] in sorted order (ballots of the whole block, see the kernel prologue)
+  const unsigned long long tn0 = TIE ? c.s_tn[lane] : 0ull, tn1 = (TIE && TWO) ? c.s_tn[lane + 32] : 0ull;
   unsigned long long rr0 = rem0, rr1 = rem1;       // replay state: removed-set at round `replayed`
-  if (TIE) {
-#pragma unroll 1
-    for (int b = 0; b < 64; ++b) {
-      const int p0 = lane * 64 + b, p1 = (lane + 32) * 64 + b;
-      if (p0 + 1 < n && c.s_score[p0] == c.s_score[p0 + 1]) tn0 |= 1ull << b;
-      if (TWO && p1 + 1 < n && c.s_score[p1] == c.s_score[p1 + 1]) tn1 |= 1ull << b;
-    }
-  }
   int nkeep = 0, hp = 0, replayed = 0;
   while (true) {
     // ---- first 64-row chunk (mask word cw) that still has a live box in (score desc, row asc) order
@@ -386,7 +380,7 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
 
 __global__ void __launch_bounds__(WARPK_THREADS)
 nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
-                     const float *__restrict__ sb, int cap, int nwords_cap, int use_smem_mask,
+                     const float *__restrict__ sorted_score, int cap, int nwords_cap, int use_smem_mask,
                      const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag,
                      const int32_t *__restrict__ src_idx, int32_t *__restrict__ keep_idx,
                      int32_t *__restrict__ keep_counts) {
@@ -396,44 +390,68 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   if (n <= 0) { if (threadIdx.x == 0) keep_counts[seg] = 0; return; }
   const int nwords = (n + 63) >> 6;
   const bool tie = tie_flag[seg] != 0;
-  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap] [keep u16 cap] [death u16 cap] [qalt u16 cap]
+  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [tn 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap]
+  //                        [keep u16 cap] [death u16 cap] [qalt u16 cap] [ord u16 cap]
   unsigned long long *s_mask = s_dyn;
   unsigned long long *s_rrem = s_dyn + (use_smem_mask ? (size_t)cap * nwords_cap : 0);
-  float *s_score = reinterpret_cast<float *>(s_rrem + 64);
+  unsigned long long *s_tn = s_rrem + 64;
+  float *s_score = reinterpret_cast<float *>(s_tn + 64);
   int *s_label = reinterpret_cast<int *>(s_score + cap);
   int *s_owner = s_label + cap;
   unsigned short *s_keep = reinterpret_cast<unsigned short *>(s_owner + cap);
   unsigned short *s_death = s_keep + cap;      // round in which a box was removed (0xffff = alive); filled lazily by the tie replay
   unsigned short *s_qalt = s_death + cap;
+  unsigned short *s_ord = s_qalt + cap;        // sorted position -> original row (n <= 4096)
   const unsigned long long *m = mask + (size_t)seg * cap * nwords_cap;
   const int32_t *ord = order + (size_t)seg * cap;
+  // ---- prologue, whole block: everything the serial warp will need goes to shared memory with coalesced loads
   if (use_smem_mask) {
+    if (nwords == nwords_cap && !(nwords & 1)) {
+      // same row pitch: straight 16-byte copy (the never-written lower triangle is never read either)
+      const uint4 *src = reinterpret_cast<const uint4 *>(m);
+      uint4 *dst = reinterpret_cast<uint4 *>(s_mask);
+      const int n4 = (n * nwords) >> 1;
 #pragma unroll 8
-    for (int i = threadIdx.x; i < n * nwords; i += WARPK_THREADS) {
-      const int r = i / nwords, w = i - r * nwords;
-      s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;   // only the upper triangle was computed
+      for (int i = threadIdx.x; i < n4; i += WARPK_THREADS) dst[i] = __ldg(src + i);
+    } else {
+#pragma unroll 8
+      for (int i = threadIdx.x; i < n * nwords; i += WARPK_THREADS) {
+        const int r = i / nwords, w = i - r * nwords;
+        s_mask[i] = (w >= (r >> 6)) ? __ldg(m + (size_t)r * nwords_cap + w) : 0ull;   // only the upper triangle was computed
+      }
     }
   }
-  if (tie) {
-    const float *seg_sb = sb + (size_t)seg * cap * 5;
-    for (int p = threadIdx.x; p < n; p += WARPK_THREADS) {
-      const int o = ord[p];
-      s_score[p] = seg_sb[(size_t)o * 5 + 4];
+  for (int p = threadIdx.x; p < n; p += WARPK_THREADS) {
+    const int o = ord[p];
+    s_ord[p] = (unsigned short)o;
+    if (tie) {
       s_label[p] = o;            // slot label = position in the reference's pointer array
+      s_score[p] = sorted_score[(size_t)seg * cap + p];
       s_owner[o] = p;            // slot -> sorted position of its occupant
       s_death[p] = 0xffffu;
     }
   }
   __syncthreads();
+  if (tie) {
+    // tienext bit p = (score[p] == score[p+1]): one ballot per 32 positions
+    unsigned *tn32 = reinterpret_cast<unsigned *>(s_tn);
+    for (int base = 0; base < nwords * 64; base += WARPK_THREADS) {
+      const int p = base + threadIdx.x;
+      const bool eq = (p + 1 < n) && (s_score[p] == s_score[p + 1]);
+      const unsigned b = __ballot_sync(0xffffffffu, eq);
+      if ((threadIdx.x & 31) == 0 && p < nwords * 64) tn32[p >> 5] = b;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
   int nkeep;
-  const WalkCtx wc{s_mask, m, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
+  const WalkCtx wc{s_mask, m, s_tn, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
   if (tie) nkeep = (nwords > 32) ? nms_walk<true, true>(wc, lane) : nms_walk<true, false>(wc, lane);
   else nkeep = (nwords > 32) ? nms_walk<false, true>(wc, lane) : nms_walk<false, false>(wc, lane);
   __syncwarp();
   for (int k = lane; k < nkeep; k += 32) {
-    const int o = ord[s_keep[k] & 0x7fff];
+    const int o = s_ord[s_keep[k] & 0x7fff];
     keep_idx[(size_t)seg * cap + k] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
   }
   if (lane == 0) keep_counts[seg] = nkeep;
@@ -541,6 +559,7 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   size_t o_cur = take(sizeof(int32_t) * (size_t)nseg * cap);
   size_t o_sorted = take(sizeof(float4) * (size_t)nseg * cap);
   size_t o_tie = take(sizeof(int32_t) * (size_t)nseg);
+  size_t o_sscore = take(sizeof(float) * (size_t)nseg * cap);
   size_t o_mask = take(sizeof(unsigned long long) * (size_t)nseg * cap * nwords);
   char *ws = nullptr;
   MPN_TRY(mpn_scratch2(ctx, off, (void **)&ws));
@@ -548,22 +567,23 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   int32_t *cur = (int32_t *)(ws + o_cur);
   float4 *sorted = (float4 *)(ws + o_sorted);
   int32_t *tie = (int32_t *)(ws + o_tie);
+  float *sscore = (float *)(ws + o_sscore);
   unsigned long long *mask = (unsigned long long *)(ws + o_mask);
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
   const bool small = cap <= WARP_CAP;
   if (!small) MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));   // the warp kernel writes every count
   dim3 g1((cap + RANK_ELEMS - 1) / RANK_ELEMS, nseg);
-  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie);
+  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie, sscore);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
   nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, small ? 0 : 1, thr, mask);
   MPN_LAUNCHED(ctx);
   if (small) {
     const int use_smem_mask = cap <= WARP_SMEM_MASK_CAP ? 1 : 0;
-    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 18 + 64 * 8 + 64;
+    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 20 + 128 * 8 + 64;
     if (smem > 48 * 1024)
       MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_warp_kernel<<<nseg, WARPK_THREADS, smem, ctx->stream>>>(mask, order, sb_dev, cap, nwords, use_smem_mask, counts_dev,
+    nms_scan_warp_kernel<<<nseg, WARPK_THREADS, smem, ctx->stream>>>(mask, order, sscore, cap, nwords, use_smem_mask, counts_dev,
                                                                     tie, src_idx_dev, keep_idx_dev, keep_counts_dev);
     MPN_LAUNCHED(ctx);
     return MPN_OK;
@@ -636,7 +656,7 @@ int mpn_nms_dense_launch(mpn_ctx *ctx, const float *sb_dev, int n, float thr, in
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * 2, ctx->stream));
   MPN_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int32_t), ctx->stream));
   dim3 g1((n + RANK_ELEMS - 1) / RANK_ELEMS, 1);
-  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, n, nullptr, order, sorted, tie);
+  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, n, nullptr, order, sorted, tie, nullptr);
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, 1);
   nms_dense_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, n, nwords, thr, mask);
