@@ -236,7 +236,7 @@ int conv_direct_nchw_launch(mpn_ctx *ctx, const float *x_nchw, int N, int Cin, i
   const size_t smem = sizeof(float) * DC_CO * Cin * kh * kw;
   MPN_CHECK_ARG(ctx, smem <= 48 * 1024, "conv_direct: filter too large");
   dim3 grid((unsigned)((pixels + 255) / 256), (unsigned)((Cout + DC_CO - 1) / DC_CO));
-  if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout == 64 && y.ld % 8 == 0 && bias) {
+  if (Cin == 3 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && Cout == 64 && y.ld == 64 && bias) {
     const char *e = getenv("MPN_CONV1_TC");           // debug knob: 0 = CUDA-core kernels below
     if (!(e && e[0] == '0')) return conv1_tc_launch(ctx, x_nchw, N, H, W, w, bias, relu, y);
   }

@@ -886,16 +886,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 // mbarrier arrive per warp. The 64 x 27 filter bank is split once per CTA into a resident B tile ([B_hi ; B_lo]).
 // Per tile: A_lo x B_hi (N = 64) and A_hi x [B_hi ; B_lo] (N = 128) for each k16 = 4 MMAs; the accumulator layout is the
 // BN = 64 layout of the generic kernel, so its epilogue (bias, ReLU, split, 16-byte stores) is reused unchanged.
-__device__ __forceinline__ int c1_chunk_first(int warp) { return ((warp - 5) >> 2) & 1; }
-constexpr int C1_BUILD_WARPS = 4, C1_THREADS = 32 * (1 + C1_BUILD_WARPS + EPI_WARPS);
+constexpr int C1_BUILD_WARPS = 4, C1_THREADS = 32 * (1 + C1_BUILD_WARPS + EPI_WARPS);   // two builder groups of 4 warps, one per A stage
 constexpr int C1_A_STAGE = 2 * A_TILE_BYTES, C1_STAGES = 2, C1_B_BYTES = 2 * 64 * 128;
+__device__ __forceinline__ int c1_chunk_first(int warp) { return ((warp - 1 - C1_BUILD_WARPS) >> 2) & 1; }
+
+
+constexpr int C1_STG_PLANE = BM * 128;                 // 128 pixels x 64 channels x bf16 = 16 KB = one contiguous block of the NHWC output
+constexpr int C1_STG_BUF = 2 * C1_STG_PLANE;           // hi + lo
 
 __global__ void __launch_bounds__(C1_THREADS, 1)
 conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *__restrict__ w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sB = smem + C1_STAGES * C1_A_STAGE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sB + C1_B_BYTES);
+  uint8_t *sStg = sB + C1_B_BYTES;                     // 2 output staging buffers (hi plane, lo plane each)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStg + 2 * C1_STG_BUF);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
   const uint32_t a_base = smem_u32(smem), b_base = smem_u32(sB), bar_base = smem_u32(bars);
   auto fullA = [&](int s) { return bar_base + 8u * s; };
@@ -903,8 +908,9 @@ conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (4 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (6 + a); };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long pixels = (long long)N * H * W;
-  const int total_tiles = (int)((pixels + BM - 1) / BM);
+  const int pixels = N * H * W;                        // < 2^31 (checked by the launcher): 32-bit index math throughout
+  const int total_tiles = (pixels + BM - 1) / BM;
+  const bool trace = (p.dbg != nullptr) && blockIdx.x == 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C1_STAGES; ++s) { mbar_init(fullA(s), C1_BUILD_WARPS); mbar_init(emptyA(s), 1); }
@@ -940,11 +946,15 @@ conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *_
   if (warp == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t IDESC_N64 = make_idesc(BM, 64), IDESC_N128 = make_idesc(BM, 128);
+    unsigned long long wc_me = 0ull, wc_mf = 0ull;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1, a = it & 1; const uint32_t ph = (it >> 1) & 1u;
+      const long long t_m0 = clock64();
       mbar_wait(tempty_bar(a), ph ^ 1u);
+      const long long t_m1 = clock64();
       mbar_wait(fullA(s), ph);
+      if (trace) { wc_me += (unsigned long long)(t_m1 - t_m0); wc_mf += (unsigned long long)(clock64() - t_m1); }
       tc_fence_after();
       const uint32_t d1 = __shfl_sync(0xffffffffu, tmem_base + (uint32_t)(a * 192), 0);
       const uint32_t sa = __shfl_sync(0xffffffffu, a_base + (uint32_t)s * C1_A_STAGE, 0);
@@ -961,37 +971,39 @@ conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *_
       }
       __syncwarp();
     }
+    if (trace && lane == 0) printf("[c1 trace] MMA warp: wait tempty %llu cyc, wait fullA %llu cyc, tiles %u\n", wc_me, wc_mf, it);
   } else if (warp <= C1_BUILD_WARPS) {
-    // ===================== im2col builders: one pixel (= one A row) per thread =====================
+    // ===================== im2col builders: one pixel (= one A row) per thread, 32-bit index math =====================
     const int row = (warp - 1) * 32 + lane;
+    const int HW = H * W;
+    unsigned long long wc_ld = 0ull, wc_wait = 0ull;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int s = it & 1; const uint32_t ph = (it >> 1) & 1u;
-      const long long pix = (long long)tile * BM + row;
+      const long long t_l0 = clock64();
+      const int pix = tile * BM + row;
       float in[32];
 #pragma unroll
       for (int k = 27; k < 32; ++k) in[k] = 0.f;
       if (pix < pixels) {
-        const int wo = (int)(pix % W), ho = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
-        const float *xn = x + (size_t)n * 3 * H * W;
+        const int n = pix / HW, rem = pix - n * HW;
+        const int ho = rem / W, wo = rem - ho * W;
+        const float *x0 = x + ((size_t)n * 3 * HW + (size_t)(ho - 1) * W + (wo - 1));      // tap (kh = 0, kw = 0) of channel 0
+        const bool rok[3] = {ho >= 1, true, ho + 1 < H}, cok[3] = {wo >= 1, true, wo + 1 < W};
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const int hi = ho + r - 1;
-            const bool hok = (hi >= 0) && (hi < H);
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const int wi = wo + q - 1;
-              const bool ok = hok && (wi >= 0) && (wi < W);
-              in[(ci * 3 + r) * 3 + q] = ok ? __ldg(xn + ((size_t)ci * H + hi) * W + wi) : 0.f;
-            }
-          }
+            for (int q = 0; q < 3; ++q)
+              in[(ci * 3 + r) * 3 + q] = (rok[r] && cok[q]) ? __ldg(x0 + ci * HW + r * W + q) : 0.f;
       } else {
 #pragma unroll
         for (int k = 0; k < 27; ++k) in[k] = 0.f;
       }
+      const long long t_l1 = clock64();
       mbar_wait(emptyA(s), ph ^ 1u);
+      if (trace) { wc_ld += (unsigned long long)(t_l1 - t_l0); wc_wait += (unsigned long long)(clock64() - t_l1); }
       uint8_t *pa = smem + (size_t)s * C1_A_STAGE + (size_t)row * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1006,24 +1018,84 @@ conv1_tc_kernel(const float *__restrict__ x, int N, int H, int W, const float *_
       __syncwarp();
       if (lane == 0) mbar_arrive(fullA(s));
     }
+    if (trace && lane == 0 && warp == 1) printf("[c1 trace] builder warp: load-issue phase %llu cyc, wait empty %llu cyc\n", wc_ld, wc_wait);
   } else {
-    // ===================== epilogue: the generic kernel's, BN = 64 accumulator layout =====================
+    // ===================== epilogue =====================
+    // Accumulators in the generic kernel's BN = 64 layout (D1 = A_lo x B_hi, D2 = A_hi x [B_hi ; B_lo]). A tile's output is
+    // ONE contiguous 16 KB block per plane (128 consecutive pixels x 64 channels, ld = 64), so the eight warps stage it in
+    // shared memory and one thread ships it with two cp.async.bulk stores: the scattered 16-byte global stores of the
+    // generic epilogue cost ~3.4k cycles of LSU wavefronts per tile here, this costs a few hundred.
     const int ew = warp - 1 - C1_BUILD_WARPS;          // 0..7
-    const int q = warp & 3;
+    const int q = warp & 3;                            // TMEM lane quarter
+    const int ch = c1_chunk_first(warp);               // which 32-channel half this warp handles
     const int row = q * 32 + lane;
+    float bias[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) bias[e] = __ldg(p.bias + ch * 32 + e);
+    unsigned long long wc_t = 0ull, wc_s = 0ull;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1; const uint32_t ph = (it >> 1) & 1u;
-      const long long pix = (long long)tile * BM + row;
+      const long long t_e0 = clock64();
       mbar_wait(tfull_bar(a), ph);
       tc_fence_after();
-      // two warps share each TMEM lane quarter: the chunk parity comes from which of them this is
-      tc_epilogue_tile<64, 1>(p, tmem_base, q, a, 0, pix < pixels, pix, nullptr, c1_chunk_first(warp));
+      const long long t_e1 = clock64();
+      uint32_t v[32], u[32];
+      const uint32_t d1 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 192);
+      tc_ld32(d1 + ch * 32, v);                        // A_lo x B_hi
+      tc_ld32(d1 + 64 + 64 + ch * 32, u);              // A_hi x B_lo
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+      tc_ld32(d1 + 64 + ch * 32, u);                   // A_hi x B_hi
+      tc_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(a));
-      (void)ew;
+      if (lane == 0) mbar_arrive(tempty_bar(a));       // accumulator drained: the MMAs of the tile after next may start
+      // staging buffer reuse: the bulk stores of the tile two steps back (same buffer) must have finished READING it
+      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      uint8_t *stg = sStg + (size_t)(it & 1) * C1_STG_BUF + (size_t)row * 128 + ch * 64;
+      uint32_t oh[16], ol[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        float f0 = (__uint_as_float(v[2 * t]) + __uint_as_float(u[2 * t])) + bias[2 * t];
+        float f1 = (__uint_as_float(v[2 * t + 1]) + __uint_as_float(u[2 * t + 1])) + bias[2 * t + 1];
+        if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+        split_bf16x2(f0, f1, oh[t], ol[t]);
+      }
+      // 16-byte column order rotated by lane pair (2-way instead of 32-way bank conflicts); registers stay statically
+      // indexed: the column's four words are picked with selects
+      const int rot = (lane >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cc = (c + rot) & 3;
+        uint32_t wh[4], wl[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t h01 = (cc & 1) ? oh[4 + t] : oh[t], h23 = (cc & 1) ? oh[12 + t] : oh[8 + t];
+          const uint32_t l01 = (cc & 1) ? ol[4 + t] : ol[t], l23 = (cc & 1) ? ol[12 + t] : ol[8 + t];
+          wh[t] = (cc & 2) ? h23 : h01; wl[t] = (cc & 2) ? l23 : l01;
+        }
+        *reinterpret_cast<uint4 *>(stg + cc * 16) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+        *reinterpret_cast<uint4 *>(stg + C1_STG_PLANE + cc * 16) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ew == 0 && lane == 0) {
+        const int pix0 = tile * BM;
+        const uint32_t bytes = (uint32_t)min(BM, pixels - pix0) * 128u;
+        const uint32_t s_hi = smem_u32(sStg + (size_t)(it & 1) * C1_STG_BUF);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(p.out_hi + (size_t)pix0 * 64), "r"(s_hi), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(p.out_lo + (size_t)pix0 * 64), "r"(s_hi + (uint32_t)C1_STG_PLANE), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (trace) { wc_t += (unsigned long long)(t_e1 - t_e0); wc_s += (unsigned long long)(clock64() - t_e1); }
     }
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the last stores
+    if (trace && lane == 0 && ew == 0) printf("[c1 trace] epilogue warp: wait tfull %llu cyc, drain+stage %llu cyc\n", wc_t, wc_s);
   }
   tc_fence_before();
   __syncthreads();
@@ -1163,7 +1235,9 @@ int conv1_tc_launch(mpn_ctx *ctx, const float *x_nchw, int N, int H, int W, cons
   memset(&tp, 0, sizeof(tp));
   tp.N = N; tp.Ho = H; tp.Wo = W; tp.Cout = 64; tp.bias = bias_dev; tp.relu = relu;
   tp.out_hi = y.hi; tp.out_lo = y.lo; tp.out_ld = y.ld;
-  const int smem = C1_STAGES * C1_A_STAGE + C1_B_BYTES + 1024 + 256;
+  { const char *e = getenv("MPN_C1_TRACE"); if (e && e[0] == '1') tp.dbg = reinterpret_cast<unsigned long long *>(y.hi); }   // any non-null value: the kernel only prints
+  MPN_CHECK_ARG(ctx, y.ld == 64 && (long long)N * H * W < (1ll << 31) - 256, "conv1_tc: dense 64-channel output and < 2^31 pixels");
+  const int smem = C1_STAGES * C1_A_STAGE + C1_B_BYTES + 2 * C1_STG_BUF + 1024 + 256;
   static int attr_set = 0;
   if (!attr_set) {
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
