@@ -274,6 +274,11 @@ def main():
 
     for i in range(args.warmup):
         step_dev(i)
+    if world > 1:
+        # warm the path's one collective too (the first NCCL call builds the communicator: tens of ms that are not
+        # part of a steady-state step); the timed region below runs the same all-gather once more
+        rec_w = torch.zeros((1, mdist.REC), dtype=torch.float32, device=dev)
+        dist.all_gather([torch.empty_like(rec_w) for _ in range(world)], rec_w)
     barrier()
 
     # ---- timed region 1: device-resident throughput (`value`)
