@@ -1,6 +1,8 @@
 // common.cuh — context, error plumbing and small device helpers shared by all TUs
 // of libmpn_b200.so. sm_100a only.
 #pragma once
+#include <utility>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -28,6 +30,8 @@ struct mpn_ctx {
   uint8_t tc_attr_set[16] = {0};
   // stream-K (gemm_tc.cu): per-CTA partial-tile slots + per-(CTA, epilogue warp) flags holding the launch epoch
   float *sk_ws = nullptr; unsigned *sk_flags = nullptr; unsigned sk_epoch = 0;
+  // NMS tie flags live in scratch2 and are reset by their last reader; (pointer, count) of the region known to be zero
+  void *nms_tie_ptr = nullptr; int nms_tie_n = 0;
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };
@@ -84,6 +88,29 @@ inline int mpn_fail(mpn_ctx *ctx, int code, const std::string &msg) {
     (ctx)->launches++;                    \
     MPN_CUDA((ctx), cudaGetLastError());  \
   } while (0)
+
+// ---- programmatic dependent launch for the short kernels of the detect tail: the launch latency and prologue of kernel
+// i+1 overlap kernel i. A kernel launched through mpn_launch_pdl MUST start with MPN_PDL_SYNC() (nothing global is read
+// or written before the previous grid has completed and flushed); MPN_TC_PDL=0 turns the attribute off.
+#define MPN_PDL_SYNC()                                                  \
+  do {                                                                  \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                  \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     \
+  } while (0)
+inline bool mpn_pdl_enabled() {
+  static const int on = [] { const char *e = getenv("MPN_TC_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t mpn_launch_pdl(mpn_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = mpn_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out);    // slot 1
 int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out);   // slot 2

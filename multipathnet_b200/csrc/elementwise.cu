@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256)
 detect_tail_kernel(const float *__restrict__ logits, int64_t R, int C, int K, int do_softmax, float *__restrict__ scores,
                    int nb_sm, const float *__restrict__ deltas, const float *__restrict__ boxes, int do_clamp, float W0,
                    float H0, float *__restrict__ bboxes, int has_norm, float4 mean, float4 stdv) {
+  MPN_PDL_SYNC();
   if ((int)blockIdx.x < nb_sm) softmax_mean_body((int64_t)blockIdx.x * 256 + threadIdx.x, logits, R, C, K, do_softmax, scores);
   else bbox_decode_body((int64_t)(blockIdx.x - nb_sm) * 256 + threadIdx.x, deltas, boxes, R, C, do_clamp, W0, H0, bboxes, has_norm, mean, stdv);
 }
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256)
 gather_scored_kernel(const float *__restrict__ scores, const float *__restrict__ bboxes, int R, int C,
                      float thresh, float *__restrict__ sb, int32_t *__restrict__ src_idx,
                      int32_t *__restrict__ counts) {
+  MPN_PDL_SYNC();
   const int seg = blockIdx.x, j = seg + 1;
   __shared__ int s_wtot[8];
   __shared__ int s_total;
@@ -267,6 +269,7 @@ __global__ void nhwc_split_to_nchw_kernel(const __nv_bfloat16 *__restrict__ ih, 
 // ---- ImageDetect.lua:66-70 project_im_rois: rois = [1, (box-1)*im_scale + 1] -----------------
 __global__ void project_rois_kernel(const float *__restrict__ boxes, int64_t R, float im_scale,
                                     float *__restrict__ rois) {
+  MPN_PDL_SYNC();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
   float4 b = reinterpret_cast<const float4 *>(boxes)[i];
@@ -331,9 +334,9 @@ int mpn_detect_tail_launch(mpn_ctx *ctx, const float *logits_dev, int64_t R, int
   MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R <= 0) return MPN_OK;
   const int nb_sm = (int)nblk(R * 32, 256), nb_dec = (int)nblk(R * C, 256);
-  detect_tail_kernel<<<nb_sm + nb_dec, 256, 0, ctx->stream>>>(
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, detect_tail_kernel, dim3(nb_sm + nb_dec), dim3(256), 0,
       logits_dev, R, C, K, do_softmax, scores_dev, nb_sm, deltas_dev, boxes_dev, do_clamp, W0, H0, bboxes_dev, has_norm,
-      make_float4(mean4[0], mean4[1], mean4[2], mean4[3]), make_float4(std4[0], std4[1], std4[2], std4[3]));
+      make_float4(mean4[0], mean4[1], mean4[2], mean4[3]), make_float4(std4[0], std4[1], std4[2], std4[3])));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -349,7 +352,7 @@ int mpn_gather_scored_launch(mpn_ctx *ctx, const float *scores_dev, const float 
                              float thresh, float *sb_dev, int32_t *src_idx_dev, int32_t *counts_dev) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (C <= 1 || R <= 0) return MPN_OK;
-  gather_scored_kernel<<<C - 1, 256, 0, ctx->stream>>>(scores_dev, bboxes_dev, R, C, thresh, sb_dev, src_idx_dev, counts_dev);
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, gather_scored_kernel, dim3(C - 1), dim3(256), 0, scores_dev, bboxes_dev, R, C, thresh, sb_dev, src_idx_dev, counts_dev));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -397,7 +400,7 @@ int mpn_nhwc_split_to_nchw_launch(mpn_ctx *ctx, const DTensor &in, float *out_de
 int mpn_project_rois_launch(mpn_ctx *ctx, const float *boxes_dev, int64_t R, float im_scale, float *rois_dev) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
   if (R <= 0) return MPN_OK;
-  project_rois_kernel<<<nblk(R, 128), 128, 0, ctx->stream>>>(boxes_dev, R, im_scale, rois_dev);
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, project_rois_kernel, dim3(nblk(R, 128)), dim3(128), 0, boxes_dev, R, im_scale, rois_dev));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }

@@ -47,7 +47,7 @@ __host__ __device__ constexpr int num_stages(int BN, int CG = 1) {
 // latency (~117 cycles measured, independent of N), so for N <= 128 (32/64 cycles of tensor work per instruction) the
 // three bf16x3 products go to separate accumulators (2 for BN=128; for BN=64 one BN-wide A_lo x B_hi and one 2*BN-wide
 // A_hi x [B_hi ; B_lo], which also saves one shared-memory read of A per k16) that the epilogue sums.
-__host__ __device__ constexpr int num_acc(int BN) { return BN == 256 ? 1 : (BN == 128 ? 2 : 3); }
+__host__ __device__ constexpr int num_acc(int BN) { return BN > 128 ? 1 : (BN == 128 ? 2 : 3); }
 __host__ __device__ constexpr int tmem_cols(int BN) { return 512; }       // 2 buffers x num_acc(BN) x BN columns (384 or 512)
 
 struct TcParams {
@@ -268,12 +268,14 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
   const bool pool = (p.pool_hi != nullptr);
   // two warps share each TMEM lane quarter: this one takes chunks ch_first, ch_first + 2, ...
 #pragma unroll 1
-  for (int ch = ch_first; ch < BN / 32; ch += 2) {
+  // (BN = 240 ends in half a chunk: columns past the tile belong to the next accumulator / the next tile and are skipped)
+  const int tile_end = min(p.Cout, nt * BN + BN);
+  for (int ch = ch_first; ch < (BN + 31) / 32; ch += 2) {
     uint32_t v[32];
     const int col0 = nt * BN + ch * 32;
     // bias for this chunk: fetched BEFORE the TMEM load so its latency hides behind tcgen05.ld / wait
     float4 bq[8];
-    const bool bias_vec = (p.bias != nullptr) && (col0 + 32 <= p.Cout);
+    const bool bias_vec = (p.bias != nullptr) && (col0 + 32 <= tile_end);
     if (bias_vec) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) bq[t] = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + t);
@@ -323,15 +325,15 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
         }
       }
     }
-    if ((row_ok || pool) && col0 < p.Cout) {
+    if ((row_ok || pool) && col0 < tile_end) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {             // 8 output channels per group
         const int c = col0 + g * 8;
-        if (c >= p.Cout) break;
+        if (c >= tile_end) break;
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]);
-        const bool full8 = (c + 8 <= p.Cout);
+        const bool full8 = (c + 8 <= tile_end);
         if (p.bias) {
           if (bias_vec) {
             const float4 b0 = bq[2 * g], b1 = bq[2 * g + 1];
@@ -1113,6 +1115,7 @@ struct ReduceParams {
   __nv_bfloat16 *out_hi, *out_lo; long long out_ld; float *out_f32; long long out_f32_ld;
 };
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceParams r) {
+  MPN_PDL_SYNC();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= r.pixels * r.Cout) return;
   const long long pix = idx / r.Cout; const int c = (int)(idx - pix * r.Cout);
@@ -1165,7 +1168,7 @@ inline bool tc_use_pdl() {
 template <int BN, int CG>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
   const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + 1024 /*align*/ + 256 /*barriers*/;
-  constexpr int slot = (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1);
+  constexpr int slot = (BN == 240 ? 6 : (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1));
   if (!ctx->tc_attr_set[slot]) {     // per ctx (= per device): the attribute is per device function
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->tc_attr_set[slot] = 1;
@@ -1307,7 +1310,11 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
       const long long tiles_m = mode ? r_tiles_m : g_tiles_m;
       for (int cg = 1; cg <= max_cg; ++cg) {
         if (cg == 2 && tiles_m < 2) continue;
-        for (int bn = 256; bn >= 64; bn >>= 1) {
+        for (int bi = 0; bi < 4; ++bi) {
+          // N tile: 256 / 128 / 64, plus 240 for flat GEMMs on CTA pairs: a 1000 x 4096 head GEMM is 4 x 16 = 64 units
+          // (of 74 pairs) at 256 but 4 x 18 = 72 units at 240, each 6% shorter, and whole-tile K loops keep chunk invariance
+          const int bn = bi == 0 ? 256 : (bi == 1 ? 240 : (bi == 2 ? 128 : 64));
+          if (bn == 240 && !(pl.flat && cg == 2 && mode == 0 && p.Cout >= 1024)) continue;
           if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
           if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
           const long long tn_ = (p.Cout + bn - 1) / bn;
@@ -1434,7 +1441,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     r.bias = p.bias; r.res_hi = p.res.hi; r.res_lo = p.res.lo; r.res_ld = p.res.ld; r.relu = p.relu;
     r.out_hi = p.y.hi; r.out_lo = p.y.lo; r.out_ld = p.y.ld; r.out_f32 = p.y.f32; r.out_f32_ld = p.y_f32_ld;
     const long long total = pixels * p.Cout;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(r);
+    MPN_CUDA(ctx, mpn_launch_pdl(ctx, splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, r));
     MPN_LAUNCHED(ctx);
     return MPN_OK;
   }
@@ -1445,6 +1452,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   if (pl.CG == 2) {
     switch (pl.BN) {
       case 256: return launch_bn<256, 2>(ctx, pl, tp);
+      case 240: return launch_bn<240, 2>(ctx, pl, tp);
       case 128: return launch_bn<128, 2>(ctx, pl, tp);
       default: return launch_bn<64, 2>(ctx, pl, tp);
     }

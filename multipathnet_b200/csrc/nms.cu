@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(RANK_THREADS)
 nms_rank_kernel(const float *__restrict__ sb, int cap, const int32_t *__restrict__ counts,
                 int32_t *__restrict__ order, float4 *__restrict__ sorted_boxes,
                 int32_t *__restrict__ tie_flag, float *__restrict__ sorted_score) {
+  MPN_PDL_SYNC();
   const int seg = blockIdx.y;
   const int n = counts ? counts[seg] : cap;
   if ((int)blockIdx.x * RANK_ELEMS >= n) return;
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(64)
 nms_mask_kernel(const float4 *__restrict__ sorted_boxes, int cap, int nwords_cap,
                 const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag, int skip_tied,
                 float thr, unsigned long long *__restrict__ mask) {
+  MPN_PDL_SYNC();
   const int seg = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;
   if (skip_tied && tie_flag[seg]) return;       // large-N path: nms_exact_kernel handles tied segments
@@ -381,13 +383,14 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
 __global__ void __launch_bounds__(WARPK_THREADS)
 nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t *__restrict__ order,
                      const float *__restrict__ sorted_score, int cap, int nwords_cap, int use_smem_mask,
-                     const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag,
+                     const int32_t *__restrict__ counts, int32_t *__restrict__ tie_flag,
                      const int32_t *__restrict__ src_idx, int32_t *__restrict__ keep_idx,
                      int32_t *__restrict__ keep_counts) {
+  MPN_PDL_SYNC();
   extern __shared__ unsigned long long s_dyn[];
   const int seg = blockIdx.x;
   const int n = counts ? counts[seg] : cap;
-  if (n <= 0) { if (threadIdx.x == 0) keep_counts[seg] = 0; return; }
+  if (n <= 0) { if (threadIdx.x == 0) { keep_counts[seg] = 0; tie_flag[seg] = 0; } return; }
   const int nwords = (n + 63) >> 6;
   const bool tie = tie_flag[seg] != 0;
   // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [tn 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap]
@@ -454,7 +457,7 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
     const int o = s_ord[s_keep[k] & 0x7fff];
     keep_idx[(size_t)seg * cap + k] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
   }
-  if (lane == 0) keep_counts[seg] = nkeep;
+  if (lane == 0) { keep_counts[seg] = nkeep; tie_flag[seg] = 0; }     // last reader of the flag: leave it zero for the next call
 }
 
 constexpr int EXACT_THREADS = 512;
@@ -569,22 +572,27 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   int32_t *tie = (int32_t *)(ws + o_tie);
   float *sscore = (float *)(ws + o_sscore);
   unsigned long long *mask = (unsigned long long *)(ws + o_mask);
-  MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
   const bool small = cap <= WARP_CAP;
+  // the warp kernel (last reader) leaves the flags zero, so steady-state calls with the same layout need no memset
+  if (!small || ctx->nms_tie_ptr != (void *)tie || ctx->nms_tie_n < nseg) {
+    MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * nseg, ctx->stream));
+    ctx->nms_tie_ptr = small ? (void *)tie : nullptr; ctx->nms_tie_n = small ? nseg : 0;
+  }
   if (!small) MPN_CUDA(ctx, cudaMemsetAsync(keep_counts_dev, 0, sizeof(int32_t) * nseg, ctx->stream));   // the warp kernel writes every count
   dim3 g1((cap + RANK_ELEMS - 1) / RANK_ELEMS, nseg);
-  nms_rank_kernel<<<g1, RANK_THREADS, 0, ctx->stream>>>(sb_dev, cap, counts_dev, order, sorted, tie, sscore);
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_rank_kernel, g1, dim3(RANK_THREADS), 0, sb_dev, cap, counts_dev, order, sorted, tie, sscore));
   MPN_LAUNCHED(ctx);
   dim3 g2(nwords, nwords, nseg);
-  nms_mask_kernel<<<g2, 64, 0, ctx->stream>>>(sorted, cap, nwords, counts_dev, tie, small ? 0 : 1, thr, mask);
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_mask_kernel, g2, dim3(64), 0, (const float4 *)sorted, cap, nwords, counts_dev, (const int32_t *)tie, small ? 0 : 1, thr, mask));
   MPN_LAUNCHED(ctx);
   if (small) {
     const int use_smem_mask = cap <= WARP_SMEM_MASK_CAP ? 1 : 0;
     const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 20 + 128 * 8 + 64;
     if (smem > 48 * 1024)
       MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_scan_warp_kernel<<<nseg, WARPK_THREADS, smem, ctx->stream>>>(mask, order, sscore, cap, nwords, use_smem_mask, counts_dev,
-                                                                    tie, src_idx_dev, keep_idx_dev, keep_counts_dev);
+    MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_scan_warp_kernel, dim3(nseg), dim3(WARPK_THREADS), smem, (const unsigned long long *)mask,
+                                 (const int32_t *)order, (const float *)sscore, cap, nwords, use_smem_mask, counts_dev, tie,
+                                 src_idx_dev, keep_idx_dev, keep_counts_dev));
     MPN_LAUNCHED(ctx);
     return MPN_OK;
   }
@@ -652,6 +660,7 @@ int mpn_nms_dense_launch(mpn_ctx *ctx, const float *sb_dev, int n, float thr, in
   int32_t *order = (int32_t *)(ws + o_order);
   float4 *sorted = (float4 *)(ws + o_sorted);
   int32_t *tie = (int32_t *)(ws + o_tie);            // tie[0]: real flag (ignored), tie[1]: always 0
+  ctx->nms_tie_ptr = nullptr; ctx->nms_tie_n = 0;    // scratch2 is re-laid out: the batched path must zero its flags again
   unsigned long long *mask = (unsigned long long *)(ws + o_mask);
   MPN_CUDA(ctx, cudaMemsetAsync(tie, 0, sizeof(int32_t) * 2, ctx->stream));
   MPN_CUDA(ctx, cudaMemsetAsync(count_dev, 0, sizeof(int32_t), ctx->stream));
