@@ -193,6 +193,7 @@ nms_scan_kernel(const unsigned long long *__restrict__ mask, const int32_t *__re
 //   The label bookkeeping is LAZY: the walk records every selection and each box's death round; only when a round
 //   actually has two live boxes with the top score is the slot history replayed up to that round (by one lane,
 //   no warp collectives), and the tie broken by label. Segments whose ties never meet pay (almost) nothing.
+__device__ int g_nms_trace = 0;      // MPN_NMS_TRACE=1: block 0 of the warp kernel prints its phase times (tools/nms_diag.py)
 constexpr int WARP_CAP = 4096;
 constexpr int WARP_SMEM_MASK_CAP = 1024;
 constexpr int WARPK_THREADS = 256;
@@ -209,7 +210,7 @@ struct WalkCtx {
 // nms.c's tie order needs is LAZY: only when a round really has two live boxes with the top score does `replay`
 // re-walk the recorded selections [replayed, nkeep) (liveness re-derived from the same mask rows) while tracking the
 // head moves, after which the tie is broken by slot label. Segments whose ties never meet pay one shuffle per round.
-template <bool TIE, bool TWO>
+template <bool TIE, bool TWO, bool SMEM>
 __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
   const int n = c.n, nwords = c.nwords;
   auto init_word = [&](int w) -> unsigned long long {
@@ -217,7 +218,7 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
     return (w == nwords - 1 && (n & 63)) ? (~0ull << (n & 63)) : 0ull;
   };
   auto mask_word = [&](int row, int w) -> unsigned long long {
-    return c.use_smem_mask ? c.s_mask[row * nwords + w] : __ldg(c.m + (size_t)row * c.nwords_cap + w);
+    return SMEM ? c.s_mask[row * nwords + w] : __ldg(c.m + (size_t)row * c.nwords_cap + w);
   };
   unsigned long long rem0 = init_word(lane), rem1 = TWO ? init_word(lane + 32) : ~0ull;
   // tienext bit p: score[p] == score[p+1] in sorted order (ballots of the whole block, see the kernel prologue)
@@ -238,51 +239,51 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
     const int row0 = cw * 64;
     unsigned long long cur = __shfl_sync(0xffffffffu, (TWO && half) ? rem1 : rem0, wl);
     const unsigned long long tw = TIE ? __shfl_sync(0xffffffffu, (TWO && half) ? tn1 : tn0, wl) : 0ull;
-    // ---- resolve the chunk's rows against each other: every lane runs the same scalar loop over the LIVE rows only
-    //      (typically 5-15 of 64): next live bit, its diagonal word (one broadcast load), clear what it suppresses. A single
-    //      warp pays ~5 cycles per dependent instruction, so the loop body is kept to a dozen instructions; a live box
-    //      whose score continues into the next row (tie) stops the loop and takes the general round below.
-    unsigned long long kb = 0ull; int tie_b = -1;
+    // ---- resolve the chunk: every lane runs the same scalar loop over the LIVE rows only (typically 5-15 of 64): next
+    //      live bit, its diagonal word (one broadcast load) clears what it suppresses inside the chunk; in the same
+    //      iteration, off the serial chain, each lane ORs its own later word of that row into its removed-set and lane 0
+    //      records the row. A single warp pays ~5-10 cycles per dependent instruction, so the chain is ffs -> address ->
+    //      load -> and. A live box whose score continues into the next row (tie) stops the loop: general round below.
+    int tie_b = -1;
     {
-      unsigned long long live = ~cur;
-      while (live) {
-        const int b = __ffsll((long long)live) - 1;
-        if (TIE && ((tw >> b) & 1ull)) {
-          // tied with the next row; skipped when that row is already dead and the tie group ends there (the common pair case)
-          const bool pair_done = (b < 63) && !((live >> ((b + 1) & 63)) & 1ull) && !((tw >> ((b + 1) & 63)) & 1ull);
-          if (!pair_done) { tie_b = b; break; }
-        }
-        const unsigned long long d = mask_word(row0 + b, cw);      // includes the diagonal bit b
-        kb |= 1ull << b;
-        live &= ~d;
-      }
-      cur = ~live;
-    }
-    // ---- record the kept rows (emission order = ascending sorted position inside the chunk)
-    if ((kb >> lane) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << lane) - 1ull))] = (unsigned short)(row0 + lane);
-    if ((kb >> (lane + 32)) & 1ull) c.s_keep[nkeep + __popcll(kb & ((1ull << (lane + 32)) - 1ull))] = (unsigned short)(row0 + lane + 32);
-    nkeep += __popcll(kb);
-    // ---- deferred suppression: OR the kept rows into the words after cw (lane-parallel over words; four loads in flight)
-    {
+      // lanes that own no later word read the diagonal word instead and discard it: no divergent branch in the loop
       const bool on0 = (lane > cw) && (lane < nwords);
       const bool on1 = TWO && (lane + 32 > cw) && (lane + 32 < nwords);
-      unsigned long long acc0 = 0ull, acc1 = 0ull, bits = kb;
-      while (bits) {
-        const int b0 = __ffsll((long long)bits) - 1; bits &= bits - 1ull;
-        const int b1 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
-        const int b2 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
-        const int b3 = bits ? __ffsll((long long)bits) - 1 : b0; bits &= bits - 1ull;
-        if (on0) {
-          const unsigned long long m0 = mask_word(row0 + b0, lane), m1 = mask_word(row0 + b1, lane);
-          const unsigned long long m2 = mask_word(row0 + b2, lane), m3 = mask_word(row0 + b3, lane);
-          acc0 |= (m0 | m1) | (m2 | m3);
-        }
-        if (on1) {
-          const unsigned long long m0 = mask_word(row0 + b0, lane + 32), m1 = mask_word(row0 + b1, lane + 32);
-          const unsigned long long m2 = mask_word(row0 + b2, lane + 32), m3 = mask_word(row0 + b3, lane + 32);
-          acc1 |= (m0 | m1) | (m2 | m3);
-        }
+      const int w0 = on0 ? lane : cw, w1 = on1 ? lane + 32 : cw;
+      const unsigned long long k0 = on0 ? ~0ull : 0ull, k1 = on1 ? ~0ull : 0ull;
+      unsigned long long acc0 = 0ull, acc1 = 0ull;
+      unsigned lo = ~(unsigned)cur, hi = ~(unsigned)(cur >> 32);       // live rows of the chunk, as two 32-bit halves
+      const unsigned tlo = (unsigned)tw, thi = (unsigned)(tw >> 32);
+      // one iteration = one kept row `b` (bit index inside the chunk)
+#define MPN_NMS_KEEP_ROW(b)                                                         \
+      {                                                                            \
+        const int row = row0 + (b);                                                \
+        const unsigned long long d = mask_word(row, cw);                           \
+        acc0 |= mask_word(row, w0) & k0;                                           \
+        if (TWO) acc1 |= mask_word(row, w1) & k1;                                  \
+        c.s_keep[nkeep] = (unsigned short)row;   /* every lane, same value */      \
+        ++nkeep;                                                                   \
+        lo &= ~(unsigned)d; hi &= ~(unsigned)(d >> 32);                            \
       }
+      while (lo) {
+        const int b = __ffs(lo) - 1;
+        if (TIE && ((tlo >> b) & 1u)) {
+          // tied with the next row; skipped when that row is already dead and the tie group ends there (the common pair case)
+          const unsigned nl = (b < 31) ? (lo >> (b + 1)) & 1u : (hi & 1u), nt = (b < 31) ? (tlo >> (b + 1)) & 1u : (thi & 1u);
+          if (nl | nt) { tie_b = b; break; }
+        }
+        MPN_NMS_KEEP_ROW(b)
+      }
+      while (tie_b < 0 && hi) {
+        const int b = __ffs(hi) - 1;
+        if (TIE && ((thi >> b) & 1u)) {
+          const bool pair_done = (b < 31) && !((hi >> (b + 1)) & 1u) && !((thi >> (b + 1)) & 1u);
+          if (!pair_done) { tie_b = 32 + b; break; }
+        }
+        MPN_NMS_KEEP_ROW(32 + b)
+      }
+#undef MPN_NMS_KEEP_ROW
+      cur = ~(((unsigned long long)hi << 32) | lo);
       rem0 |= acc0; if (TWO) rem1 |= acc1;
       if (lane == wl) { if (TWO && half) rem1 = cur; else rem0 = cur; }
     }
@@ -389,6 +390,8 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   MPN_PDL_SYNC();
   extern __shared__ unsigned long long s_dyn[];
   const int seg = blockIdx.x;
+  const bool trace = (g_nms_trace != 0) && seg == 0;
+  const long long t0 = clock64();
   const int n = counts ? counts[seg] : cap;
   if (n <= 0) { if (threadIdx.x == 0) { keep_counts[seg] = 0; tie_flag[seg] = 0; } return; }
   const int nwords = (n + 63) >> 6;
@@ -448,16 +451,25 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   }
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
+  const long long t1 = clock64();
   int nkeep;
   const WalkCtx wc{s_mask, m, s_tn, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
-  if (tie) nkeep = (nwords > 32) ? nms_walk<true, true>(wc, lane) : nms_walk<true, false>(wc, lane);
-  else nkeep = (nwords > 32) ? nms_walk<false, true>(wc, lane) : nms_walk<false, false>(wc, lane);
+  if (use_smem_mask) {          // n <= 1024, hence one removed-word per lane
+    nkeep = tie ? nms_walk<true, false, true>(wc, lane) : nms_walk<false, false, true>(wc, lane);
+  } else {
+    if (tie) nkeep = (nwords > 32) ? nms_walk<true, true, false>(wc, lane) : nms_walk<true, false, false>(wc, lane);
+    else nkeep = (nwords > 32) ? nms_walk<false, true, false>(wc, lane) : nms_walk<false, false, false>(wc, lane);
+  }
   __syncwarp();
+  const long long t2 = clock64();
   for (int k = lane; k < nkeep; k += 32) {
     const int o = s_ord[s_keep[k] & 0x7fff];
     keep_idx[(size_t)seg * cap + k] = src_idx ? src_idx[(size_t)seg * cap + o] : o;
   }
   if (lane == 0) { keep_counts[seg] = nkeep; tie_flag[seg] = 0; }     // last reader of the flag: leave it zero for the next call
+  if (trace && lane == 0)
+    printf("[nms trace] seg 0: n %d tie %d kept %d | prologue %lld cyc, walk %lld cyc, output %lld cyc\n", n, (int)tie, nkeep,
+           t1 - t0, t2 - t1, clock64() - t2);
 }
 
 constexpr int EXACT_THREADS = 512;
@@ -590,6 +602,14 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
     const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 20 + 128 * 8 + 64;
     if (smem > 48 * 1024)
       MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+      static int trace_set = -1;
+      if (trace_set < 0) {
+        const char *e = getenv("MPN_NMS_TRACE");
+        trace_set = (e && e[0] == '1') ? 1 : 0;
+        if (trace_set) MPN_CUDA(ctx, cudaMemcpyToSymbol(g_nms_trace, &trace_set, sizeof(int)));
+      }
+    }
     MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_scan_warp_kernel, dim3(nseg), dim3(WARPK_THREADS), smem, (const unsigned long long *)mask,
                                  (const int32_t *)order, (const float *)sscore, cap, nwords, use_smem_mask, counts_dev, tie,
                                  src_idx_dev, keep_idx_dev, keep_counts_dev));
