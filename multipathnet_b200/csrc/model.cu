@@ -10,6 +10,7 @@
 #include "conv_gemm.cuh"
 #include "roi.cuh"
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <memory>
 #include <set>
@@ -265,8 +266,14 @@ int plan_trunk(mpn_model *m, int H, int W) {
       MPN_CHECK_ARG(ctx, m->trunk_slots.count(slot) && slot > 0, "tower level reads an undefined trunk slot");
       const DTensor &f = m->trunk_slots[slot];
       mpn_model::Pyramid &P = m->pyramids[slot];
+      // a level with block 2^k is only ever used for a bin window whose smaller side is >= 2^k cells; a bin of this tower
+      // spans at most ceil(region_scale * map_side / pooled_side) + 1 cells of the (clipped) region, so higher levels are dead
+      const double rs = T.region == 0 ? 1.0 : (T.region == 1 ? 1.5 : (T.region == 2 ? 2.0 : 4.0));
+      const long long max_bin = std::min<long long>(std::min(f.H, f.W),
+          (long long)std::ceil(rs * (double)std::max(f.H, f.W) / (double)std::min(T.pooled_h, T.pooled_w)) + 2);
       int nlev = 1;
-      while (nlev < ROI_MAX_LEVELS && (1 << nlev) <= std::min(f.H, f.W)) ++nlev;
+      while (nlev < ROI_MAX_LEVELS && (1ll << nlev) <= max_bin) ++nlev;
+      nlev = std::max(nlev, P.nlev);                                   // several towers may share the slot: keep the deepest
       P.nlev = nlev;
       P.lv.resize(nlev);
       for (int k = 0; k < nlev; ++k) {

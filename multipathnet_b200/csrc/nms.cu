@@ -96,8 +96,11 @@ nms_mask_kernel(const float4 *__restrict__ sorted_boxes, int cap, int nwords_cap
                 const int32_t *__restrict__ counts, const int32_t *__restrict__ tie_flag, int skip_tied,
                 float thr, unsigned long long *__restrict__ mask) {
   MPN_PDL_SYNC();
-  const int seg = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
-  if (cb < rb) return;
+  // grid.x enumerates the nb*(nb+1)/2 tiles of the upper triangle: tile t -> (rb, cb >= rb)
+  const int seg = blockIdx.z;
+  int rb = 0, cb = (int)blockIdx.x;
+  for (int rowlen = nwords_cap; cb >= rowlen; cb -= rowlen, --rowlen) ++rb;
+  cb += rb;
   if (skip_tied && tie_flag[seg]) return;       // large-N path: nms_exact_kernel handles tied segments
   const int n = counts ? counts[seg] : cap;
   if (rb * 64 >= n || cb * 64 >= n) return;
@@ -594,7 +597,7 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   dim3 g1((cap + RANK_ELEMS - 1) / RANK_ELEMS, nseg);
   MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_rank_kernel, g1, dim3(RANK_THREADS), 0, sb_dev, cap, counts_dev, order, sorted, tie, sscore));
   MPN_LAUNCHED(ctx);
-  dim3 g2(nwords, nwords, nseg);
+  dim3 g2((unsigned)(nwords * (nwords + 1) / 2), 1, nseg);   // upper-triangle tiles only
   MPN_CUDA(ctx, mpn_launch_pdl(ctx, nms_mask_kernel, g2, dim3(64), 0, (const float4 *)sorted, cap, nwords, counts_dev, (const int32_t *)tie, small ? 0 : 1, thr, mask));
   MPN_LAUNCHED(ctx);
   if (small) {
