@@ -475,6 +475,7 @@ int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bi
   p.x.hi = a.at<__nv_bfloat16>(o_ah); p.x.lo = a.at<__nv_bfloat16>(o_al); p.x.N = M; p.x.H = 1; p.x.W = 1; p.x.C = K; p.x.ld = K;
   p.w_hi = a.at<__nv_bfloat16>(o_bh); p.w_lo = a.at<__nv_bfloat16>(o_bl); p.bias = bias ? a.at<float>(o_bias) : nullptr;
   p.Cout = (int)N; p.relu = relu;
+  p.m_invariant = 1;     // a Linear over independent rows: the result of a row must not depend on M
   p.y.f32 = a.at<float>(o_c); p.y.N = M; p.y.H = 1; p.y.W = 1; p.y.C = N; p.y.ld = N; p.y_f32_ld = N;
   if (impl == 1) { MPN_TRY(conv_ref_launch(ctx, p)); }
   else { ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl)); }

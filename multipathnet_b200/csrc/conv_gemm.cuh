@@ -17,6 +17,10 @@ struct ConvProblem {
   int64_t y_f32_ld = 0;
   DTensor pool;                    // optional: 2x2/2 ceil max pool of y written by the epilogue (3x3 tcgen05 kernel only)
   int pool_only = 0;               // 1: y itself is not written (nobody else reads it)
+  // 1: rows are independent samples (per-ROI layers): the plan may depend on (Cout, K) only where it affects rounding —
+  // accumulator grouping, split-K count, no stream-K — so a row's result does not change with the number of rows in
+  // the call (chunked forward == full forward, bit for bit: modules/test.lua:85-98, ImageDetect.lua:126-133)
+  int m_invariant = 0;
   void *dbg = nullptr;             // diagnostics: device buffer of 16 x u64 pipeline-wait counters (tools/engine_sweep.py)
 };
 

@@ -1316,6 +1316,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
           const int bn = bi == 0 ? 256 : (bi == 1 ? 240 : (bi == 2 ? 128 : 64));
           if (bn == 240 && !(pl.flat && cg == 2 && mode == 0 && p.Cout >= 1024)) continue;
           if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
+          if (p.m_invariant && num_acc(bn) != (p.Cout > 128 ? 1 : (p.Cout > 64 ? 2 : 3))) continue;   // rounding must not depend on M
           if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
           const long long tn_ = (p.Cout + bn - 1) / bn;
           const long long units = ((tiles_m + cg - 1) / cg) * tn_;
@@ -1325,7 +1326,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
           const double cyc = std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
           double cost = (double)rounds * cyc * cblocks;
           int sk = 0;
-          if (mode == 1 && allow_sk) {
+          if (mode == 1 && allow_sk && !p.m_invariant) {
             // stream-K: no round quantisation, but one partial-tile exchange per pair (~6k cycles) and >= 4 steps per pair
             // (measured: merging one partial costs the finisher ~40 cycles per accumulator column; it is hidden behind the
             //  following tiles unless a pair's whole range is shorter than about two tiles)
@@ -1369,7 +1370,8 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     const long long slots = ctx->sm_count / pl.CG;
     const long long num_kb = (long long)p.kh * p.kw * (p.x.C / BK);
     long long sk = std::min<long long>(num_kb / 8, 8);
-    if (sk < 2 || units * sk > slots) sk = 1;
+    if (p.m_invariant) { if (!(pl.flat && p.Cout <= 128) || sk < 2) sk = 1; }      // a function of (Cout, K) only
+    else if (sk < 2 || units * sk > slots) sk = 1;
     const char *env2 = getenv("MPN_TC_SPLITK");
     if (env2 && env2[0] == '0') sk = 1;
     pl.splitk = (int)std::max<long long>(sk, 1);

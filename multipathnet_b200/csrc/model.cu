@@ -165,7 +165,7 @@ DTensor make_split_view(SplitBuf &b, int64_t N, int64_t H, int64_t W, int64_t C)
 // Build the executable form of one CONV layer (weights prepared, problem + plan filled).
 // flat_from: if the layer consumes a FLATTENed (h,w,c) tensor, its Linear weight [Cout][c*h*w]
 // in (c,h,w) order is re-laid as a (kh=h,kw=w,Cin=c) conv weight => (h,w,c) K order.
-int build_conv(mpn_model *m, LayerExec &e, const DTensor &in, DTensor out, int fh, int fw, int fc) {
+int build_conv(mpn_model *m, LayerExec &e, const DTensor &in, DTensor out, int fh, int fw, int fc, bool per_roi = false) {
   mpn_ctx *ctx = m->ctx;
   const mpn_layer &L = e.L;
   e.in = in; e.out = out;
@@ -173,6 +173,7 @@ int build_conv(mpn_model *m, LayerExec &e, const DTensor &in, DTensor out, int f
   p = ConvProblem();
   p.x = in; p.Cout = L.cout; p.kh = L.kh; p.kw = L.kw; p.stride = L.stride; p.pad = L.pad; p.relu = L.relu;
   p.y = out; p.y_f32_ld = out.ld;
+  p.m_invariant = per_roi ? 1 : 0;
   MPN_CHECK_ARG(ctx, L.weight >= 0, "conv layer without weight");
   if (fc > 0) { MPN_TRY(prepare_conv_weight(m, L.weight, L.cout, fc, fh, fw)); }
   else { MPN_TRY(prepare_conv_weight(m, L.weight, L.cout, L.cin, L.kh, L.kw)); }
@@ -434,7 +435,7 @@ int plan_heads(mpn_model *m, int64_t R) {
       }
       if (L.kind == MPN_LAYER_CONV) {
         const bool from_flat = (L.in_slot == flat_slot) && L.kh == 1 && L.kw == 1;
-        MPN_TRY(build_conv(m, e, in, out, from_flat ? flat_h : 0, from_flat ? flat_w : 0, from_flat ? flat_c : 0));
+        MPN_TRY(build_conv(m, e, in, out, from_flat ? flat_h : 0, from_flat ? flat_w : 0, from_flat ? flat_c : 0, /*per_roi=*/true));
         if (L.residual_slot >= 0) {
           MPN_CHECK_ARG(ctx, X.slots.count(L.residual_slot), "tower residual slot undefined");
           e.prob.res = X.slots[L.residual_slot];
@@ -461,7 +462,7 @@ int plan_heads(mpn_model *m, int64_t R) {
     DTensor in; in.hi = (__nv_bfloat16 *)m->concat_buf.hi.p + h.col_begin; in.lo = (__nv_bfloat16 *)m->concat_buf.lo.p + h.col_begin;
     in.N = R; in.H = 1; in.W = 1; in.C = h.col_len; in.ld = width;
     DTensor out; out.f32 = out_ptr; out.N = R; out.H = 1; out.W = 1; out.C = h.cout; out.ld = h.cout;
-    MPN_TRY(build_conv(m, e, in, out, 0, 0, 0));
+    MPN_TRY(build_conv(m, e, in, out, 0, 0, 0, /*per_roi=*/true));
     m->head_flops += 2.0 * (double)h.col_len * h.cout * (double)R;
     m->head_exec.push_back(e);
     return MPN_OK;

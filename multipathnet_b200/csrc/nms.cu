@@ -202,7 +202,7 @@ constexpr int WARP_SMEM_MASK_CAP = 1024;
 constexpr int WARPK_THREADS = 256;
 
 struct WalkCtx {
-  const unsigned long long *s_mask, *m, *s_tn; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
+  const unsigned long long *s_mask, *m, *s_tn; unsigned long long *s_diag; const float *s_score; int *s_label, *s_owner; unsigned long long *s_rrem;
   unsigned short *s_keep, *s_death, *s_qalt;
   int n, nwords, nwords_cap, use_smem_mask;
 };
@@ -258,12 +258,24 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
       unsigned lo = ~(unsigned)cur, hi = ~(unsigned)(cur >> 32);       // live rows of the chunk, as two 32-bit halves
       const unsigned tlo = (unsigned)tw, thi = (unsigned)(tw >> 32);
       // one iteration = one kept row `b` (bit index inside the chunk)
+      // mask in L2 (n > 1024): the chunk's 64 diagonal words are prefetched into shared memory with one round trip, the
+      // kept rows are only recorded in the loop, and their later words are OR-ed in afterwards with eight loads in flight
+      unsigned kb_lo = 0u, kb_hi = 0u;
+      if (!SMEM) {
+        c.s_diag[lane] = __ldg(c.m + (size_t)min(row0 + lane, n - 1) * c.nwords_cap + cw);
+        c.s_diag[lane + 32] = __ldg(c.m + (size_t)min(row0 + 32 + lane, n - 1) * c.nwords_cap + cw);
+        __syncwarp();
+      }
 #define MPN_NMS_KEEP_ROW(b)                                                         \
       {                                                                            \
         const int row = row0 + (b);                                                \
-        const unsigned long long d = mask_word(row, cw);                           \
-        acc0 |= mask_word(row, w0) & k0;                                           \
-        if (TWO) acc1 |= mask_word(row, w1) & k1;                                  \
+        const unsigned long long d = SMEM ? mask_word(row, cw) : c.s_diag[(b)];    \
+        if (SMEM) {                                                                \
+          acc0 |= mask_word(row, w0) & k0;                                         \
+          if (TWO) acc1 |= mask_word(row, w1) & k1;                                \
+        } else {                                                                   \
+          if ((b) < 32) kb_lo |= 1u << ((b) & 31); else kb_hi |= 1u << ((b) & 31); \
+        }                                                                          \
         c.s_keep[nkeep] = (unsigned short)row;   /* every lane, same value */      \
         ++nkeep;                                                                   \
         lo &= ~(unsigned)d; hi &= ~(unsigned)(d >> 32);                            \
@@ -286,6 +298,22 @@ __device__ __forceinline__ int nms_walk(const WalkCtx &c, const int lane) {
         MPN_NMS_KEEP_ROW(32 + b)
       }
 #undef MPN_NMS_KEEP_ROW
+      if (!SMEM) {
+        unsigned long long bits = ((unsigned long long)kb_hi << 32) | kb_lo;
+        while (bits) {
+          int rb[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { rb[t] = bits ? __ffsll((long long)bits) - 1 : rb[0]; bits &= bits - 1ull; }
+          unsigned long long m0[8], m1[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            m0[t] = mask_word(row0 + rb[t], w0);
+            if (TWO) m1[t] = mask_word(row0 + rb[t], w1);
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) { acc0 |= m0[t] & k0; if (TWO) acc1 |= m1[t] & k1; }
+        }
+      }
       cur = ~(((unsigned long long)hi << 32) | lo);
       rem0 |= acc0; if (TWO) rem1 |= acc1;
       if (lane == wl) { if (TWO && half) rem1 = cur; else rem0 = cur; }
@@ -399,12 +427,13 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   if (n <= 0) { if (threadIdx.x == 0) { keep_counts[seg] = 0; tie_flag[seg] = 0; } return; }
   const int nwords = (n + 63) >> 6;
   const bool tie = tie_flag[seg] != 0;
-  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [tn 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap]
+  // dynamic smem carve-up: [mask n*nwords u64 (optional)] [rrem 64 u64] [tn 64 u64] [diag 64 u64] [score f32 cap] [label i32 cap] [owner i32 cap]
   //                        [keep u16 cap] [death u16 cap] [qalt u16 cap] [ord u16 cap]
   unsigned long long *s_mask = s_dyn;
   unsigned long long *s_rrem = s_dyn + (use_smem_mask ? (size_t)cap * nwords_cap : 0);
   unsigned long long *s_tn = s_rrem + 64;
-  float *s_score = reinterpret_cast<float *>(s_tn + 64);
+  unsigned long long *s_diag = s_tn + 64;
+  float *s_score = reinterpret_cast<float *>(s_diag + 64);
   int *s_label = reinterpret_cast<int *>(s_score + cap);
   int *s_owner = s_label + cap;
   unsigned short *s_keep = reinterpret_cast<unsigned short *>(s_owner + cap);
@@ -456,7 +485,7 @@ nms_scan_warp_kernel(const unsigned long long *__restrict__ mask, const int32_t 
   const int lane = threadIdx.x;
   const long long t1 = clock64();
   int nkeep;
-  const WalkCtx wc{s_mask, m, s_tn, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
+  const WalkCtx wc{s_mask, m, s_tn, s_diag, s_score, s_label, s_owner, s_rrem, s_keep, s_death, s_qalt, n, nwords, nwords_cap, use_smem_mask};
   if (use_smem_mask) {          // n <= 1024, hence one removed-word per lane
     nkeep = tie ? nms_walk<true, false, true>(wc, lane) : nms_walk<false, false, true>(wc, lane);
   } else {
@@ -602,7 +631,7 @@ int mpn_nms_launch(mpn_ctx *ctx, const float *sb_dev, int cap, int nseg, const i
   MPN_LAUNCHED(ctx);
   if (small) {
     const int use_smem_mask = cap <= WARP_SMEM_MASK_CAP ? 1 : 0;
-    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 20 + 128 * 8 + 64;
+    const size_t smem = (use_smem_mask ? sizeof(unsigned long long) * (size_t)cap * nwords : 0) + (size_t)cap * 20 + 192 * 8 + 64;
     if (smem > 48 * 1024)
       MPN_CUDA(ctx, cudaFuncSetAttribute(nms_scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {

@@ -43,6 +43,22 @@ def test_gemm_row_chunk_invariance(ctx):
     assert np.array_equal(full, parts)
 
 
+@pytest.mark.parametrize("M,N,K,cuts", [(1000, 4096, 1024, (300,)), (1000, 4096, 1024, (128, 129, 700)), (900, 84, 4096, (77, 500)),
+                                        (700, 21, 4096, (1, 699)), (640, 512, 2048, (100, 356))])
+def test_gemm_row_chunk_invariance_head_shapes(ctx, M, N, K, cuts):
+    """Per-ROI GEMMs at head sizes: the plan may depend on the row count (N tile 240/256, CTA pairs, SM fill) but nothing
+    that changes rounding may (accumulator grouping and split-K are functions of (N, K) only), so any chunking of the
+    rows gives the same bits as the full call (ImageDetect.lua:126-133 forwards ROIs in chunks)."""
+    rng = np.random.default_rng(M + N)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    full = ctx.gemm_check(A, B, b)
+    edges = [0, *cuts, M]
+    parts = np.concatenate([ctx.gemm_check(A[a:z], B, b) for a, z in zip(edges[:-1], edges[1:])])
+    assert np.array_equal(full, parts)
+
+
 @pytest.mark.parametrize("impl", [1, 0])
 @pytest.mark.parametrize("N,Cin,H,W,Cout,k,s,p", [
     (1, 64, 16, 16, 64, 3, 1, 1), (1, 64, 37, 53, 128, 3, 1, 1), (1, 128, 75, 100, 256, 3, 1, 1), (1, 512, 38, 50, 512, 3, 1, 1),
