@@ -27,6 +27,8 @@ struct ConvProblem {
 // Plan = tile decomposition + TMA descriptors for one ConvProblem on the tcgen05 path.
 struct ConvPlan {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  CUtensorMap tmY_hi, tmY_lo;      // 3x3 kernel: output maps of the TMA-store epilogue
+  int tma_store = 0;
   int BN = 0;                      // 64 / 128 / 256
   int CG = 1;                      // CTAs per MMA (tcgen05 cta_group): 2 = CTA pair sharing the B tile
   int tn = 0, th = 0, tw = 0;      // 128 output pixels per M tile = tn*th*tw

@@ -69,6 +69,7 @@ struct TcParams {
   // inside a tile writes its raw fp32 partial to sk_ws and raises sk_flags (= sk_epoch), the range that starts the tile
   // adds the partials in pair order (fixed => deterministic) and runs the real epilogue.
   int streamk; unsigned sk_epoch; float *sk_ws; unsigned *sk_flags;
+  int tma_store;                 // 3x3 kernel: the epilogue stages 64-channel slabs in shared memory and ships them with TMA tensor stores
 };
 
 // Work walk of one scheduling unit (CTA or CTA pair). Plain: tiles unit, unit + num_units, ... each with all S steps.
@@ -400,6 +401,93 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
   }
 }
 
+// ---------------------------------------------------------------- epilogue with TMA tensor stores (3x3 kernel)
+// The generic epilogue stores 16 bytes per lane to 32 different lines per instruction: ~13k cycles of LSU wavefronts for
+// one 128 x 256 tile, fully exposed on layers with one or two tiles per CTA (conv4, conv5). Here the eight epilogue warps
+// stage one 64-channel slab of the tile (128 pixels x 128 B per plane, 128B-swizzled like the operand tiles) in shared
+// memory and one thread ships it with two cp.async.bulk.tensor stores (box {64 ch, 8 px, 16 rows}; pixels outside the
+// image are clipped by the TMA unit). Plain outputs only: no residual, no fp32 output, no fused pooling.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+constexpr int STG_PLANE = BM * 128;      // 128 pixels x 64 channels x bf16
+constexpr int STG_BYTES = 2 * STG_PLANE; // hi + lo
+
+template <int BN, int CG>
+__device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CUtensorMap *tmYh, const CUtensorMap *tmYl, uint8_t *stg,
+                                                     uint32_t tmem_base, int q, int a, int nt, int ch_first, int ew, int w0,
+                                                     int h0, int n0, const EpiSk sk) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int row = q * 32 + lane;
+  constexpr int NACC = num_acc(BN);
+#pragma unroll 1
+  for (int ch = ch_first, slab = 0; ch < BN / 32; ch += 2, ++slab) {
+    uint32_t v[32];
+    const int col0 = nt * BN + ch * 32;
+    const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NACC * BN + ch * 32);
+    tc_ld32(tcol, v);
+    if (NACC >= 2) {
+      uint32_t w[32];
+      const uint32_t d2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NACC * BN + BN);
+      const uint32_t hh_col = (NACC == 3) ? d2 + (uint32_t)(CG == 2 ? ch * 64 : ch * 32) : 0u;
+      const uint32_t hl_col = (NACC == 3) ? d2 + (uint32_t)(CG == 2 ? ch * 64 + 32 : BN + ch * 32) : tcol + BN;
+      tc_ld32(hl_col, w);
+      tc_wait_ld();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+      if (NACC == 3) {
+        tc_ld32(hh_col, w);
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
+      }
+    } else {
+      tc_wait_ld();
+    }
+    if (sk.role == SK_FINISHER) {
+      for (int t = 0; t < sk.ncont; ++t) {            // fixed order: pair u+1, u+2, ...
+        const float4 *pi = sk.part_in + (long long)t * sk.part_stride4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = __ldcg(pi + (ch * 8 + j) * 128 + row);
+          v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x.x);
+          v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x.y);
+          v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x.z);
+          v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x.w);
+        }
+      }
+    }
+    uint32_t oh[16], ol[16];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float f0 = __uint_as_float(v[4 * t]), f1 = __uint_as_float(v[4 * t + 1]), f2 = __uint_as_float(v[4 * t + 2]), f3 = __uint_as_float(v[4 * t + 3]);
+      if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + t); f0 += bb.x; f1 += bb.y; f2 += bb.z; f3 += bb.w; }
+      if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
+      split_bf16x2(f0, f1, oh[2 * t], ol[2 * t]);
+      split_bf16x2(f2, f3, oh[2 * t + 1], ol[2 * t + 1]);
+    }
+    // the single staging buffer is free once the previous slab's stores have finished READING it
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    uint8_t *pr = stg + (size_t)row * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int phys = (((ch & 1) * 4 + j) ^ (row & 7)) * 16;      // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+      *reinterpret_cast<uint4 *>(pr + phys) = make_uint4(oh[4 * j], oh[4 * j + 1], oh[4 * j + 2], oh[4 * j + 3]);
+      *reinterpret_cast<uint4 *>(pr + STG_PLANE + phys) = make_uint4(ol[4 * j], ol[4 * j + 1], ol[4 * j + 2], ol[4 * j + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (ew == 0 && lane == 0) {
+      const uint32_t s_hi = smem_u32(stg);
+      tma_store_4d(tmYh, s_hi, nt * BN + slab * 64, w0, h0, n0);
+      tma_store_4d(tmYl, s_hi + (uint32_t)STG_PLANE, nt * BN + slab * 64, w0, h0, n0);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -611,14 +699,15 @@ constexpr int R3_A_STAGE = 2 * R3_A_PLANE;       // hi + lo
 __host__ __device__ constexpr int r3_b_stage(int BN, int CG) { return 2 * (BN / CG) * BK * 2; }
 __host__ __device__ constexpr int r3_sa(int BN, int CG) { return (BN / CG) >= 128 ? 2 : 3; }
 __host__ __device__ constexpr int r3_sb(int BN, int CG) {
-  // fill what is left of ~215 KB after the A ring (B tiles are small for narrow layers: a deep ring hides the TMA latency)
-  return (220160 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 12 ? 12 : (220160 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
+  // fill what is left of ~184 KB (32 KB go to the epilogue staging slab) after the A ring (B tiles are small for narrow layers: a deep ring hides the TMA latency)
+  return (188416 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 12 ? 12 : (188416 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
 }
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                   const TcParams p) {
   constexpr int SA = r3_sa(BN, CG), SB = r3_sb(BN, CG);
   constexpr int B_STAGE = r3_b_stage(BN, CG);
@@ -628,7 +717,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   static_assert(SB >= 2, "B ring too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)SA * R3_A_STAGE + (size_t)SB * B_STAGE);
+  uint8_t *stg = smem + (size_t)SA * R3_A_STAGE + (size_t)SB * B_STAGE;        // epilogue staging slab (TMA store path)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stg + STG_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * SA + 2 * SB + 4);
   const uint32_t a_base = smem_u32(smem);
   const uint32_t b_base = a_base + (uint32_t)SA * R3_A_STAGE;
@@ -845,7 +935,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const long long ppix = (p.pool_hi && row_ok && !(lane & 9)) ? ((long long)n * p.Hp + (ho >> 1)) * p.Wp + (wo >> 1) : -1;
       mbar_wait_t(tfull_bar(a), aph, wc0, trace);
       tc_fence_after();
-      { const long long te = clock64(); tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk); if (trace) wc1 += (unsigned long long)(clock64() - te); }
+      {
+        const long long te = clock64();
+        if (p.tma_store && sk.role != SK_WRITER)
+          tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2, twi * 8, thi * 16, tni, sk);
+        else
+          tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk);
+        if (trace) wc1 += (unsigned long long)(clock64() - te);
+      }
       tc_fence_before();
       if (sk.role == SK_WRITER) {                  // publish the partial: data, fence, then the flag (release)
         __threadfence();
@@ -863,6 +960,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
   }
 
+  if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging must outlive its stores
   if (trace && lane == 0) {
     // dbg[0..2] producer: wait emptyA, wait emptyB, total; [3..6] MMA: wait fullA, fullB, tempty, total; [7..9] epilogue warp 2: wait tfull, store time, total
     const unsigned long long tot = (unsigned long long)(clock64() - t_start);
@@ -1198,7 +1296,7 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
 
 template <int BN, int CG>
 int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
-  const int smem = r3_sa(BN, CG) * R3_A_STAGE + r3_sb(BN, CG) * r3_b_stage(BN, CG) + 1024 + 512;
+  const int smem = r3_sa(BN, CG) * R3_A_STAGE + r3_sb(BN, CG) * r3_b_stage(BN, CG) + STG_BYTES + 1024 + 512;
   constexpr int slot = 8 + (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1);
   if (!ctx->tc_attr_set[slot]) {
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1222,7 +1320,7 @@ int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -1380,6 +1478,19 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
   } else {
     pl.splitk = 1; pl.kb_per_split = 9 * (int)(p.x.C / BK);
   }
+  pl.tma_store = 0;
+  if (pl.mode == 1 && p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0) {
+    // output tensor maps of the TMA-store epilogue: box = one 64-channel slab of a 16 x 8 patch
+    cuuint64_t yd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.y.W, (cuuint64_t)p.y.H, (cuuint64_t)p.y.N};
+    cuuint64_t ys[3] = {(cuuint64_t)p.y.ld * 2, (cuuint64_t)p.y.W * p.y.ld * 2, (cuuint64_t)p.y.H * p.y.W * p.y.ld * 2};
+    cuuint32_t yb[4] = {64, 8, 16, 1}, ye[4] = {1, 1, 1, 1};
+    MPN_TRY(encode_map(ctx, &pl.tmY_hi, p.y.hi, 4, yd, ys, yb, ye));
+    MPN_TRY(encode_map(ctx, &pl.tmY_lo, p.y.lo, 4, yd, ys, yb, ye));
+    const char *envs = getenv("MPN_TC_TMA_STORE");
+    pl.tma_store = (envs && envs[0] == '0') ? 0 : 1;
+  } else {
+    pl.tmY_hi = pl.tmA_hi; pl.tmY_lo = pl.tmA_lo;      // never used; keep the kernel arguments defined
+  }
   MPN_TRY(encode_map(ctx, &pl.tmA_hi, p.x.hi, 4, dims, strides, box, estr));
   MPN_TRY(encode_map(ctx, &pl.tmA_lo, p.x.lo, 4, dims, strides, box, estr));
   const long long Ktot = (long long)p.kh * p.kw * p.x.C;
@@ -1410,6 +1521,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.dbg = (unsigned long long *)p.dbg;
   tp.pool_hi = tp.pool_lo = nullptr; tp.pool_ld = 0; tp.Hp = tp.Wp = 0;
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
+  tp.tma_store = (pl.tma_store && pl.mode == 1 && !p.pool.hi && !p.res.hi && !p.y.f32 && p.y.hi) ? 1 : 0;
   if (pl.streamk && pl.mode == 1) {
     if (!ctx->sk_ws) {
       MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_ws, (size_t)ctx->sm_count * 128 * 256 * sizeof(float)));
