@@ -414,12 +414,19 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *tm, uint32_t src
 constexpr int STG_PLANE = BM * 128;      // 128 pixels x 64 channels x bf16
 constexpr int STG_BYTES = 2 * STG_PLANE; // hi + lo
 
+constexpr int STG_POOL_PLANE = 32 * 128; // 32 pooled pixels x 64 channels x bf16
+constexpr int STG_POOL_BYTES = 2 * STG_POOL_PLANE;
+
+// full != 0: store the tile itself; pooled != 0: store its 2x2/2 max pool (8 x 4 pooled pixels per 16 x 8 patch; window =
+// lanes {l, l^1, l^8} of a warp, rows outside the image count as -inf: ceil-mode borders). Both may be set.
 template <int BN, int CG>
-__device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CUtensorMap *tmYh, const CUtensorMap *tmYl, uint8_t *stg,
+__device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CUtensorMap *tmYh, const CUtensorMap *tmYl,
+                                                     const CUtensorMap *tmPh, const CUtensorMap *tmPl, uint8_t *stg, uint8_t *stg_pool,
                                                      uint32_t tmem_base, int q, int a, int nt, int ch_first, int ew, int w0,
-                                                     int h0, int n0, const EpiSk sk) {
+                                                     int h0, int n0, bool row_ok, const EpiSk sk) {
   const int lane = (int)(threadIdx.x & 31);
   const int row = q * 32 + lane;
+  const bool full = (p.out_hi != nullptr), pooled = (p.pool_hi != nullptr);
   constexpr int NACC = num_acc(BN);
 #pragma unroll 1
   for (int ch = ch_first, slab = 0; ch < BN / 32; ch += 2, ++slab) {
@@ -458,31 +465,64 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
         }
       }
     }
-    uint32_t oh[16], ol[16];
+    // bias + ReLU in place (v now holds the final fp32 values)
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       float f0 = __uint_as_float(v[4 * t]), f1 = __uint_as_float(v[4 * t + 1]), f2 = __uint_as_float(v[4 * t + 2]), f3 = __uint_as_float(v[4 * t + 3]);
       if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + t); f0 += bb.x; f1 += bb.y; f2 += bb.z; f3 += bb.w; }
       if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
-      split_bf16x2(f0, f1, oh[2 * t], ol[2 * t]);
-      split_bf16x2(f2, f3, oh[2 * t + 1], ol[2 * t + 1]);
+      v[4 * t] = __float_as_uint(f0); v[4 * t + 1] = __float_as_uint(f1); v[4 * t + 2] = __float_as_uint(f2); v[4 * t + 3] = __float_as_uint(f3);
     }
-    // the single staging buffer is free once the previous slab's stores have finished READING it
+    // the staging buffers are free once the previous slab's stores have finished READING them
     if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    uint8_t *pr = stg + (size_t)row * 128;
+    if (full) {
+      uint8_t *pr = stg + (size_t)row * 128;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int phys = (((ch & 1) * 4 + j) ^ (row & 7)) * 16;      // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-      *reinterpret_cast<uint4 *>(pr + phys) = make_uint4(oh[4 * j], oh[4 * j + 1], oh[4 * j + 2], oh[4 * j + 3]);
-      *reinterpret_cast<uint4 *>(pr + STG_PLANE + phys) = make_uint4(ol[4 * j], ol[4 * j + 1], ol[4 * j + 2], ol[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) {
+        uint32_t oh[4], ol[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) split_bf16x2(__uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t]);
+        const int phys = (((ch & 1) * 4 + j) ^ (row & 7)) * 16;      // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+        *reinterpret_cast<uint4 *>(pr + phys) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+        *reinterpret_cast<uint4 *>(pr + STG_PLANE + phys) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      }
+    }
+    if (pooled) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        float x = row_ok ? __uint_as_float(v[e]) : -INFINITY;
+        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+        x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 8));
+        v[e] = __float_as_uint(x);
+      }
+      if (!(lane & 9)) {                        // top-left lane of each window: pooled pixel (row>>4, (row&7)>>1) of the 8 x 4 pooled patch
+        const int prow = (row >> 4) * 4 + ((row & 7) >> 1);
+        uint8_t *pp = stg_pool + (size_t)prow * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t oh[4], ol[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) split_bf16x2(__uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t]);
+          const int phys = (((ch & 1) * 4 + j) ^ (prow & 7)) * 16;
+          *reinterpret_cast<uint4 *>(pp + phys) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4 *>(pp + STG_POOL_PLANE + phys) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        }
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (ew == 0 && lane == 0) {
-      const uint32_t s_hi = smem_u32(stg);
-      tma_store_4d(tmYh, s_hi, nt * BN + slab * 64, w0, h0, n0);
-      tma_store_4d(tmYl, s_hi + (uint32_t)STG_PLANE, nt * BN + slab * 64, w0, h0, n0);
+      if (full) {
+        const uint32_t s_hi = smem_u32(stg);
+        tma_store_4d(tmYh, s_hi, nt * BN + slab * 64, w0, h0, n0);
+        tma_store_4d(tmYl, s_hi + (uint32_t)STG_PLANE, nt * BN + slab * 64, w0, h0, n0);
+      }
+      if (pooled) {
+        const uint32_t s_p = smem_u32(stg_pool);
+        tma_store_4d(tmPh, s_p, nt * BN + slab * 64, w0 >> 1, h0 >> 1, n0);
+        tma_store_4d(tmPl, s_p + (uint32_t)STG_POOL_PLANE, nt * BN + slab * 64, w0 >> 1, h0 >> 1, n0);
+      }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
@@ -700,7 +740,7 @@ __host__ __device__ constexpr int r3_b_stage(int BN, int CG) { return 2 * (BN / 
 __host__ __device__ constexpr int r3_sa(int BN, int CG) { return (BN / CG) >= 128 ? 2 : 3; }
 __host__ __device__ constexpr int r3_sb(int BN, int CG) {
   // fill what is left of ~184 KB (32 KB go to the epilogue staging slab) after the A ring (B tiles are small for narrow layers: a deep ring hides the TMA latency)
-  return (188416 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 12 ? 12 : (188416 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
+  return (184320 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG) > 12 ? 12 : (184320 - r3_sa(BN, CG) * R3_A_STAGE) / r3_b_stage(BN, CG);
 }
 
 template <int BN, int CG>
@@ -708,6 +748,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                  const __grid_constant__ CUtensorMap tmP_hi, const __grid_constant__ CUtensorMap tmP_lo,
                   const TcParams p) {
   constexpr int SA = r3_sa(BN, CG), SB = r3_sb(BN, CG);
   constexpr int B_STAGE = r3_b_stage(BN, CG);
@@ -718,7 +759,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *stg = smem + (size_t)SA * R3_A_STAGE + (size_t)SB * B_STAGE;        // epilogue staging slab (TMA store path)
-  uint64_t *bars = reinterpret_cast<uint64_t *>(stg + STG_BYTES);
+  uint8_t *stg_pool = stg + STG_BYTES;                                         // pooled slab (fused 2x2 max pool)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stg_pool + STG_POOL_BYTES);
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * SA + 2 * SB + 4);
   const uint32_t a_base = smem_u32(smem);
   const uint32_t b_base = a_base + (uint32_t)SA * R3_A_STAGE;
@@ -938,7 +980,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       {
         const long long te = clock64();
         if (p.tma_store && sk.role != SK_WRITER)
-          tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2, twi * 8, thi * 16, tni, sk);
+          tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, &tmP_hi, &tmP_lo, stg, stg_pool, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
+                                       twi * 8, thi * 16, tni, row_ok, sk);
         else
           tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk);
         if (trace) wc1 += (unsigned long long)(clock64() - te);
@@ -1295,8 +1338,8 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
 }
 
 template <int BN, int CG>
-int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
-  const int smem = r3_sa(BN, CG) * R3_A_STAGE + r3_sb(BN, CG) * r3_b_stage(BN, CG) + STG_BYTES + 1024 + 512;
+int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp, const CUtensorMap &tmP_hi, const CUtensorMap &tmP_lo) {
+  const int smem = r3_sa(BN, CG) * R3_A_STAGE + r3_sb(BN, CG) * r3_b_stage(BN, CG) + STG_BYTES + STG_POOL_BYTES + 1024 + 512;
   constexpr int slot = 8 + (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1);
   if (!ctx->tc_attr_set[slot]) {
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv3x3_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1320,7 +1363,7 @@ int launch_r3(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tp));
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tmP_hi, tmP_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -1521,7 +1564,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.dbg = (unsigned long long *)p.dbg;
   tp.pool_hi = tp.pool_lo = nullptr; tp.pool_ld = 0; tp.Hp = tp.Wp = 0;
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
-  tp.tma_store = (pl.tma_store && pl.mode == 1 && !p.pool.hi && !p.res.hi && !p.y.f32 && p.y.hi) ? 1 : 0;
+  tp.tma_store = 0;      // decided below, once the pooled output (if any) is known
   if (pl.streamk && pl.mode == 1) {
     if (!ctx->sk_ws) {
       MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_ws, (size_t)ctx->sm_count * 128 * 256 * sizeof(float)));
@@ -1560,8 +1603,18 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     return MPN_OK;
   }
   if (pl.mode == 1) {
-    if (pl.CG == 2) return pl.BN == 256 ? launch_r3<256, 2>(ctx, pl, tp) : (pl.BN == 128 ? launch_r3<128, 2>(ctx, pl, tp) : launch_r3<64, 2>(ctx, pl, tp));
-    return pl.BN == 128 ? launch_r3<128, 1>(ctx, pl, tp) : launch_r3<64, 1>(ctx, pl, tp);
+    // TMA-store epilogue: plain split outputs and/or the fused pooled output, 64-channel slabs
+    CUtensorMap tmP_hi = pl.tmY_hi, tmP_lo = pl.tmY_lo;
+    tp.tma_store = (pl.tma_store && !p.res.hi && !tp.out_f32 && (tp.out_hi || tp.pool_hi) && (!tp.pool_hi || p.pool.ld % 8 == 0)) ? 1 : 0;
+    if (tp.tma_store && tp.pool_hi) {
+      cuuint64_t pd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.pool.W, (cuuint64_t)p.pool.H, (cuuint64_t)p.pool.N};
+      cuuint64_t ps[3] = {(cuuint64_t)p.pool.ld * 2, (cuuint64_t)p.pool.W * p.pool.ld * 2, (cuuint64_t)p.pool.H * p.pool.W * p.pool.ld * 2};
+      cuuint32_t pb[4] = {64, 4, 8, 1}, pe[4] = {1, 1, 1, 1};
+      MPN_TRY(encode_map(ctx, &tmP_hi, p.pool.hi, 4, pd, ps, pb, pe));
+      MPN_TRY(encode_map(ctx, &tmP_lo, p.pool.lo, 4, pd, ps, pb, pe));
+    }
+    if (pl.CG == 2) return pl.BN == 256 ? launch_r3<256, 2>(ctx, pl, tp, tmP_hi, tmP_lo) : (pl.BN == 128 ? launch_r3<128, 2>(ctx, pl, tp, tmP_hi, tmP_lo) : launch_r3<64, 2>(ctx, pl, tp, tmP_hi, tmP_lo));
+    return pl.BN == 128 ? launch_r3<128, 1>(ctx, pl, tp, tmP_hi, tmP_lo) : launch_r3<64, 1>(ctx, pl, tp, tmP_hi, tmP_lo);
   }
   if (pl.CG == 2) {
     switch (pl.BN) {
