@@ -46,6 +46,18 @@ H, W, R, C = 600, 800, 1000, 21
 WORKLOAD = WORKLOADS["vgg16_frcnn"]["name"]
 
 
+def traffic_from_profiles(config):
+    """DRAM bytes (read + write) per launch of the dominant launch of the dominant kernel family, from the committed
+    `ncu --set full` capture (profiles/traffic.json); None when no capture of this config is committed."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            t = json.load(f).get(config)
+        return None if t is None else {"dram_bytes_per_launch": t["dram_bytes_per_launch"], "launch": t["dominant_launch"],
+                                       "algorithmic_bytes_per_launch": t["algorithmic_bytes_per_launch"], "source": t["source"]}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def roi_algorithmic_bytes(spec, shapes, R):
     """each pooled feature map once + R*5*4 + sum over towers of the pooled output (fp32-equivalent bytes)."""
     used = {}
@@ -388,7 +400,8 @@ def main():
     n_tc = prof["conv_gemm_tc"][1] // args.steps
     roofline = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (tcgen05 bf16x3 implicit-GEMM, %d launches/step)" % n_tc,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "issued_frac": 3.0 * achieved / peak_tf if peak_tf else None, "peak_source": peak_src, "traffic": None,
+                "issued_frac": 3.0 * achieved / peak_tf if peak_tf else None, "peak_source": peak_src,
+                "traffic": traffic_from_profiles(args.config),
                 "algorithmic_tflop_per_step": tflop_step, "kernel_ms_per_step": tc_ms_step,
                 "by_category_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     # ROI pooling (HBM-bound secondary kernel): algorithmic bytes = feature map once + rois + pooled output
