@@ -423,7 +423,7 @@ template <int BN, int CG>
 __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CUtensorMap *tmYh, const CUtensorMap *tmYl,
                                                      const CUtensorMap *tmPh, const CUtensorMap *tmPl, uint8_t *stg, uint8_t *stg_pool,
                                                      uint32_t tmem_base, int q, int a, int nt, int ch_first, int ew, int w0,
-                                                     int h0, int n0, bool row_ok, const EpiSk sk) {
+                                                     int h0, int n0, bool row_ok, long long pix, const EpiSk sk) {
   const int lane = (int)(threadIdx.x & 31);
   const int row = q * 32 + lane;
   const bool full = (p.out_hi != nullptr), pooled = (p.pool_hi != nullptr);
@@ -465,13 +465,28 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
         }
       }
     }
-    // bias + ReLU in place (v now holds the final fp32 values)
+    // bias (+ residual) + ReLU in place (v now holds the final fp32 values); 8 channels per step = one 16-byte residual load per plane
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      float f0 = __uint_as_float(v[4 * t]), f1 = __uint_as_float(v[4 * t + 1]), f2 = __uint_as_float(v[4 * t + 2]), f3 = __uint_as_float(v[4 * t + 3]);
-      if (p.bias) { const float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + t); f0 += bb.x; f1 += bb.y; f2 += bb.z; f3 += bb.w; }
-      if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); f2 = fmaxf(f2, 0.f); f3 = fmaxf(f3, 0.f); }
-      v[4 * t] = __float_as_uint(f0); v[4 * t + 1] = __float_as_uint(f1); v[4 * t + 2] = __float_as_uint(f2); v[4 * t + 3] = __float_as_uint(f3);
+    for (int t = 0; t < 4; ++t) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * t + e]);
+      if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + 2 * t), b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + 2 * t + 1);
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      }
+      if (p.res_hi && row_ok) {                 // same op order as the register-store path: (acc + bias) + (res_hi + res_lo)
+        const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + col0 + 8 * t);
+        const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + col0 + 8 * t);
+        const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 x = bf16x2_to_float2(hh[u]), y = bf16x2_to_float2(ll[u]);
+          f[2 * u] += x.x + y.x; f[2 * u + 1] += x.y + y.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[8 * t + e] = __float_as_uint(p.relu ? fmaxf(f[e], 0.f) : f[e]);
     }
     // the staging buffers are free once the previous slab's stores have finished READING them
     if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -533,6 +548,7 @@ template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                     const TcParams p) {
   constexpr int S = num_stages(BN, CG);
   constexpr int STAGE = stage_bytes(BN, CG);
@@ -542,7 +558,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for SWIZZLE_128B tiles
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)S * STAGE);
+  uint8_t *stg = smem + (size_t)S * STAGE;                     // epilogue staging slab (TMA-store path)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(stg + STG_BYTES);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
   const uint32_t smem_base = smem_u32(smem);
@@ -705,7 +722,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const long long pix = ((long long)n * p.Ho + ho) * p.Wo + wo;
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
-      tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
+      if (p.tma_store)       // plain split output: 64-channel slabs through shared memory + TMA tensor stores (box = the tile's patch)
+        tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, &tmY_hi, &tmY_lo, stg, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
+                                     twi * p.tw, thi * p.th, tni * p.tn, row_ok, pix, EpiSk());
+      else
+        tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                             // 4*CG arrivals (one per epilogue warp of the pair) free the buffer
@@ -715,6 +736,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
   }
 
+  if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging must outlive its stores
   // ---- teardown: everyone (both CTAs) done with TMEM / peer smem / peer barriers before anything is freed
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -981,7 +1003,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const long long te = clock64();
         if (p.tma_store && sk.role != SK_WRITER)
           tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, &tmP_hi, &tmP_lo, stg, stg_pool, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
-                                       twi * 8, thi * 16, tni, row_ok, sk);
+                                       twi * 8, thi * 16, tni, row_ok, pix, sk);
         else
           tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, p.out_f32, (warp - 2) >> 2, ppix, sk);
         if (trace) wc1 += (unsigned long long)(clock64() - te);
@@ -1308,7 +1330,7 @@ inline bool tc_use_pdl() {
 
 template <int BN, int CG>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
-  const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + 1024 /*align*/ + 256 /*barriers*/;
+  const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   constexpr int slot = (BN == 240 ? 6 : (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1));
   if (!ctx->tc_attr_set[slot]) {     // per ctx (= per device): the attribute is per device function
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1332,7 +1354,7 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, tp));
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -1522,11 +1544,14 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     pl.splitk = 1; pl.kb_per_split = 9 * (int)(p.x.C / BK);
   }
   pl.tma_store = 0;
-  if (pl.mode == 1 && p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0) {
-    // output tensor maps of the TMA-store epilogue: box = one 64-channel slab of a 16 x 8 patch
-    cuuint64_t yd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.y.W, (cuuint64_t)p.y.H, (cuuint64_t)p.y.N};
-    cuuint64_t ys[3] = {(cuuint64_t)p.y.ld * 2, (cuuint64_t)p.y.W * p.y.ld * 2, (cuuint64_t)p.y.H * p.y.W * p.y.ld * 2};
-    cuuint32_t yb[4] = {64, 8, 16, 1}, ye[4] = {1, 1, 1, 1};
+  if (p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0 && pl.BN != 240) {
+    // output tensor maps of the TMA-store epilogue: box = one 64-channel slab of the tile's pixel patch
+    // (3x3 kernel: 16 x 8; generic: tn x th x tw; flat: 128 consecutive rows)
+    const long long Py = (long long)p.y.N * p.y.H * p.y.W;
+    cuuint64_t yd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)(pl.flat ? Py : p.y.W), (cuuint64_t)(pl.flat ? 1 : p.y.H), (cuuint64_t)(pl.flat ? 1 : p.y.N)};
+    cuuint64_t ys[3] = {(cuuint64_t)p.y.ld * 2, (cuuint64_t)(pl.flat ? Py : p.y.W) * p.y.ld * 2,
+                        (cuuint64_t)(pl.flat ? Py : p.y.H * p.y.W) * p.y.ld * 2};
+    cuuint32_t yb[4] = {64, (cuuint32_t)pl.tw, (cuuint32_t)pl.th, (cuuint32_t)pl.tn}, ye[4] = {1, 1, 1, 1};
     MPN_TRY(encode_map(ctx, &pl.tmY_hi, p.y.hi, 4, yd, ys, yb, ye));
     MPN_TRY(encode_map(ctx, &pl.tmY_lo, p.y.lo, 4, yd, ys, yb, ye));
     const char *envs = getenv("MPN_TC_TMA_STORE");
@@ -1582,6 +1607,8 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     if (p.pool_only) { tp.out_hi = tp.out_lo = nullptr; tp.out_f32 = nullptr; }
   }
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
+  if (pl.mode == 0 && pl.splitk == 1)
+    tp.tma_store = (pl.tma_store && !tp.out_f32 && tp.out_hi && !tp.pool_hi) ? 1 : 0;
   if (pl.splitk > 1) {
     // partial accumulators go to a dense fp32 workspace [split][pixel][Cout]; bias/residual/ReLU/output split move to the reduce
     const long long pixels = (long long)p.y.N * p.y.H * p.y.W;
@@ -1605,7 +1632,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   if (pl.mode == 1) {
     // TMA-store epilogue: plain split outputs and/or the fused pooled output, 64-channel slabs
     CUtensorMap tmP_hi = pl.tmY_hi, tmP_lo = pl.tmY_lo;
-    tp.tma_store = (pl.tma_store && !p.res.hi && !tp.out_f32 && (tp.out_hi || tp.pool_hi) && (!tp.pool_hi || p.pool.ld % 8 == 0)) ? 1 : 0;
+    tp.tma_store = (pl.tma_store && !tp.out_f32 && (tp.out_hi || tp.pool_hi) && (!tp.pool_hi || p.pool.ld % 8 == 0)) ? 1 : 0;
     if (tp.tma_store && tp.pool_hi) {
       cuuint64_t pd[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.pool.W, (cuuint64_t)p.pool.H, (cuuint64_t)p.pool.N};
       cuuint64_t ps[3] = {(cuuint64_t)p.pool.ld * 2, (cuuint64_t)p.pool.W * p.pool.ld * 2, (cuuint64_t)p.pool.H * p.pool.W * p.pool.ld * 2};
