@@ -263,7 +263,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 template <int BN, int CG>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tmem_base, int q, int a, int nt, bool row_ok,
                                                  long long pix, float *out_f32, int ch_first, long long ppix = -1,
-                                                 const EpiSk sk = EpiSk()) {
+                                                 const EpiSk sk = EpiSk(), int ch_lo = 0) {
   // fused 2x2/2 max pool (3x3 kernel: lane = (h & 3) * 8 + w of a 16 x 8 patch, so a window is lanes {l, l^1, l^8});
   // ppix = pooled pixel this lane writes (its window's top-left lane), -1 otherwise. pool is warp-uniform.
   const bool pool = (p.pool_hi != nullptr);
@@ -271,7 +271,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
 #pragma unroll 1
   // (BN = 240 ends in half a chunk: columns past the tile belong to the next accumulator / the next tile and are skipped)
   const int tile_end = min(p.Cout, nt * BN + BN);
-  for (int ch = ch_first; ch < (BN + 31) / 32; ch += 2) {
+  for (int ch = ch_lo + ch_first; ch < (BN + 31) / 32; ch += 2) {
     uint32_t v[32];
     const int col0 = nt * BN + ch * 32;
     // bias for this chunk: fetched BEFORE the TMEM load so its latency hides behind tcgen05.ld / wait
@@ -429,7 +429,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
   const bool full = (p.out_hi != nullptr), pooled = (p.pool_hi != nullptr);
   constexpr int NACC = num_acc(BN);
 #pragma unroll 1
-  for (int ch = ch_first, slab = 0; ch < BN / 32; ch += 2, ++slab) {
+  for (int ch = ch_first, slab = 0; ch < (BN / 64) * 2; ch += 2, ++slab) {       // whole 64-channel slabs only (BN = 240: three)
     uint32_t v[32];
     const int col0 = nt * BN + ch * 32;
     const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NACC * BN + ch * 32);
@@ -471,11 +471,12 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * t + e]);
-      if (p.bias) {
+      const bool col_ok = (col0 + 8 * t + 8 <= p.Cout);      // columns past Cout (last N tile of BN = 240) are clipped by the TMA store
+      if (p.bias && col_ok) {
         const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + 2 * t), b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + col0) + 2 * t + 1);
         f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
       }
-      if (p.res_hi && row_ok) {                 // same op order as the register-store path: (acc + bias) + (res_hi + res_lo)
+      if (p.res_hi && row_ok && col_ok) {       // same op order as the register-store path: (acc + bias) + (res_hi + res_lo)
         const uint4 rh = *reinterpret_cast<const uint4 *>(p.res_hi + pix * p.res_ld + col0 + 8 * t);
         const uint4 rl = *reinterpret_cast<const uint4 *>(p.res_lo + pix * p.res_ld + col0 + 8 * t);
         const uint32_t hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
@@ -725,6 +726,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       if (p.tma_store)       // plain split output: 64-channel slabs through shared memory + TMA tensor stores (box = the tile's patch)
         tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, &tmY_hi, &tmY_lo, stg, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
                                      twi * p.tw, thi * p.th, tni * p.tn, row_ok, pix, EpiSk());
+      if (p.tma_store && (BN % 64) != 0)       // BN = 240: the last 48 channels are not a whole slab: register-store path
+        tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2, -1, EpiSk(), (BN / 64) * 2);
+      else if (p.tma_store) {}
       else
         tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
       tc_fence_before();
@@ -1544,7 +1548,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     pl.splitk = 1; pl.kb_per_split = 9 * (int)(p.x.C / BK);
   }
   pl.tma_store = 0;
-  if (p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0 && pl.BN != 240) {
+  if (p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0) {
     // output tensor maps of the TMA-store epilogue: box = one 64-channel slab of the tile's pixel patch
     // (3x3 kernel: 16 x 8; generic: tn x th x tw; flat: 128 consecutive rows)
     const long long Py = (long long)p.y.N * p.y.H * p.y.W;
