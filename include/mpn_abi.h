@@ -231,6 +231,11 @@ int mpn_gemm_bench(mpn_ctx *ctx, int64_t M, int64_t N, int64_t K, int32_t iters,
 int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride,
                    int32_t pad, int32_t iters, double *ms_per_launch, int32_t *bn, int32_t *cta_group, int32_t *mode,
                    uint64_t *dbg16);
+/* host-only view of the tcgen05 kernels' work walk (no GPU): the (tile, s0, s1) pieces scheduling unit `unit` of
+ * `num_units` visits, in order, for `total_tiles` tiles of `steps_per_tile` K steps; streamk = 0: whole tiles round-robin,
+ * 1: contiguous (tile, step) ranges in rotated order (continuation piece, head piece, whole tiles). pieces: max_pieces x 3. */
+int mpn_debug_segwalk(int32_t streamk, int32_t unit, int32_t num_units, int32_t total_tiles, int32_t steps_per_tile,
+                      int32_t *pieces, int32_t max_pieces, int32_t *n_pieces);
 /* standalone conv check entry (tests): x N x Cin x H x W, w Cout x Cin x kh x kw (Torch layouts) */
 int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t H, int64_t W,
                    const float *w, const float *bias, int64_t Cout, int32_t kh, int32_t kw,

@@ -79,7 +79,7 @@ struct TcParams {
 // MMAs of what follows instead of sitting at the end of the kernel), (3) the whole tiles in between.
 struct SegWalk {
   long long w, wend, cE, hS, w0, w1; int S, tile_step, phase; bool sk;
-  __device__ SegWalk(bool sk_, int unit, int num_units, int total_tiles, int S_) : S(S_), tile_step(num_units), phase(0), sk(sk_) {
+  __host__ __device__ SegWalk(bool sk_, int unit, int num_units, int total_tiles, int S_) : S(S_), tile_step(num_units), phase(0), sk(sk_) {
     if (sk) {
       const long long W = (long long)total_tiles * S;
       w0 = W * unit / num_units; w1 = W * (unit + 1) / num_units;
@@ -90,11 +90,11 @@ struct SegWalk {
       w = cE; wend = hS;
     } else { w = unit; wend = total_tiles; }
   }
-  __device__ bool emit(long long a, long long b, int &tile, int &s0, int &s1) {
+  __host__ __device__ bool emit(long long a, long long b, int &tile, int &s0, int &s1) {
     tile = (int)(a / S); s0 = (int)(a - (long long)tile * S); s1 = s0 + (int)(b - a);
     return true;
   }
-  __device__ bool next(int &tile, int &s0, int &s1) {
+  __host__ __device__ bool next(int &tile, int &s0, int &s1) {
     if (!sk) {
       if (w >= wend) return false;
       tile = (int)w; s0 = 0; s1 = S; w += tile_step;
@@ -1595,6 +1595,11 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
   tp.tma_store = 0;      // decided below, once the pooled output (if any) is known
   if (pl.streamk && pl.mode == 1) {
+    {   // every pair must own >= 4 steps: an empty range would leave a finisher waiting for a partial nobody writes
+      const long long tiles_m_ = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
+      const long long units_ = ((tiles_m_ + pl.CG - 1) / pl.CG) * pl.tiles_n;
+      MPN_CHECK_ARG(ctx, units_ * 3 * tp.cblocks >= 4ll * (ctx->sm_count / pl.CG), "conv_tc: stream-K needs at least 4 steps per CTA pair");
+    }
     if (!ctx->sk_ws) {
       MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_ws, (size_t)ctx->sm_count * 128 * 256 * sizeof(float)));
       MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_flags, (size_t)ctx->sm_count * EPI_WARPS * sizeof(unsigned)));
@@ -1660,4 +1665,19 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     case 128: return launch_bn<128, 1>(ctx, pl, tp);
     default: return launch_bn<64, 1>(ctx, pl, tp);
   }
+}
+
+// Host-side view of the device work walk (diagnostics / CPU tests of the stream-K partition; no GPU involved):
+// writes the (tile, s0, s1) pieces of `unit` in the order the kernel visits them.
+extern "C" int mpn_debug_segwalk(int32_t streamk, int32_t unit, int32_t num_units, int32_t total_tiles, int32_t steps_per_tile,
+                                 int32_t *pieces, int32_t max_pieces, int32_t *n_pieces) {
+  if (!pieces || !n_pieces || num_units <= 0 || unit < 0 || unit >= num_units || total_tiles < 0 || steps_per_tile <= 0) return MPN_ERR_ARG;
+  SegWalk walk(streamk != 0, unit, num_units, total_tiles, steps_per_tile);
+  int tile, s0, s1, n = 0;
+  while (walk.next(tile, s0, s1)) {
+    if (n >= max_pieces) return MPN_ERR_ARG;
+    pieces[3 * n] = tile; pieces[3 * n + 1] = s0; pieces[3 * n + 2] = s1; ++n;
+  }
+  *n_pieces = n;
+  return MPN_OK;
 }

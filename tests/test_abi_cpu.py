@@ -151,3 +151,56 @@ def test_model_desc_builds_without_gpu():
     assert d.n_trunk_layers == 17 and d.n_towers == 1 and d.num_classes == 21 and d.bbox_head.cout == 84
     d, keep = mpn.Model.build_desc(models.vgg16_multipathnet(81, width_div=4, fc_dim=256))
     assert d.n_towers == 5 and d.n_tower_layers == 20 and d.towers[4].region == 1 and d.towers[4].n_levels == 3
+
+
+def _segwalk(lib, sk, unit, units, tiles, S):
+    buf = (ctypes.c_int32 * (3 * 4096))()
+    n = ctypes.c_int32(0)
+    assert lib.mpn_debug_segwalk(int(sk), unit, units, tiles, S, buf, 4096, ctypes.byref(n)) == 0
+    return [(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]) for i in range(n.value)]
+
+
+@pytest.mark.parametrize("tiles,S,units", [(22, 24, 74), (44, 24, 74), (125, 12, 74), (250, 6, 74), (66, 24, 74), (13, 24, 74),
+                                           (74, 9, 74), (75, 9, 74), (3, 100, 74), (500, 3, 148), (7, 5, 2), (148, 6, 148)])
+def test_streamk_partition_is_exact_and_deadlock_free(tiles, S, units):
+    """The stream-K work walk of the tcgen05 kernels (host view of the same struct the kernels run, no GPU):
+    every (tile, step) is owned by exactly one piece; a unit visits at most one continuation piece (a tile begun by the
+    previous unit: it only WRITES a partial, first, never waits), then at most one head piece (the tile's finisher, which
+    waits only for continuation pieces = first pieces of later units), then whole tiles; the finisher's tile is completed
+    by the immediately following units. (The planner only picks stream-K with >= 4 steps per unit, and the launcher
+    refuses less: with fewer steps than units some ranges would be empty and a finisher would wait for nobody.)"""
+    assert tiles * S >= 4 * units
+    lib = mpn.load_library()
+    owner = {}
+    first_piece = {}
+    for u in range(units):
+        pieces = _segwalk(lib, 1, u, units, tiles, S)
+        kinds = []
+        for (t, s0, s1) in pieces:
+            assert 0 <= t < tiles and 0 <= s0 < s1 <= S
+            for st in range(s0, s1):
+                assert (t, st) not in owner, "step covered twice"
+                owner[(t, st)] = u
+            kinds.append("writer" if s0 > 0 else ("finisher" if s1 < S else "full"))
+        # order: [writer] [finisher] full*
+        stripped = kinds[:]
+        if stripped and stripped[0] == "writer":
+            stripped.pop(0)
+        if stripped and stripped[0] == "finisher":
+            stripped.pop(0)
+        assert all(k == "full" for k in stripped), kinds
+        first_piece[u] = pieces[0] if pieces else None
+    assert len(owner) == tiles * S, "steps missing"
+    # every finisher's tile is completed by the FIRST pieces of the following units (what the kernel waits for)
+    for u in range(units):
+        for (t, s0, s1) in _segwalk(lib, 1, u, units, tiles, S):
+            if s0 == 0 and s1 < S:
+                nxt, v = s1, u + 1
+                while nxt < S:
+                    assert v < units and first_piece[v] is not None
+                    tt, a, b = first_piece[v]
+                    assert (tt, a) == (t, nxt), "continuation is not the next unit's first piece"
+                    nxt, v = b, v + 1
+    # plain schedule: whole tiles round-robin
+    seen = sorted(p for u in range(units) for p in _segwalk(lib, 0, u, units, tiles, S))
+    assert seen == [(t, 0, S) for t in range(tiles)]
