@@ -47,6 +47,11 @@ const char *mpn_version(void);
  * fused ROI pooling, NMS, elementwise glue, max/avg pooling}; launches_by_cat likewise (may be NULL). */
 int mpn_ctx_profile_begin(mpn_ctx *ctx);
 int mpn_ctx_profile_end(mpn_ctx *ctx, double *ms_by_cat, int64_t *launches_by_cat);
+/* in-kernel timeline of the tcgen05 launches (diagnostics, tools/timeline.py): between begin and end every tensor-core
+ * launch i records %globaltimer stamps, min over CTAs in stamps_min[4i..]: {kernel entry, dependency wait passed, first
+ * MMA issued, -}, max over CTAs in stamps_max[4i..]: {last MMA issued, last epilogue finished, kernel exit, -} (ns). */
+int mpn_ctx_timeline_begin(mpn_ctx *ctx, int32_t max_launches);
+int mpn_ctx_timeline_end(mpn_ctx *ctx, uint64_t *stamps_min, uint64_t *stamps_max, int32_t *n_launches);
 
 /* ---- NMS: replaces utils.nms -> nms.c:NMS (utils.lua:29-33, nms.c:59-108) --
  * scored_boxes: N x 5 [x1,y1,x2,y2,score]. Writes the kept ROW INDICES

@@ -69,6 +69,8 @@ SIGNATURES = {
     "mpn_version": (C.c_char_p, []),
     "mpn_ctx_profile_begin": (C.c_int, [_vp]),
     "mpn_ctx_profile_end": (C.c_int, [_vp, C.POINTER(C.c_double), _i64p]),
+    "mpn_ctx_timeline_begin": (C.c_int, [_vp, C.c_int32]),
+    "mpn_ctx_timeline_end": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _i32p]),
     "mpn_nms": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp, _i64p]),
     "mpn_nms_batched": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _i64p]),
     "mpn_nms_batched_dev": (C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_float, _vp, _vp]),

@@ -89,6 +89,8 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->scratch3) cudaFree(ctx->scratch3);
   if (ctx->sk_ws) cudaFree(ctx->sk_ws);
   if (ctx->sk_flags) cudaFree(ctx->sk_flags);
+  if (ctx->tl_min) cudaFree(ctx->tl_min);
+  if (ctx->tl_max) cudaFree(ctx->tl_max);
   for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
@@ -107,6 +109,33 @@ int mpn_ctx_synchronize(mpn_ctx *ctx) {
 }
 
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int mpn_ctx_timeline_begin(mpn_ctx *ctx, int32_t max_launches) {
+  if (!ctx || max_launches <= 0) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (max_launches > ctx->tl_cap) {
+    if (ctx->tl_min) { cudaFree(ctx->tl_min); cudaFree(ctx->tl_max); ctx->tl_min = ctx->tl_max = nullptr; }
+    MPN_CUDA(ctx, cudaMalloc((void **)&ctx->tl_min, sizeof(unsigned long long) * 4 * (size_t)max_launches));
+    MPN_CUDA(ctx, cudaMalloc((void **)&ctx->tl_max, sizeof(unsigned long long) * 4 * (size_t)max_launches));
+    ctx->tl_cap = max_launches;
+  }
+  MPN_CUDA(ctx, cudaMemsetAsync(ctx->tl_min, 0xff, sizeof(unsigned long long) * 4 * (size_t)ctx->tl_cap, ctx->stream));
+  MPN_CUDA(ctx, cudaMemsetAsync(ctx->tl_max, 0, sizeof(unsigned long long) * 4 * (size_t)ctx->tl_cap, ctx->stream));
+  ctx->tl_n = 0; ctx->tl_on = 1;
+  return MPN_OK;
+}
+
+int mpn_ctx_timeline_end(mpn_ctx *ctx, uint64_t *stamps_min, uint64_t *stamps_max, int32_t *n_launches) {
+  if (!ctx || !stamps_min || !stamps_max || !n_launches) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->tl_on = 0;
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int n = std::min(ctx->tl_n, ctx->tl_cap);
+  MPN_CUDA(ctx, cudaMemcpy(stamps_min, ctx->tl_min, sizeof(uint64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  MPN_CUDA(ctx, cudaMemcpy(stamps_max, ctx->tl_max, sizeof(uint64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  *n_launches = n;
+  return MPN_OK;
+}
 
 int mpn_ctx_profile_begin(mpn_ctx *ctx) {
   if (!ctx) return MPN_ERR_ARG;

@@ -32,6 +32,8 @@ struct mpn_ctx {
   float *sk_ws = nullptr; unsigned *sk_flags = nullptr; unsigned sk_epoch = 0;
   // NMS tie flags live in scratch2 and are reset by their last reader; (pointer, count) of the region known to be zero
   void *nms_tie_ptr = nullptr; int nms_tie_n = 0;
+  // in-kernel timeline of the tcgen05 launches (diagnostics, mpn_ctx_timeline_begin/end): per launch 4 min- and 4 max-stamps
+  unsigned long long *tl_min = nullptr, *tl_max = nullptr; int tl_cap = 0, tl_n = 0, tl_on = 0;
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };

@@ -69,6 +69,8 @@ struct TcParams {
   // inside a tile writes its raw fp32 partial to sk_ws and raises sk_flags (= sk_epoch), the range that starts the tile
   // adds the partials in pair order (fixed => deterministic) and runs the real epilogue.
   int streamk; unsigned sk_epoch; float *sk_ws; unsigned *sk_flags;
+  unsigned long long *tl_min, *tl_max;   // diagnostics: %globaltimer stamps of this launch (4 + 4 u64) or null
+  int b_prefetch;                // 3x3 kernel: fill the B ring with weight tiles before the programmatic-dependency wait
   int tma_store;                 // 3x3 kernel: the epilogue stages 64-channel slabs in shared memory and ships them with TMA tensor stores
 };
 
@@ -111,6 +113,16 @@ struct SegWalk {
 struct EpiSk { int role = 0; float4 *part_out = nullptr; const float4 *part_in = nullptr; long long part_stride4 = 0; int ncont = 0; };
 enum { SK_FULL = 0, SK_WRITER = 1, SK_FINISHER = 2 };
 
+// ---------------------------------------------------------------- timeline stamps (diagnostics)
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+__device__ __forceinline__ void tl_min_stamp(const unsigned long long *base_, int i) {
+  if (base_) atomicMin(const_cast<unsigned long long *>(base_) + i, gtimer());
+}
+__device__ __forceinline__ void tl_max_stamp(const unsigned long long *base_, int i) {
+  if (base_) atomicMax(const_cast<unsigned long long *>(base_) + i, gtimer());
+}
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -571,6 +583,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tl_min_stamp(p.tl_min, 0);
   // CG=2: the grid is made of CTA pairs (cluster 2x1x1). Pair `unit` walks the schedule; CTA `rank` of the pair owns
   // m-tile 2*mp+rank and rows [rank*BN/2, (rank+1)*BN/2) of the B tile; rank 0 (leader) issues the MMAs for both.
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -608,6 +621,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   // tail of the previous kernel in the stream; no global memory is touched before the previous grid has completed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 32) tl_min_stamp(p.tl_min, 1);
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop uniformly; one elected lane issues) =====================
@@ -664,6 +678,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % S; const uint32_t ph = (it / S) & 1u;
         mbar_wait(full_bar(s), ph);                // TMA bytes landed
+        if (it == 0 && lane == 0) tl_min_stamp(p.tl_min, 2);
         tc_fence_after();
         const uint32_t sa = __shfl_sync(0xffffffffu, smem_base + (uint32_t)s * STAGE, 0);      // warp-uniform by construction
         const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
@@ -706,6 +721,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         __syncwarp();
       }
     }
+    if (lane == 0 && rank == 0) tl_max_stamp(p.tl_max, 0);
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
@@ -741,9 +757,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 
   if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging must outlive its stores
+  if (warp == 2 && lane == 0) tl_max_stamp(p.tl_max, 1);
   // ---- teardown: everyone (both CTAs) done with TMEM / peer smem / peer barriers before anything is freed
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) tl_max_stamp(p.tl_max, 2);
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2)
@@ -799,6 +817,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SB + 2 + a); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tl_min_stamp(p.tl_min, 0);
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
   const int unit = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_units = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -830,8 +849,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
   // tail of the previous kernel in the stream; no global memory is touched before the previous grid has completed.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Exception: the producer warp first fills the B ring with WEIGHT tiles (static data, never written by a kernel), so
+  // the HBM latency of the first weight tiles also hides behind the previous layer's tail; it waits before its first A load.
+  if (warp != 0) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 32) tl_min_stamp(p.tl_min, 1);
+  }
 
   const bool trace = (p.dbg != nullptr) && (blockIdx.x == 0);
   unsigned long long wc0 = 0ull, wc1 = 0ull, wc2 = 0ull;
@@ -840,6 +864,41 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     // ===================== TMA producer: A ring (one box per kw) + B ring (one tile per tap) =====================
     // (whole warp runs the loop uniformly; one elected lane issues)
     {
+      auto issue_b = [&](uint32_t itb, int kcol, int b_row0) {
+        const int s = itb % SB; const uint32_t ph = (itb / SB) & 1u;
+        mbar_wait_t(emptyB(s), ph ^ 1u, wc1, trace);
+        const uint32_t sb = b_base + (uint32_t)s * B_STAGE;
+        if (elect_one()) {
+          if (CG == 2) {
+            if (rank == 0) mbar_expect_tx(fullB(s), (uint32_t)(2 * B_STAGE)); else mbar_arrive_remote(fullB(s), 0u);
+            const uint32_t lbar = leader_addr(fullB(s));
+            tma_load_2d_2sm(sb, &tmB_hi, lbar, kcol, b_row0);
+            tma_load_2d_2sm(sb + B_TILE_BYTES, &tmB_lo, lbar, kcol, b_row0);
+          } else {
+            mbar_expect_tx(fullB(s), (uint32_t)B_STAGE);
+            tma_load_2d(sb, &tmB_hi, fullB(s), kcol, b_row0);
+            tma_load_2d(sb + B_TILE_BYTES, &tmB_lo, fullB(s), kcol, b_row0);
+          }
+        }
+        __syncwarp();
+      };
+      // ---- weight prefetch: the first SB B tiles of this CTA's walk, before the dependency wait
+      uint32_t b_pre = 0;
+      {
+        SegWalk pw(p.streamk != 0, unit, num_units, total_tiles, 3 * p.cblocks);
+        int tile, s0, s1;
+        const uint32_t pre_cap = p.b_prefetch ? (uint32_t)SB : 0u;
+        while (b_pre < pre_cap && pw.next(tile, s0, s1)) {
+          const int b_row0 = (tile % p.tiles_n) * BN + (int)rank * (BN / CG);
+          for (int st = s0; st < s1 && b_pre < pre_cap; ++st) {
+            const int cb = st / 3, kwi = st - cb * 3;
+            for (int khi = 0; khi < 3 && b_pre < pre_cap; ++khi, ++b_pre)
+              issue_b(b_pre, ((khi * 3 + kwi) * p.cblocks + cb) * BK, b_row0);
+          }
+        }
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
       uint32_t itA = 0, itB = 0;
       SegWalk walk(p.streamk != 0, unit, num_units, total_tiles, 3 * p.cblocks);
       int tile, s0, s1;
@@ -869,25 +928,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               __syncwarp();
               ++itA;
             }
-            for (int khi = 0; khi < 3; ++khi, ++itB) {
-              const int s = itB % SB; const uint32_t ph = (itB / SB) & 1u;
-              mbar_wait_t(emptyB(s), ph ^ 1u, wc1, trace);
-              const uint32_t sb = b_base + (uint32_t)s * B_STAGE;
-              const int kcol = ((khi * 3 + kwi) * p.cblocks + cb) * BK;          // weights are [Cout][(kh,kw,ci)]
-              if (elect_one()) {
-                if (CG == 2) {
-                  if (rank == 0) mbar_expect_tx(fullB(s), (uint32_t)(2 * B_STAGE)); else mbar_arrive_remote(fullB(s), 0u);
-                  const uint32_t lbar = leader_addr(fullB(s));
-                  tma_load_2d_2sm(sb, &tmB_hi, lbar, kcol, b_row0);
-                  tma_load_2d_2sm(sb + B_TILE_BYTES, &tmB_lo, lbar, kcol, b_row0);
-                } else {
-                  mbar_expect_tx(fullB(s), (uint32_t)B_STAGE);
-                  tma_load_2d(sb, &tmB_hi, fullB(s), kcol, b_row0);
-                  tma_load_2d(sb + B_TILE_BYTES, &tmB_lo, fullB(s), kcol, b_row0);
-                }
-              }
-              __syncwarp();
-            }
+            for (int khi = 0; khi < 3; ++khi, ++itB)                            // weights are [Cout][(kh,kw,ci)]
+              if (itB >= b_pre) issue_b(itB, ((khi * 3 + kwi) * p.cblocks + cb) * BK, b_row0);
           }
       }
     }
@@ -912,6 +954,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           for (int khi = 0; khi < 3; ++khi, ++itB) {
             const int sB = itB % SB; const uint32_t phB = (itB / SB) & 1u;
             mbar_wait_t(fullB(sB), phB, wc1, trace);
+            if (itB == 0 && lane == 0) tl_min_stamp(p.tl_min, 2);
             tc_fence_after();
             // rows khi*8 .. khi*8+127 of the A box; all values warp-uniform by construction
             const uint32_t sa = __shfl_sync(0xffffffffu, a_base + (uint32_t)sA * R3_A_STAGE + (uint32_t)khi * 1024u, 0);
@@ -958,6 +1001,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           }
         }
     }
+    if (lane == 0 && rank == 0) tl_max_stamp(p.tl_max, 0);
   } else {
     // ===================== epilogue (warps 2..5): identical to the generic kernel, patch = 16 rows x 8 cols =====================
     const int q = warp & 3;
@@ -1030,6 +1074,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
 
   if (p.tma_store && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging must outlive its stores
+  if (warp == 2 && lane == 0) tl_max_stamp(p.tl_max, 1);
   if (trace && lane == 0) {
     // dbg[0..2] producer: wait emptyA, wait emptyB, total; [3..6] MMA: wait fullA, fullB, tempty, total; [7..9] epilogue warp 2: wait tfull, store time, total
     const unsigned long long tot = (unsigned long long)(clock64() - t_start);
@@ -1039,6 +1084,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) tl_max_stamp(p.tl_max, 2);
   if (warp == 1) {
     tc_fence_after();
     if (CG == 2)
@@ -1594,6 +1640,9 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.pool_hi = tp.pool_lo = nullptr; tp.pool_ld = 0; tp.Hp = tp.Wp = 0;
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
   tp.tma_store = 0;      // decided below, once the pooled output (if any) is known
+  tp.tl_min = tp.tl_max = nullptr;
+  if (ctx->tl_on && ctx->tl_n < ctx->tl_cap) { tp.tl_min = ctx->tl_min + 4 * ctx->tl_n; tp.tl_max = ctx->tl_max + 4 * ctx->tl_n; ++ctx->tl_n; }
+  { static const int bp = [] { const char *e = getenv("MPN_TC_BPREFETCH"); return (e && e[0] == '0') ? 0 : 1; }(); tp.b_prefetch = bp; }
   if (pl.streamk && pl.mode == 1) {
     {   // every pair must own >= 4 steps: an empty range would leave a finisher waiting for a partial nobody writes
       const long long tiles_m_ = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
