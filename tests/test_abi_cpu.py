@@ -204,3 +204,27 @@ def test_streamk_partition_is_exact_and_deadlock_free(tiles, S, units):
     # plain schedule: whole tiles round-robin
     seen = sorted(p for u in range(units) for p in _segwalk(lib, 0, u, units, tiles, S))
     assert seen == [(t, 0, S) for t in range(tiles)]
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The last committed bench line (profiles/) carries every key of the bench.py contract, with sane values."""
+    import glob
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "profiles", "r01*_bench_n1.json")))
+    assert files, "no committed bench line"
+    d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["metric"] == "proposals/sec" and d["unit"] == "proposals/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and "workload" in d["config"] and d["warmup"] >= 3
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and {"achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.0 < r["frac"] < 1.0
+    assert d["gpu_launches"] > 0 and d["value"] > 1e5
+    if "cpu_baseline" in d:
+        assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
