@@ -6,6 +6,11 @@
 // One convolution (or Linear = 1x1 conv on a 1x1 map) in the internal NHWC split-bf16
 // representation. y[n,ho,wo,co] = sum_{kh,kw,ci} x[n, ho*s+kh-p, wo*s+kw-p, ci] * w[co,(kh,kw,ci)]
 //                                 + bias[co] (+ residual) (ReLU)
+// fp32 output of a split-K GEMM scattered by column range (several small heads computed by ONE GEMM): the reduce pass
+// writes column c in [c0, c1) of segment s to ptr[pixel * ld + (c - c0)]
+struct OutSeg { int c0, c1; float *ptr; long long ld; };
+struct OutScatter { int n = 0; OutSeg seg[8]; };
+
 struct ConvProblem {
   DTensor x;                       // input  (split planes)
   const __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;   // [Cout][kh*kw*Cin], K order (kh,kw,ci)
@@ -21,6 +26,7 @@ struct ConvProblem {
   // accumulator grouping, split-K count, no stream-K — so a row's result does not change with the number of rows in
   // the call (chunked forward == full forward, bit for bit: modules/test.lua:85-98, ImageDetect.lua:126-133)
   int m_invariant = 0;
+  OutScatter scatter;              // n > 0: split-K plans only (conv_tc_launch rejects it otherwise)
   void *dbg = nullptr;             // diagnostics: device buffer of 16 x u64 pipeline-wait counters (tools/engine_sweep.py)
 };
 

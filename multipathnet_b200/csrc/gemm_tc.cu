@@ -1326,6 +1326,7 @@ struct ReduceParams {
   const float *ws; long long split_stride; int splitk; long long pixels; int Cout;
   const float *bias; const __nv_bfloat16 *res_hi, *res_lo; long long res_ld; int relu;
   __nv_bfloat16 *out_hi, *out_lo; long long out_ld; float *out_f32; long long out_f32_ld;
+  OutScatter scatter;
 };
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceParams r) {
   MPN_PDL_SYNC();
@@ -1338,7 +1339,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceParams r
   if (r.res_hi) acc += join_bf16(r.res_hi[pix * r.res_ld + c], r.res_lo[pix * r.res_ld + c]);
   if (r.relu) acc = fmaxf(acc, 0.f);
   if (r.out_hi) { __nv_bfloat16 h, l; split_bf16(acc, h, l); r.out_hi[pix * r.out_ld + c] = h; r.out_lo[pix * r.out_ld + c] = l; }
-  if (r.out_f32) r.out_f32[pix * r.out_f32_ld + c] = acc;
+  if (r.scatter.n > 0) {                      // several heads in one GEMM: each column range has its own dense destination
+#pragma unroll 1
+    for (int g = 0; g < r.scatter.n; ++g)
+      if (c >= r.scatter.seg[g].c0 && c < r.scatter.seg[g].c1) { r.scatter.seg[g].ptr[pix * r.scatter.seg[g].ld + (c - r.scatter.seg[g].c0)] = acc; break; }
+  } else if (r.out_f32) r.out_f32[pix * r.out_f32_ld + c] = acc;
 }
 
 // ---------------------------------------------------------------- host: TMA descriptors
@@ -1667,6 +1672,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   if (p.y.hi) MPN_CHECK_ARG(ctx, p.Cout % 8 == 0 && p.y.ld % 8 == 0, "conv_tc: split output needs Cout, ld multiples of 8");
   if (pl.mode == 0 && pl.splitk == 1)
     tp.tma_store = (pl.tma_store && !tp.out_f32 && tp.out_hi && !tp.pool_hi) ? 1 : 0;
+  MPN_CHECK_ARG(ctx, p.scatter.n == 0 || pl.splitk > 1, "conv_tc: scattered outputs need a split-K plan");
   if (pl.splitk > 1) {
     // partial accumulators go to a dense fp32 workspace [split][pixel][Cout]; bias/residual/ReLU/output split move to the reduce
     const long long pixels = (long long)p.y.N * p.y.H * p.y.W;
@@ -1682,6 +1688,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     r.ws = ws; r.split_stride = tp.split_stride; r.splitk = pl.splitk; r.pixels = pixels; r.Cout = p.Cout;
     r.bias = p.bias; r.res_hi = p.res.hi; r.res_lo = p.res.lo; r.res_ld = p.res.ld; r.relu = p.relu;
     r.out_hi = p.y.hi; r.out_lo = p.y.lo; r.out_ld = p.y.ld; r.out_f32 = p.y.f32; r.out_f32_ld = p.y_f32_ld;
+    r.scatter = p.scatter;
     const long long total = pixels * p.Cout;
     MPN_CUDA(ctx, mpn_launch_pdl(ctx, splitk_reduce_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, r));
     MPN_LAUNCHED(ctx);
