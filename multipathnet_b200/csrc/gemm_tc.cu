@@ -1459,10 +1459,9 @@ int conv1_tc_launch(mpn_ctx *ctx, const float *x_nchw, int N, int H, int W, cons
   { const char *e = getenv("MPN_C1_TRACE"); if (e && e[0] == '1') tp.dbg = reinterpret_cast<unsigned long long *>(y.hi); }   // any non-null value: the kernel only prints
   MPN_CHECK_ARG(ctx, y.ld == 64 && (long long)N * H * W < (1ll << 31) - 256, "conv1_tc: dense 64-channel output and < 2^31 pixels");
   const int smem = C1_STAGES * C1_A_STAGE + C1_B_BYTES + 2 * C1_STG_BUF + 1024 + 256;
-  static int attr_set = 0;
-  if (!attr_set) {
+  if (!ctx->tc_attr_set[14]) {       // per ctx (= per device): the attribute is per device function
     MPN_CUDA(ctx, cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = 1;
+    ctx->tc_attr_set[14] = 1;
   }
   const long long tiles = ((long long)N * H * W + BM - 1) / BM;
   cudaLaunchConfig_t cfg = {};
@@ -1659,7 +1658,8 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
       MPN_CUDA(ctx, cudaMalloc((void **)&ctx->sk_flags, (size_t)ctx->sm_count * EPI_WARPS * sizeof(unsigned)));
       MPN_CUDA(ctx, cudaMemsetAsync(ctx->sk_flags, 0, (size_t)ctx->sm_count * EPI_WARPS * sizeof(unsigned), ctx->stream));
     }
-    tp.streamk = 1; tp.sk_epoch = ++ctx->sk_epoch; tp.sk_ws = ctx->sk_ws; tp.sk_flags = ctx->sk_flags;
+    if (++ctx->sk_epoch == 0) ++ctx->sk_epoch;      // 0 is the flags' initial value
+    tp.streamk = 1; tp.sk_epoch = ctx->sk_epoch; tp.sk_ws = ctx->sk_ws; tp.sk_flags = ctx->sk_flags;
   }
   if (p.pool.hi) {
     // fused 2x2/2 (ceil) max pool: the 3x3 kernel's 16 x 8 patches start at even coordinates, so no window straddles tiles
