@@ -1532,7 +1532,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
           // (of 74 pairs) at 256 but 4 x 18 = 72 units at 240, each 6% shorter, and whole-tile K loops keep chunk invariance
           const int bn = bi == 0 ? 256 : (bi == 1 ? 240 : (bi == 2 ? 128 : 64));
           if (bn == 240 && !(pl.flat && cg == 2 && mode == 0 && p.Cout >= 1024)) continue;
-          if (bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
+          if (!p.m_invariant && bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
           if (p.m_invariant && num_acc(bn) != (p.Cout > 128 ? 1 : (p.Cout > 64 ? 2 : 3))) continue;   // rounding must not depend on M
           if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
           const long long tn_ = (p.Cout + bn - 1) / bn;
