@@ -241,6 +241,11 @@ int mpn_conv_bench(mpn_ctx *ctx, int64_t N, int64_t Cin, int64_t H, int64_t W, i
  * 1: contiguous (tile, step) ranges in rotated order (continuation piece, head piece, whole tiles). pieces: max_pieces x 3. */
 int mpn_debug_segwalk(int32_t streamk, int32_t unit, int32_t num_units, int32_t total_tiles, int32_t steps_per_tile,
                       int32_t *pieces, int32_t max_pieces, int32_t *n_pieces);
+/* host-only view of the planner (no GPU): the engine configuration chosen for a conv / Linear layer (Cin multiple of 64) on
+ * a device with sm_count SMs; per_roi = 1 for per-ROI layers (rounding-relevant choices from (Cout, K) only).
+ * out[8] = {mode (bit 0: 3x3 A-reuse kernel), CTA group, N tile, split-K, stream-K, patch tn, th, tw}. */
+int mpn_debug_plan(int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride, int32_t pad,
+                   int32_t per_roi, int32_t sm_count, int32_t *out);
 /* standalone conv check entry (tests): x N x Cin x H x W, w Cout x Cin x kh x kw (Torch layouts) */
 int mpn_conv_check(mpn_ctx *ctx, const float *x, int64_t N, int64_t Cin, int64_t H, int64_t W,
                    const float *w, const float *bias, int64_t Cout, int32_t kh, int32_t kw,

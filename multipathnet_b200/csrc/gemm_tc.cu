@@ -1481,9 +1481,11 @@ double conv_flops(const ConvProblem &p) {
   return 2.0 * (double)p.x.C * p.Cout * p.kh * p.kw * Ho * Wo * (double)p.y.N;
 }
 
-int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
+// choose_only: stop after the (kernel, CG, BN, stream-K, split-K, patch) choice — no pointers, no TMA descriptors, no GPU
+// (mpn_debug_plan: CPU tests pin the planner's choices for the BASELINE layers).
+static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, ConvPlan &pl, bool choose_only) {
   pl.valid = 0;
-  MPN_CHECK_ARG(ctx, p.x.hi && p.x.lo && p.w_hi && p.w_lo, "conv_tc: operands must be split-bf16");
+  MPN_CHECK_ARG(ctx, choose_only || (p.x.hi && p.x.lo && p.w_hi && p.w_lo), "conv_tc: operands must be split-bf16");
   MPN_CHECK_ARG(ctx, p.x.C % BK == 0, "conv_tc: Cin must be a multiple of 64");
   MPN_CHECK_ARG(ctx, p.x.ld % 8 == 0, "conv_tc: input pixel stride must be a multiple of 8 elements");
   MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
@@ -1537,7 +1539,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
           if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
           const long long tn_ = (p.Cout + bn - 1) / bn;
           const long long units = ((tiles_m + cg - 1) / cg) * tn_;
-          const long long slots = ctx->sm_count / cg;
+          const long long slots = sm_count / cg;
           const long long rounds = (units + slots - 1) / slots;
           const double rows = mode ? (3.0 * 144 + 9.0 * bn / cg) : (double)taps * (128 + bn / cg);
           const double cyc = std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
@@ -1584,7 +1586,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     // small); it is either that value or 1
     const long long tiles_m = (long long)pl.tiles_img * pl.tiles_h * pl.tiles_w;
     const long long units = ((tiles_m + pl.CG - 1) / pl.CG) * pl.tiles_n;
-    const long long slots = ctx->sm_count / pl.CG;
+    const long long slots = sm_count / pl.CG;
     const long long num_kb = (long long)p.kh * p.kw * (p.x.C / BK);
     long long sk = std::min<long long>(num_kb / 8, 8);
     if (p.m_invariant) { if (!(pl.flat && p.Cout <= 128) || sk < 2) sk = 1; }      // a function of (Cout, K) only
@@ -1598,6 +1600,7 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
     pl.splitk = 1; pl.kb_per_split = 9 * (int)(p.x.C / BK);
   }
   pl.tma_store = 0;
+  if (choose_only) return MPN_OK;
   if (p.y.hi && p.y.lo && (p.Cout % 64) == 0 && (p.y.ld % 8) == 0) {
     // output tensor maps of the TMA-store epilogue: box = one 64-channel slab of the tile's pixel patch
     // (3x3 kernel: 16 x 8; generic: tn x th x tw; flat: 128 consecutive rows)
@@ -1623,6 +1626,8 @@ int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) {
   pl.valid = 1;
   return MPN_OK;
 }
+
+int conv_tc_plan(mpn_ctx *ctx, const ConvProblem &p, ConvPlan &pl) { return conv_tc_plan_impl(ctx, ctx->sm_count, p, pl, false); }
 
 int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_TC);
@@ -1735,5 +1740,23 @@ extern "C" int mpn_debug_segwalk(int32_t streamk, int32_t unit, int32_t num_unit
     pieces[3 * n] = tile; pieces[3 * n + 1] = s0; pieces[3 * n + 2] = s1; ++n;
   }
   *n_pieces = n;
+  return MPN_OK;
+}
+
+// Host-only view of the planner (no GPU): which engine configuration conv_tc_plan would pick for a layer on a device
+// with `sm_count` SMs. out[8] = {mode (bit 0: 3x3 A-reuse kernel), CTA group, BN, split-K, stream-K, tn, th, tw}.
+extern "C" int mpn_debug_plan(int64_t N, int64_t Cin, int64_t H, int64_t W, int64_t Cout, int32_t k, int32_t stride, int32_t pad,
+                              int32_t per_roi, int32_t sm_count, int32_t *out) {
+  if (!out || N <= 0 || Cin <= 0 || Cin % 64 || H <= 0 || W <= 0 || Cout <= 0 || k <= 0 || stride < 1 || stride > 2 || pad < 0 || sm_count < 2)
+    return MPN_ERR_ARG;
+  ConvProblem p;
+  p.x.N = N; p.x.H = H; p.x.W = W; p.x.C = Cin; p.x.ld = Cin;
+  p.Cout = (int)Cout; p.kh = p.kw = k; p.stride = stride; p.pad = pad; p.m_invariant = per_roi ? 1 : 0;
+  p.y.N = N; p.y.H = (H + 2 * pad - k) / stride + 1; p.y.W = (W + 2 * pad - k) / stride + 1; p.y.C = Cout; p.y.ld = Cout;
+  if (p.y.H <= 0 || p.y.W <= 0) return MPN_ERR_ARG;
+  ConvPlan pl;
+  const int rc = conv_tc_plan_impl(nullptr, sm_count, p, pl, true);
+  if (rc != MPN_OK) return rc;
+  out[0] = pl.mode; out[1] = pl.CG; out[2] = pl.BN; out[3] = pl.splitk; out[4] = pl.streamk; out[5] = pl.tn; out[6] = pl.th; out[7] = pl.tw;
   return MPN_OK;
 }

@@ -228,3 +228,44 @@ def test_committed_bench_line_follows_the_contract():
     assert d["gpu_launches"] > 0 and d["value"] > 1e5
     if "cpu_baseline" in d:
         assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def _plan(lib, N, Cin, H, W, Cout, k=3, s=1, p=1, per_roi=0, sm=148):
+    out = (ctypes.c_int32 * 8)()
+    assert lib.mpn_debug_plan(N, Cin, H, W, Cout, k, s, p, per_roi, sm, out) == 0
+    return dict(zip(("mode", "cg", "bn", "splitk", "streamk", "tn", "th", "tw"), out))
+
+
+def test_planner_choices_for_the_default_workload():
+    """Host view of conv_tc_plan (no GPU) on a 148-SM device: the configurations the measured launch lists show
+    (profiles/r01h_launches.csv) — a regression guard for the cost model."""
+    lib = mpn.load_library()
+    want = {  # layer: (args, mode, cg, bn, splitk, streamk)
+        "conv1_2": ((1, 64, 600, 800, 64), 1, 2, 64, 1, 0), "conv2_1": ((1, 64, 300, 400, 128), 1, 2, 128, 1, 0),
+        "conv2_2": ((1, 128, 300, 400, 128), 1, 2, 128, 1, 0), "conv3_1": ((1, 128, 150, 200, 256), 1, 2, 256, 1, 0),
+        "conv3_2": ((1, 256, 150, 200, 256), 1, 2, 128, 1, 1), "conv4_1": ((1, 256, 75, 100, 512), 1, 2, 256, 1, 0),
+        "conv4_2": ((1, 512, 75, 100, 512), 1, 2, 256, 1, 0), "conv5_1": ((1, 512, 38, 50, 512), 1, 2, 128, 1, 1),
+    }
+    for name, (args, mode, cg, bn, sk, stk) in want.items():
+        pl = _plan(lib, *args)
+        assert (pl["mode"], pl["cg"], pl["bn"], pl["splitk"], pl["streamk"]) == (mode, cg, bn, sk, stk), (name, pl)
+        assert (pl["tn"], pl["th"], pl["tw"]) == (1, 16, 8)
+    heads = {"fc6": ((1000, 25088, 1, 1, 4096), 240, 1), "fc7": ((1000, 4096, 1, 1, 4096), 240, 1),
+             "cls": ((1000, 4096, 1, 1, 21), 64, 8), "bbox": ((1000, 4096, 1, 1, 84), 128, 8)}
+    for name, (args, bn, sk) in heads.items():
+        pl = _plan(lib, *args, k=1, s=1, p=0, per_roi=1)
+        assert (pl["mode"], pl["cg"], pl["bn"], pl["splitk"], pl["streamk"], pl["tw"]) == (0, 2, bn, sk, 0, 128), (name, pl)
+
+
+@pytest.mark.parametrize("Cout,K", [(21, 4096), (84, 4096), (128, 1024), (160, 2048), (512, 2048), (4096, 25088), (4096, 4096)])
+def test_planner_keeps_per_roi_rounding_independent_of_row_count(Cout, K):
+    """Per-ROI layers: whatever the number of rows, the accumulator grouping (a function of the N tile class) and the
+    split-K count are the same, and stream-K is never used — the preconditions of bit-exact chunk invariance."""
+    lib = mpn.load_library()
+    acc = lambda bn: 1 if bn > 128 else (2 if bn == 128 else 3)
+    seen = set()
+    for rows in (1, 7, 100, 128, 129, 300, 1000, 2000, 5000, 40000):
+        pl = _plan(lib, rows, K, 1, 1, Cout, k=1, s=1, p=0, per_roi=1)
+        assert pl["streamk"] == 0
+        seen.add((acc(pl["bn"]), pl["splitk"]))
+    assert len(seen) == 1, seen
