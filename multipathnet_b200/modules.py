@@ -109,6 +109,35 @@ class ROIPooling(_Module):
         return out
 
 
+class SelectBoxes:
+    """nn.SelectBoxes (modules/SelectBoxes.lua:26-56), forward only: input {classes R x C, boxes R x 4C} -> for every row
+    the 4 values of its arg-max class (first maximum, like torch.max), optionally de-normalised with std / mean
+    (SelectBoxes.lua:45-52). Host side (numpy): R x C is tiny, and the reference only uses it between two detect() calls
+    of the iterative localisation (Tester_FRCNN.lua:82-89)."""
+
+    def __init__(self, mean=None, std=None):
+        self.mean = None if mean is None else np.asarray(mean, np.float32).reshape(1, 4)
+        self.std = None if std is None else np.asarray(std, np.float32).reshape(1, 4)
+        self.output = None
+
+    def forward(self, input):
+        classes, ys = input
+        classes = np.asarray(classes, np.float32)
+        ys = np.asarray(ys, np.float32)
+        if classes.ndim != 2 or ys.ndim != 2 or ys.shape[0] != classes.shape[0] or ys.shape[1] != 4 * classes.shape[1]:
+            raise ValueError("SelectBoxes: expected {R x C, R x 4C}")
+        maxids = np.argmax(classes, axis=1)                       # first maximum on ties
+        cols = maxids[:, None] * 4 + np.arange(4)[None, :]
+        out = np.take_along_axis(ys, cols, axis=1)
+        if self.std is not None:
+            out = out * self.std + self.mean
+        self.output = out.astype(np.float32)
+        return self.output
+
+    def updateGradInput(self, input, gradOutput):
+        raise RuntimeError("SelectBoxes: training is out of scope here")
+
+
 class ImageTransformer:
     """fbcoco.ImageTransformer (host side). kind: 'ross' = RossTransformer, 'imagenet' = ImagenetTransformer."""
 

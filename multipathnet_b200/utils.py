@@ -44,3 +44,31 @@ def keep_top_k(boxes: List[np.ndarray], top_k: int):
     scores = np.sort(np.concatenate([b[:, -1] for b in nz]))[::-1]
     thresh = scores[min(len(scores), top_k) - 1]
     return [b[b[:, -1] >= thresh] if b.size else b for b in boxes], float(thresh)
+
+
+def joinTable(tensors: List[np.ndarray], dim: int = 0) -> np.ndarray:
+    """utils.joinTable (utils.lua:42-71): concatenate, skipping empty tensors."""
+    nz = [np.asarray(t) for t in tensors if np.asarray(t).size]
+    if not nz:
+        return np.zeros((0,), np.float32)
+    return np.concatenate(nz, axis=dim)
+
+
+def transposeBoxes(aboxes_t: List[List[np.ndarray]], num_classes: int) -> List[List[np.ndarray]]:
+    """Tester:transposeBoxes (Tester_FRCNN.lua:176-187): [image][class] -> [class][image]."""
+    return [[aboxes_t[i][j] for i in range(len(aboxes_t))] for j in range(num_classes)]
+
+
+def coco_results(aboxes: List[List[np.ndarray]], image_ids: List[int], category_ids: List[int]) -> np.ndarray:
+    """testCoco.evaluate's result tensor (testCoco/init.lua:65-86): rows [image_id, x1-1, y1-1, w, h, score, category_id]
+    with w = x2 - x1 and h = y2 - y1 (no +1, as the reference), classes outermost, images in order."""
+    rows = []
+    for j, per_img in enumerate(aboxes):
+        for i, t in enumerate(per_img):
+            t = np.asarray(t, np.float32)
+            if t.ndim == 2 and t.shape[0] > 0:
+                r = np.empty((t.shape[0], 7), np.float32)
+                r[:, 0] = image_ids[i]; r[:, 1] = t[:, 0] - 1; r[:, 2] = t[:, 1] - 1
+                r[:, 3] = t[:, 2] - t[:, 0]; r[:, 4] = t[:, 3] - t[:, 1]; r[:, 5] = t[:, 4]; r[:, 6] = category_ids[j]
+                rows.append(r)
+    return np.concatenate(rows, 0) if rows else np.zeros((0, 7), np.float32)
