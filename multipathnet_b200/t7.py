@@ -301,8 +301,8 @@ def fast_rcnn_from_t7(model, num_classes: int = None, name: str = "t7"):
     """The graph `models/vgg.lua:23-31` (or alexnet / any trunk of conv / ReLU / max-pool) returns, as saved by train.lua,
     -> ModelSpec:  Sequential{ ParallelTable{trunk, Identity}, inn.ROIPooling(W,H,s), View, top (Linear/ReLU/Dropout...),
     ConcatTable{Linear cls, Linear bbox} [, BBoxNorm / SoftMax added at test time] }.
-    Grouped convolutions, LRN and the MultiPathNet / ResNet graphs (ModelParallelTable towers, residual blocks) are not
-    covered here: those specs are built by multipathnet_b200.models from the same Lua files."""
+    Flat-list reader for this one graph; `model_from_t7` below evaluates the general table algebra (ResNet residual
+    blocks, MultiPathNet towers). Grouped convolutions and LRN (CaffeNet) are refused by both."""
     from ._lib import Head, Layer, ModelSpec, Tower, MPN_LAYER_CONV, MPN_LAYER_FLATTEN, MPN_LAYER_MAXPOOL
     if not isinstance(model, T7Object) or _base(model.typename) != "Sequential":
         raise ValueError("expected the nn.Sequential detection model")
@@ -435,3 +435,395 @@ def proposals_from_t7(obj) -> Dict[str, Any]:
             v = obj[k]
             res[k] = [v[i] for i in sorted(v)] if isinstance(v, dict) else v
     return res
+
+
+# ------------------------------------------------------------------------- general nn table algebra -> ModelSpec
+# The MultiPathNet (models/multipathnet.lua:30-121) and ResNet (models/resnet.lua:28-50) graphs are not flat lists:
+# residual blocks are ConcatTable{branch, shortcut} + CAddTable, the skip trunk returns a table {conv5, conv4, conv3}
+# through ConcatTable / ParallelTable / FlattenTable. `_Layers` evaluates that table algebra symbolically: a value is a
+# slot number or a (nested) list of values, leaf modules append Layer records.  PARITY UNPINNED like the rest of this file;
+# the field names of third-party modules (nn.SpatialBatchNormalization running_mean / running_var | running_std,
+# inn.ConstAffine a / b, nn.Narrow index / length, nn.Select index, nn.MulConstant constant_scalar) are recalled from
+# torch/nn and imagine-nn, checked only against graphs this repo's tests assemble.
+_PASS = ("Identity", "Copy", "Contiguous", "View", "Reshape", "Transpose", "Squeeze")
+
+
+def _f32(a):
+    return np.ascontiguousarray(np.asarray(a, np.float32))
+
+
+class _Layers:
+    def __init__(self, add, arrays, cin: int, hw=None):
+        from ._lib import Layer                                     # noqa: F401  (dataclass used below)
+        self.add, self.arrays = add, arrays
+        self.layers: List[Any] = []
+        self.next = 1
+        self.shape = {0: (cin, None, None) if hw is None else (cin, hw[0], hw[1])}
+
+    # -- helpers
+    def _slot(self, shape):
+        s = self.next
+        self.next += 1
+        self.shape[s] = shape
+        return s
+
+    def _producer(self, slot):
+        for L in reversed(self.layers):
+            if L.out_slot == slot:
+                return L
+        return None
+
+    @staticmethod
+    def _need_slot(v, what):
+        if not isinstance(v, int):
+            raise NotImplementedError(f"{what} applied to a table")
+        return v
+
+    def _open_conv(self, slot, what):
+        from ._lib import MPN_LAYER_CONV
+        L = self._producer(slot)
+        if L is None or L.kind != MPN_LAYER_CONV or L.relu or L.residual_slot >= 0:
+            raise NotImplementedError(f"{what} that does not directly follow a convolution / Linear")
+        return L
+
+    def _affine(self, slot, scale, shift, what):
+        """y = scale[c] * x + shift[c] right after a convolution: fold into its weight and bias (inn.utils.foldBatchNorm)."""
+        L = self._open_conv(slot, what)
+        scale, shift = np.asarray(scale, np.float64).reshape(-1), np.asarray(shift, np.float64).reshape(-1)
+        if scale.size != L.cout or shift.size != L.cout:
+            raise ValueError(f"{what}: {scale.size} channels after a convolution with {L.cout}")
+        w = self.arrays[L.weight].astype(np.float64)
+        self.arrays[L.weight] = _f32(w * scale.reshape((-1,) + (1,) * (w.ndim - 1)))
+        self.arrays[L.bias] = _f32(self.arrays[L.bias].astype(np.float64) * scale + shift)
+
+    # -- the evaluator
+    def run(self, m, v):
+        from ._lib import Layer, MPN_LAYER_AVGPOOL, MPN_LAYER_CONV, MPN_LAYER_FLATTEN, MPN_LAYER_MAXPOOL
+        if not isinstance(m, T7Object):
+            raise ValueError("not a torch object")
+        b = _base(m.typename)
+        if b in ("Sequential", "NoBackprop"):
+            for c in _children(m):
+                v = self.run(c, v)
+            return v
+        if b in ("DataParallelTable", "DataParallel"):
+            kids = _children(m)
+            return self.run(kids[0], v) if kids else v
+        if b == "ConcatTable":
+            return [self.run(c, v) for c in _children(m)]
+        if b == "ParallelTable":
+            kids = _children(m)
+            if not isinstance(v, list) or len(v) != len(kids):
+                raise ValueError("nn.ParallelTable arity does not match its input table")
+            return [self.run(c, vi) for c, vi in zip(kids, v)]
+        if b == "FlattenTable":
+            def flat(x):
+                return [y for e in x for y in flat(e)] if isinstance(x, list) else [x]
+            return flat(v)
+        if b == "SelectTable":
+            i = int(m.index)
+            if not isinstance(v, list):
+                raise ValueError("nn.SelectTable on a tensor")
+            return v[i - 1] if i > 0 else v[i]
+        if b in _PASS:
+            return v
+        if b == "Dropout":
+            if m.get("v2", True) is False:
+                raise NotImplementedError("nn.Dropout(v2=false) scales at test time")
+            return v
+        if b == "CAddTable":
+            if not isinstance(v, list) or len(v) != 2 or not all(isinstance(x, int) for x in v):
+                raise NotImplementedError("nn.CAddTable of anything but two tensors")
+            for main, other in ((v[0], v[1]), (v[1], v[0])):
+                L = self._producer(main)
+                if L is not None and L.kind == MPN_LAYER_CONV and not L.relu and L.residual_slot < 0 and self.shape[main] == self.shape[other]:
+                    self.layers.remove(L)                      # the shortcut branch was emitted after it: run it last
+                    self.layers.append(L)
+                    L.residual_slot = other
+                    return main
+            raise NotImplementedError("residual add whose branches do not end in a bare convolution")
+        s = self._need_slot(v, m.typename)
+        c, h, w = self.shape[s]
+        if b in ("SpatialConvolution", "SpatialConvolutionMM"):
+            if int(m.get("groups", 1) or 1) != 1:
+                raise NotImplementedError("grouped convolution (CaffeNet) is not on the accelerated path")
+            cout, cin, kh, kw = int(m.nOutputPlane), int(m.nInputPlane), int(m.kH), int(m.kW)
+            st, pd = int(m.get("dW", 1)), int(m.get("padW", 0) or 0)
+            if kh != kw or st != int(m.get("dH", st)) or pd != int(m.get("padH", pd) or 0):
+                raise NotImplementedError("anisotropic kernel / stride / padding")
+            if cin != c:
+                raise ValueError(f"conv expects {cin} input planes, its input has {c}")
+            bias = m.get("bias")
+            o = self._slot((cout, None if h is None else (h + 2 * pd - kh) // st + 1, None if w is None else (w + 2 * pd - kw) // st + 1))
+            self.layers.append(Layer(MPN_LAYER_CONV, s, o, cin=cin, cout=cout, kh=kh, kw=kw, stride=st, pad=pd, relu=0,
+                                     weight=self.add(_f32(m.weight).reshape(cout, cin, kh, kw)),
+                                     bias=self.add(np.zeros(cout, np.float32) if bias is None else _f32(bias).reshape(cout))))
+            return o
+        if b == "Linear":
+            wt = _f32(m.weight)
+            if h is not None and h * w > 1:                     # View(-1):setNumInputDims(3) before the first Linear
+                s2 = self._slot((c * h * w, 1, 1))
+                self.layers.append(Layer(MPN_LAYER_FLATTEN, s, s2))
+                s, c = s2, c * h * w
+            if wt.shape[1] != c:
+                raise ValueError(f"Linear expects {wt.shape[1]} inputs, its input has {c}")
+            bias = m.get("bias")
+            o = self._slot((wt.shape[0], 1, 1))
+            self.layers.append(Layer(MPN_LAYER_CONV, s, o, cin=c, cout=wt.shape[0], relu=0, weight=self.add(wt),
+                                     bias=self.add(np.zeros(wt.shape[0], np.float32) if bias is None else _f32(bias).reshape(-1))))
+            return o
+        if b in ("SpatialBatchNormalization", "BatchNormalization"):
+            eps = float(m.get("eps", 1e-5))
+            if m.get("running_var") is not None:
+                inv = 1.0 / np.sqrt(np.asarray(m.running_var, np.float64) + eps)
+            elif m.get("running_std") is not None:              # older nn: running_std already holds 1 / sqrt(var + eps)
+                inv = np.asarray(m.running_std, np.float64)
+            else:
+                raise ValueError("batch normalisation without running statistics")
+            g = np.asarray(m.weight, np.float64) if m.get("weight") is not None else np.ones_like(inv)
+            beta = np.asarray(m.bias, np.float64) if m.get("bias") is not None else np.zeros_like(inv)
+            scale = g * inv
+            self._affine(s, scale, beta - np.asarray(m.running_mean, np.float64) * scale, m.typename)
+            return s
+        if b == "ConstAffine":                                  # inn.utils.BNtoFixed: y = a * x + b per channel
+            a = m.get("a", m.get("weight"))
+            sh = m.get("b", m.get("bias"))
+            if a is None or sh is None:
+                raise ValueError("inn.ConstAffine without a / b")
+            self._affine(s, a, sh, m.typename)
+            return s
+        if b == "MulConstant":
+            k = float(m.constant_scalar)
+            self._affine(s, np.full(c, k), np.zeros(c), m.typename)
+            return s
+        if b in ("ReLU", "Threshold"):
+            if b == "Threshold" and (float(m.get("threshold", 0)) != 0.0 or float(m.get("val", 0)) != 0.0):
+                raise NotImplementedError("nn.Threshold other than ReLU")
+            L = self._producer(s)
+            if L is None or L.kind != MPN_LAYER_CONV:
+                raise NotImplementedError("ReLU that does not follow a convolution / Linear / residual add")
+            L.relu = 1
+            return s
+        if b == "SpatialMaxPooling":
+            k, st, pd = int(m.kW), int(m.dW), int(m.get("padW", 0) or 0)
+            if k != int(m.kH) or st != int(m.dH):
+                raise NotImplementedError("anisotropic pooling")
+            ceil = 1 if m.get("ceil_mode", False) else 0
+            from .models import _pool_out
+            o = self._slot((c, None if h is None else _pool_out(h, k, st, pd, ceil), None if w is None else _pool_out(w, k, st, pd, ceil)))
+            self.layers.append(Layer(MPN_LAYER_MAXPOOL, s, o, kh=k, kw=k, stride=st, pad=pd, ceil_mode=ceil))
+            return o
+        if b == "SpatialAveragePooling":
+            if h is None or (int(m.kH), int(m.kW)) != (h, w):
+                raise NotImplementedError("average pooling other than the global one that ends a ResNet (resnet.lua:39)")
+            o = self._slot((c, 1, 1))
+            self.layers.append(Layer(MPN_LAYER_AVGPOOL, s, o))
+            return o
+        raise NotImplementedError(f"module {m.typename}")
+
+
+def _linear_heads(mods, width, add, narrows=None):
+    """classAndBBoxLinear (model_utils.lua:105-119) and its integral-loss rewrite (:275-317):
+    {Linear | ConcatTable{K x Linear}, Linear} fed by the whole tower output or by two nn.Narrow column ranges."""
+    from ._lib import Head
+    if len(mods) != 2:
+        raise NotImplementedError("expected {class head(s), bbox head}")
+    cols = narrows or [(0, width), (0, width)]
+    cls_m = _children(mods[0]) if _base(mods[0].typename) == "ConcatTable" else [mods[0]]
+    out = []
+    for ms, (c0, cl) in ((cls_m, cols[0]), ([mods[1]], cols[1])):
+        hs = []
+        for m in ms:
+            if _base(m.typename) != "Linear":
+                raise NotImplementedError(f"head module {m.typename}")
+            w = _f32(m.weight)
+            if w.shape[1] != cl:
+                raise ValueError(f"head Linear expects {w.shape[1]} inputs, its columns are {cl} wide")
+            bias = m.get("bias")
+            hs.append(Head(c0, cl, w.shape[0], add(w), add(np.zeros(w.shape[0], np.float32) if bias is None else _f32(bias).reshape(-1))))
+        out.append(hs)
+    return out[0], out[1][0]
+
+
+def _parse_pool_level(seq, trunk_vals):
+    """make1PoolingLayer (model_utils.lua:212-228): ParallelTable{SelectTable(idx), Identity}, inn.ROIPooling(7,7,s),
+    then View / Normalize(2) / Contiguous / View  |  MulConstant(f)."""
+    kids = _children(seq)
+    if len(kids) < 2 or _base(kids[0].typename) != "ParallelTable" or _base(kids[1].typename) != "ROIPooling":
+        raise NotImplementedError("pooling branch is not ParallelTable{SelectTable, Identity} + inn.ROIPooling")
+    sel = _children(kids[0])[0]
+    if _base(sel.typename) != "SelectTable":
+        raise NotImplementedError("pooling branch does not select a trunk output")
+    slot = trunk_vals[int(sel.index) - 1]
+    roi = kids[1]
+    norm, factor = False, 1.0
+    for m in kids[2:]:
+        b = _base(m.typename)
+        if b == "Normalize":
+            if float(m.get("p", 2)) != 2.0:
+                raise NotImplementedError("nn.Normalize with p != 2")
+            norm = True
+        elif b == "MulConstant":
+            factor *= float(m.constant_scalar)
+        elif b not in _PASS:
+            raise NotImplementedError(f"pooling branch module {m.typename}")
+    return slot, (int(roi.W), int(roi.H), float(roi.spatial_scale)), norm, factor
+
+
+def model_from_t7(model, name: str = "t7", transformer: str = None, num_classes: int = None):
+    """Any of the detection graphs the reference's model files return (models/{vgg,alexnet,resnet,multipathnet}.lua), as
+    torch.save'd by train.lua:195, -> ModelSpec.
+      Sequential{ ParallelTable{trunk, Identity},
+                  inn.ROIPooling, per-ROI modules                                   (vgg.lua:23-31, resnet.lua:41-50)
+                | ParallelTable{Identity, Sequential{Foveal, View, Transpose}},
+                  ModelParallelTable{ towers }, [ConcatTable{Narrow, Narrow}]        (multipathnet.lua:61-117)
+                  ConcatTable | ParallelTable {class head(s), bbox head} [, ModeSwitch (integral loss)] [, SoftMax / BBoxNorm] }
+    Batch normalisation (raw, or inn.ConstAffine after inn.utils.BNtoFixed) is folded into the preceding convolution, as
+    inn.utils.foldBatchNorm does for the frozen layers (resnet.lua:33-36); per-level MulConstant factors of the
+    un-normalised conv345Combine are folded into conv_mix's input columns (the mix is linear in them)."""
+    from ._lib import Layer, ModelSpec, Tower, MPN_LAYER_CONV, MPN_LAYER_FLATTEN
+    if not isinstance(model, T7Object) or _base(model.typename) != "Sequential":
+        raise ValueError("expected the nn.Sequential detection model")
+    top = _children(model)
+    if not top or _base(top[0].typename) != "ParallelTable" or len(_children(top[0])) != 2:
+        raise ValueError("expected nn.ParallelTable{trunk, Identity} first (vgg.lua:23-27)")
+    arrays: List[np.ndarray] = []
+
+    def add(a):
+        arrays.append(np.ascontiguousarray(a, np.float32))
+        return len(arrays) - 1
+
+    tb = _Layers(add, arrays, 3)
+    tv = tb.run(_children(top[0])[0], 0)
+    trunk_vals = tv if isinstance(tv, list) else [tv]
+    if not all(isinstance(x, int) for x in trunk_vals):
+        raise NotImplementedError("trunk returns a nested table")
+    has_res = any(L.residual_slot >= 0 for L in tb.layers)
+    rest = top[1:]
+    towers: List[Any] = []
+    widths: List[int] = []
+    i = 0
+    if rest and _base(rest[0].typename) == "ROIPooling":
+        roi = rest[0]
+        pw, ph, sc = int(roi.W), int(roi.H), float(roi.spatial_scale)
+        if len(trunk_vals) != 1:
+            raise ValueError("inn.ROIPooling on a trunk that returns several maps")
+        lb = _Layers(add, arrays, tb.shape[trunk_vals[0]][0], (ph, pw))
+        v, i = 0, 1
+        while i < len(rest) and _base(rest[i].typename) not in ("ConcatTable", "ParallelTable"):
+            v = lb.run(rest[i], v)
+            i += 1
+        c, h, w = lb.shape[v]
+        if h * w > 1:                                           # heads read a flat vector
+            v2 = lb._slot((c * h * w, 1, 1))
+            lb.layers.append(Layer(MPN_LAYER_FLATTEN, v, v2))
+            v, c = v2, c * h * w
+        if not lb.layers:
+            raise NotImplementedError("no per-ROI layer between inn.ROIPooling and the heads")
+        towers.append(Tower(region=0, levels=[(trunk_vals[0], sc)], pooled_w=pw, pooled_h=ph, normalize=0, layers=lb.layers, out_slot=v))
+        widths.append(c)
+    elif len(rest) >= 2 and _base(rest[0].typename) == "ParallelTable" and _base(rest[1].typename) == "ModelParallelTable":
+        fov = flatten_sequential(_children(rest[0])[1])
+        if not fov or _base(fov[0].typename) != "Foveal":
+            raise NotImplementedError("expected nn.Foveal on the ROI branch (multipathnet.lua:65-69)")
+        if int(rest[1].get("dimension", 2)) != 2:
+            raise NotImplementedError("ModelParallelTable joining along a dimension other than 2")
+        for t in _children(rest[1]):
+            kids = _children(t)
+            if len(kids) < 3 or _base(kids[0].typename) != "ParallelTable":
+                raise NotImplementedError("tower is not {ParallelTable{Identity, Select}, conv345Combine, classifier}")
+            sel = _children(kids[0])[1]
+            if _base(sel.typename) != "Select" or int(sel.dimension) != 1:
+                raise NotImplementedError("tower does not nn.Select(1, region) its ROIs")
+            region = int(sel.index) - 1
+            if not 0 <= region < 4:
+                raise ValueError("nn.Foveal produces 4 regions")
+            levels, shapes, norms, factors, post = [], [], [], [], 1.0
+            mix_seen, lb, v = False, None, 0
+            for m in _children(kids[1]):
+                b = _base(m.typename)
+                if b == "ConcatTable" and not levels:
+                    for br in _children(m):
+                        slot, (pw, ph, sc), nm, f = _parse_pool_level(br, trunk_vals)
+                        levels.append((slot, sc)); shapes.append((pw, ph)); norms.append(nm); factors.append(f)
+                elif b == "JoinTable":
+                    if int(m.dimension) != 2:
+                        raise NotImplementedError("levels are joined along channels (JoinTable(2), model_utils.lua:237)")
+                elif b == "MulConstant" and not mix_seen:
+                    post *= float(m.constant_scalar)
+                elif b in ("SpatialConvolution", "SpatialConvolutionMM") and not mix_seen:
+                    if len(set(shapes)) != 1 or len(set(norms)) != 1:
+                        raise NotImplementedError("levels pooled to different sizes / mixed normalisation")
+                    chans = [tb.shape[s][0] for s, _sc in levels]
+                    lb = _Layers(add, arrays, sum(chans), (shapes[0][1], shapes[0][0]))
+                    v = lb.run(m, 0)
+                    col = np.concatenate([np.full(c, f, np.float64) for c, f in zip(chans, factors)])
+                    col *= post / 1000.0 if norms[0] else post   # the kernel applies Normalize + MulConstant(1000) itself
+                    if not np.all(col == 1.0):
+                        L = lb.layers[0]
+                        arrays[L.weight] = _f32(arrays[L.weight].astype(np.float64) * col.reshape(1, -1, 1, 1))
+                    mix_seen = True
+                elif b in _PASS:
+                    continue
+                else:
+                    raise NotImplementedError(f"conv345Combine module {m.typename}")
+            if not mix_seen:
+                raise NotImplementedError("tower without conv_mix (model_utils.lua:242)")
+            for m in kids[2:]:
+                v = lb.run(m, v)
+            c, h, w = lb.shape[v]
+            if h * w > 1:
+                raise NotImplementedError("tower output is not a vector")
+            towers.append(Tower(region=region, levels=levels, pooled_w=shapes[0][0], pooled_h=shapes[0][1],
+                                normalize=1 if norms[0] else 0, layers=lb.layers, out_slot=v))
+            widths.append(c)
+        i = 2
+    else:
+        raise NotImplementedError("expected inn.ROIPooling or the foveal ModelParallelTable after the trunk")
+
+    total = sum(widths)
+    narrows, cls_heads, bbox_head = None, None, None
+    no_softmax = 1 if model.get("noSoftMax") else 0
+    bbox_mean, bbox_std, has_norm = (0.0, 0.0, 0.0, 0.0), (0.1, 0.1, 0.2, 0.2), 0
+
+    def norm_of(k):
+        return 1, tuple(float(x) for x in np.asarray(k.mean).reshape(-1)[:4]), tuple(float(x) for x in np.asarray(k.std).reshape(-1)[:4])
+
+    for m in rest[i:]:
+        b = _base(m.typename)
+        kids = _children(m)
+        if b == "ConcatTable" and kids and all(_base(k.typename) == "Narrow" for k in kids) and cls_heads is None:
+            if len(kids) != 2 or any(int(k.dimension) != 2 for k in kids):
+                raise NotImplementedError("expected two nn.Narrow(2, ...) column ranges (multipathnet.lua:115)")
+            narrows = [(int(k.index) - 1, int(k.length)) for k in kids]
+            if any(c0 < 0 or c0 + cl > total for c0, cl in narrows):
+                raise ValueError("nn.Narrow reaches past the tower outputs")
+        elif b in ("ConcatTable", "ParallelTable") and cls_heads is None:
+            if b == "ParallelTable" and narrows is None:
+                raise NotImplementedError("ParallelTable heads without the Narrow split before them")
+            cls_heads, bbox_head = _linear_heads(kids, total, add, narrows)
+        elif b == "ModeSwitch" and cls_heads is not None:
+            no_softmax = 1                                       # eval branch = mean of the K softmaxes (model_utils.lua:300-313)
+        elif b == "ParallelTable" and cls_heads is not None:
+            for k in kids:
+                if _base(k.typename) == "BBoxNorm":
+                    has_norm, bbox_mean, bbox_std = norm_of(k)
+        elif b == "BBoxNorm":
+            has_norm, bbox_mean, bbox_std = norm_of(m)
+        elif b in ("SoftMax",) + _PASS:
+            continue
+        else:
+            raise NotImplementedError(f"head module {m.typename}")
+    if cls_heads is None:
+        raise ValueError("no {class, bbox} head found")
+    C = cls_heads[0].cout
+    if any(h.cout != C for h in cls_heads) or bbox_head.cout != 4 * C:
+        raise ValueError("class / bbox head sizes disagree")
+    if num_classes is not None and C != num_classes:
+        raise ValueError(f"class head has {C} outputs, expected {num_classes}")
+    if len(cls_heads) > 1:
+        no_softmax = 1
+    taps = {f"out{k + 1}": s for k, s in enumerate(trunk_vals)}
+    return ModelSpec(name=name, trunk_layers=tb.layers, towers=towers, cls_heads=cls_heads, bbox_head=bbox_head, num_classes=C,
+                     weights=arrays, roi_variant=2, no_softmax=no_softmax, has_bbox_norm=has_norm, bbox_mean=bbox_mean,
+                     bbox_std=bbox_std, transformer=transformer or ("imagenet" if has_res else "ross"), taps=taps)
