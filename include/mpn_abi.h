@@ -165,6 +165,34 @@ void mpn_model_destroy(mpn_model *m);
  * image: 3 x H x W fp32 host (or device with _dev), already transformed+scaled. */
 int mpn_model_trunk(mpn_model *m, const float *image, int32_t H, int32_t W);
 int mpn_model_trunk_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W);
+/* ---- getImages on the device: ImageDetect.lua:22-52 + modules/ImageTransformer.lua:19-33 ----------
+ * fbcoco.ImageTransformer(mean, std, scale, swap) as plain data: out[c] = (im[swap[c]] * scale - mean[c]) / std[c],
+ * each step fp32 in that order, `* scale` skipped when scale == 1, `/ std` when has_std == 0 (RossTransformer:
+ * swap {3,2,1}, scale 255, Ross' BGR means, no std; ImagenetTransformer: swap {1,2,3}, scale 1, mean + std;
+ * model_utils.lua:138-155).                                                                                  */
+typedef struct mpn_image_transform {
+  int32_t swap[3];   /* 1-based source channel of each output channel */
+  float scale;
+  float mean[3];
+  float std[3];
+  int32_t has_std;
+} mpn_image_transform;
+/* host-only (no GPU): the size getImages scales a H0 x W0 image to for the single test scale (`scale`, `max_size` as
+ * ImageDetect.lua:17-18) and the im_scale it returns: im_scale = scale / min side, capped so that
+ * round(im_scale * max side) <= max_size; h = trunc(H0 * im_scale), w = trunc(W0 * im_scale) (:31-39). */
+int mpn_get_images_size(int32_t H0, int32_t W0, double scale, double max_size, int32_t *h, int32_t *w, double *im_scale);
+/* transformer + image.scale(im, w, h) ('bilinear', the third-party `image` package: parity unpinned, see
+ * csrc/image_scale.cuh) in one kernel. im: 3 x H0 x W0 fp32 RGB in [0,1] (loaders/loader.lua:79), out: 3 x h x w.
+ * Host buffers, synchronous; _dev: device buffers, stream-ordered. */
+int mpn_get_images(mpn_ctx *ctx, const float *im, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                   int32_t h, int32_t w, float *out);
+int mpn_get_images_dev(mpn_ctx *ctx, const float *im_dev, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                       int32_t h, int32_t w, float *out_dev);
+/* getImages + model:get(1):forward: uploads the RAW image (host), transforms and scales it on the device into the
+ * model's image buffer and runs the trunk; *im_scale, *h, *w as mpn_get_images_size. Follow with mpn_model_detect(...,
+ * image = NULL, recompute_features = 0) on the cached features. */
+int mpn_model_trunk_image(mpn_model *m, const float *im, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                          double scale, double max_size, double *im_scale, int32_t *h, int32_t *w);
 /* modules 2..n on cached trunk features (recompute_features=false path,
  * ImageDetect.lua:109-124): rois R x 5 in scaled-image coords. Outputs are the
  * RAW network outputs: cls R x C (logits, or probabilities if no_softmax) and

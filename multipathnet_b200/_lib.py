@@ -43,6 +43,23 @@ class CHead(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("col_begin", "col_len", "cout", "weight", "bias")]
 
 
+class CImageTransform(C.Structure):
+    """mpn_image_transform: fbcoco.ImageTransformer(mean, std, scale, swap) as plain data"""
+    _fields_ = [("swap", C.c_int32 * 3), ("scale", C.c_float), ("mean", C.c_float * 3), ("std", C.c_float * 3), ("has_std", C.c_int32)]
+
+    @staticmethod
+    def of(kind: str) -> "CImageTransform":
+        from . import workloads as wl
+        t = CImageTransform()
+        if kind == "ross":                                   # utils.RossTransformer, model_utils.lua:138-140
+            t.swap[:] = [3, 2, 1]; t.scale = 255.0; t.mean[:] = wl.ROSS_MEAN; t.std[:] = [1, 1, 1]; t.has_std = 0
+        elif kind == "imagenet":                             # utils.ImagenetTransformer, model_utils.lua:143-155
+            t.swap[:] = [1, 2, 3]; t.scale = 1.0; t.mean[:] = wl.IMAGENET_MEAN; t.std[:] = wl.IMAGENET_STD; t.has_std = 1
+        else:
+            raise ValueError(f"unknown transformer {kind!r}")
+        return t
+
+
 class CModelDesc(C.Structure):
     _fields_ = [("n_trunk_layers", C.c_int32), ("trunk_layers", C.POINTER(CLayer)),
                 ("n_towers", C.c_int32), ("towers", C.POINTER(CTower)),
@@ -84,6 +101,10 @@ SIGNATURES = {
                                C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp]),
     "mpn_roi_pool_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64,
                                    C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp]),
+    "mpn_get_images_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, _i32p, _i32p, C.POINTER(C.c_double)]),
+    "mpn_get_images": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
+    "mpn_get_images_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
+    "mpn_model_trunk_image": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, C.POINTER(C.c_double), _i32p, _i32p]),
     "mpn_model_create": (C.c_int, [_vp, C.POINTER(CModelDesc), C.POINTER(_vp), _i64p, C.c_int32, C.POINTER(_vp)]),
     "mpn_model_destroy": (None, [_vp]),
     "mpn_model_trunk": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
@@ -242,6 +263,20 @@ class Context:
         out = np.empty_like(r)
         self.check(self.lib.mpn_context_region(self.h, _ptr(r), r.shape[0], float(scale), _ptr(out)), "mpn_context_region")
         return out
+
+    def get_images(self, im, kind: str, scale: float = 600, max_size: float = 1000):
+        """getImages on the device (ImageDetect.lua:22-52): raw 3 x H0 x W0 image -> (transformed + scaled image, im_scale)"""
+        im = _f32(im)
+        if im.ndim != 3 or im.shape[0] != 3:
+            raise ValueError("ImageTransformer expects a 3 x H x W image")
+        h, w, s = C.c_int32(), C.c_int32(), C.c_double()
+        self.check(self.lib.mpn_get_images_size(im.shape[1], im.shape[2], float(scale), float(max_size), C.byref(h), C.byref(w), C.byref(s)),
+                   "mpn_get_images_size")
+        out = np.empty((3, h.value, w.value), np.float32)
+        tf = CImageTransform.of(kind)
+        self.check(self.lib.mpn_get_images(self.h, _ptr(im), im.shape[1], im.shape[2], C.addressof(tf), h.value, w.value, _ptr(out)),
+                   "mpn_get_images")
+        return out, float(s.value)
 
     def bbox_norm(self, deltas, mean, std) -> np.ndarray:
         d = _f32(deltas).copy()
@@ -433,6 +468,17 @@ class Model:
         im = _f32(image_chw)
         assert im.ndim == 3 and im.shape[0] == 3
         self.ctx.check(self.ctx.lib.mpn_model_trunk(self.h, _ptr(im), im.shape[1], im.shape[2]), "mpn_model_trunk")
+
+    def trunk_image(self, raw_image_chw, kind: str, scale: float = 600, max_size: float = 1000):
+        """getImages + trunk on the device from the RAW image -> (im_scale, h, w)"""
+        im = _f32(raw_image_chw)
+        if im.ndim != 3 or im.shape[0] != 3:
+            raise ValueError("ImageTransformer expects a 3 x H x W image")
+        h, w, s = C.c_int32(), C.c_int32(), C.c_double()
+        tf = CImageTransform.of(kind)
+        self.ctx.check(self.ctx.lib.mpn_model_trunk_image(self.h, _ptr(im), im.shape[1], im.shape[2], C.addressof(tf), float(scale),
+                                                          float(max_size), C.byref(s), C.byref(h), C.byref(w)), "mpn_model_trunk_image")
+        return float(s.value), h.value, w.value
 
     def heads(self, rois):
         r = _f32(rois)

@@ -11,6 +11,8 @@ int mpn_nms_dense_launch(mpn_ctx *, const float *, int, float, int32_t *, int32_
 int mpn_bbox_vote_launch(mpn_ctx *, const float *, int, const float *, int, float, float *);
 int mpn_foveal_launch(mpn_ctx *, const float *, int64_t, float *);
 int mpn_context_region_launch(mpn_ctx *, const float *, int64_t, float, float *);
+int mpn_get_images_launch(mpn_ctx *, const float *, int32_t, int32_t, const mpn_image_transform *, int32_t, int32_t, float *);
+int mpn_get_images_size_impl(int32_t, int32_t, double, double, int32_t *, int32_t *, double *);
 int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
 int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
 int mpn_split_rows_launch(mpn_ctx *, const float *, int64_t, int64_t, int64_t, __nv_bfloat16 *, __nv_bfloat16 *, int64_t);
@@ -289,6 +291,32 @@ static int foveal_adapter(mpn_ctx *c, const float *i, int64_t R, float, float *o
 int mpn_foveal(mpn_ctx *ctx, const float *rois, int64_t R, float *out) { return unary_rois(ctx, rois, R, 4, out, foveal_adapter, 0.f); }
 int mpn_context_region(mpn_ctx *ctx, const float *rois, int64_t R, float scale, float *out) {
   return unary_rois(ctx, rois, R, 1, out, mpn_context_region_launch, scale);
+}
+
+// ------------------------------------------------------------------ getImages
+int mpn_get_images_size(int32_t H0, int32_t W0, double scale, double max_size, int32_t *h, int32_t *w, double *im_scale) {
+  return mpn_get_images_size_impl(H0, W0, scale, max_size, h, w, im_scale);
+}
+int mpn_get_images_dev(mpn_ctx *ctx, const float *im_dev, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                       int32_t h, int32_t w, float *out_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  return mpn_get_images_launch(ctx, im_dev, H0, W0, tf, h, w, out_dev);
+}
+int mpn_get_images(mpn_ctx *ctx, const float *im, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                   int32_t h, int32_t w, float *out) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, im && out && tf && H0 > 0 && W0 > 0 && h > 0 && w > 0, "getImages: buffers missing or bad sizes");
+  Arena a{ctx};
+  const size_t bi = sizeof(float) * 3 * (size_t)H0 * W0, bo = sizeof(float) * 3 * (size_t)h * w;
+  size_t o_i = a.reserve(bi), o_o = a.reserve(bo);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_i), im, bi, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_get_images_launch(ctx, a.at<float>(o_i), H0, W0, tf, h, w, a.at<float>(o_o)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, a.at<float>(o_o), bo, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
 }
 
 int mpn_bbox_norm(mpn_ctx *ctx, float *deltas, int64_t R, int64_t C4, const float *mean4, const float *std4) {

@@ -21,6 +21,8 @@ int mpn_avgpool_launch(mpn_ctx *, const DTensor &, DTensor &);
 int mpn_weight_permute_split_launch(mpn_ctx *, const float *, int64_t, int, int, int, __nv_bfloat16 *, __nv_bfloat16 *);
 int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
 int mpn_project_rois_launch(mpn_ctx *, const float *, int64_t, float, float *);
+int mpn_get_images_launch(mpn_ctx *, const float *, int32_t, int32_t, const mpn_image_transform *, int32_t, int32_t, float *);
+int mpn_get_images_size_impl(int32_t, int32_t, double, double, int32_t *, int32_t *, double *);
 int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
 int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
 int mpn_softmax_mean_launch(mpn_ctx *, const float *, int64_t, int, int, int, float *);
@@ -93,7 +95,7 @@ struct mpn_model {
   int tH = 0, tW = 0; bool trunk_valid = false;
   std::vector<LayerExec> trunk_exec;
   std::map<int, DTensor> trunk_slots; std::map<int, std::unique_ptr<SplitBuf>> trunk_bufs;
-  DevBuf image_dev;
+  DevBuf image_dev, raw_image_dev;
   int merged_w = -1, merged_b = -1;   // weight-table entries of the concatenated head weights / biases (plan_heads)
   std::set<int> elided_slots;      // conv outputs the last trunk forward did not materialise (conv+pool fusion)
   double trunk_flops = 0, head_flops = 0;
@@ -648,6 +650,28 @@ int mpn_model_trunk(mpn_model *m, const float *image, int32_t H, int32_t W) {
   MPN_CUDA(ctx, cudaMemcpyAsync(m->image_dev.p, image, bytes, cudaMemcpyHostToDevice, ctx->stream));
   MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, H, W));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_model_trunk_image(mpn_model *m, const float *im, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                          double scale, double max_size, double *im_scale, int32_t *h_out, int32_t *w_out) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, im && tf && H0 > 0 && W0 > 0, "image or transformer missing");
+  int32_t h = 0, w = 0; double s = 0;
+  MPN_CHECK_ARG(ctx, mpn_get_images_size_impl(H0, W0, scale, max_size, &h, &w, &s) == MPN_OK && h > 0 && w > 0, "bad scale / max_size");
+  MPN_CHECK_ARG(ctx, h <= m->d.max_h && w <= m->d.max_w, "scaled image larger than max_h x max_w");
+  const size_t braw = sizeof(float) * 3 * (size_t)H0 * W0, bimg = sizeof(float) * 3 * (size_t)h * w;
+  MPN_TRY(m->raw_image_dev.ensure(ctx, braw));
+  MPN_TRY(m->image_dev.ensure(ctx, bimg));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->raw_image_dev.p, im, braw, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_get_images_launch(ctx, (const float *)m->raw_image_dev.p, H0, W0, tf, h, w, (float *)m->image_dev.p));
+  MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, h, w));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (im_scale) *im_scale = s;
+  if (h_out) *h_out = h;
+  if (w_out) *w_out = w;
   return MPN_OK;
 }
 

@@ -1,0 +1,49 @@
+// getImages on the device: ImageTransformer + image.scale fused into one HBM-bound kernel.
+// Reference: ImageDetect.lua:22-52, modules/ImageTransformer.lua:19-33; the arithmetic lives in image_scale.cuh
+// (shared with the CPU suite). One thread per output pixel of the 3 x h x w scaled image, x fastest so the store is
+// coalesced; the 4 .. (f+2)^2 source reads of neighbouring threads overlap and are served by L1 / L2 (the raw image is
+// a few MB, far below the 126 MB L2). Algorithmic bytes: 3*H0*W0*4 read + 3*h*w*4 written.
+#include "common.cuh"
+#include "image_scale.cuh"
+
+__global__ void __launch_bounds__(256) get_images_kernel(mpn_img::TransformedImage I, int h, int w, float *__restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int c = blockIdx.z;
+  if (x >= w) return;
+  out[((int64_t)c * h + y) * w + x] = mpn_img::scaled_pixel(I, h, w, c, y, x);
+}
+
+// ImageDetect.lua:31-39: im_scale = scale / min(H0, W0), capped so that round(im_scale * max(H0, W0)) <= max_size;
+// image.scale receives H0*im_scale, W0*im_scale as Lua numbers and allocates the result with them truncated to long.
+int mpn_get_images_size_impl(int32_t H0, int32_t W0, double scale, double max_size, int32_t *h, int32_t *w, double *im_scale) {
+  if (H0 <= 0 || W0 <= 0 || !(scale > 0) || !(max_size > 0)) return MPN_ERR_ARG;
+  const double smin = H0 < W0 ? H0 : W0, smax = H0 < W0 ? W0 : H0;
+  double s = scale / smin;
+  if (floor(s * smax + 0.5) > max_size) s = max_size / smax;    // torch.round: half away from zero (positive here)
+  if (h) *h = (int32_t)(long)((double)H0 * s);
+  if (w) *w = (int32_t)(long)((double)W0 * s);
+  if (im_scale) *im_scale = s;
+  return MPN_OK;
+}
+
+int mpn_get_images_launch(mpn_ctx *ctx, const float *im_dev, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                          int32_t h, int32_t w, float *out_dev) {
+  MPN_CHECK_ARG(ctx, im_dev && out_dev && tf, "getImages: buffers missing");
+  MPN_CHECK_ARG(ctx, H0 > 0 && W0 > 0 && h > 0 && w > 0 && h <= 65535, "getImages: bad sizes");
+  mpn_img::TransformedImage I;
+  I.im = im_dev; I.H0 = H0; I.W0 = W0;
+  for (int c = 0; c < 3; ++c) {
+    MPN_CHECK_ARG(ctx, tf->swap[c] >= 1 && tf->swap[c] <= 3, "ImageTransformer: swap entries are 1-based channel numbers");
+    I.t.src_chan[c] = tf->swap[c] - 1;
+    I.t.neg_mean[c] = (float)(-(double)tf->mean[c]);
+    I.t.std[c] = tf->std[c];
+  }
+  I.t.has_scale = tf->scale != 1.0f;
+  I.t.scale = tf->scale;
+  I.t.has_std = tf->has_std != 0;
+  dim3 grid((unsigned)((w + 255) / 256), (unsigned)h, 3);
+  get_images_kernel<<<grid, 256, 0, ctx->stream>>>(I, h, w, out_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}

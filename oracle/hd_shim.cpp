@@ -1,0 +1,22 @@
+// TEST INFRASTRUCTURE: host build of the product's __host__ __device__ getImages arithmetic
+// (multipathnet_b200/csrc/image_scale.cuh), so the CPU suite can run exactly what get_images_kernel runs per pixel and
+// compare it with the independent two-pass restatement orc_image_scale. Built with -ffp-contract=off (the device side
+// uses *_rn intrinsics). Not linked into the product.
+#include "../multipathnet_b200/csrc/image_scale.cuh"
+
+extern "C" void hd_get_images(const float *im, int H0, int W0, const int *swap /* 1-based */, float scale, const float *mean,
+                              const float *std /* or NULL */, int h, int w, float *out) {
+  mpn_img::TransformedImage I;
+  I.im = im; I.H0 = H0; I.W0 = W0;
+  for (int c = 0; c < 3; ++c) {
+    I.t.src_chan[c] = swap[c] - 1;
+    I.t.neg_mean[c] = (float)(-(double)mean[c]);
+    I.t.std[c] = std ? std[c] : 1.0f;
+  }
+  I.t.has_scale = scale != 1.0f;
+  I.t.scale = scale;
+  I.t.has_std = std != nullptr;
+  for (int c = 0; c < 3; ++c)
+    for (int y = 0; y < h; ++y)
+      for (int x = 0; x < w; ++x) out[((long)c * h + y) * w + x] = mpn_img::scaled_pixel(I, h, w, c, y, x);
+}

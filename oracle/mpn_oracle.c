@@ -19,6 +19,10 @@
  *       UNPINNED version, source absent from /root/reference). "parity unpinned":
  *       the reference's only test of it (modules/test.lua:60-83) pins
  *       chunk-invariance, not values. Both known variants are implemented.
+ *   orc_image_transform : ImageTransformer.lua:19-33 line by line; unpinned (no reference test).
+ *   orc_image_scale / orc_get_images_size : restate `image.scale` ('bilinear') of the
+ *       third-party torch `image` package (luarocks scm, UNPINNED, source absent from
+ *       /root/reference) from generic/image.c as recalled => "parity unpinned".
  * ==========================================================================*/
 #include <math.h>
 #include <float.h>
@@ -295,4 +299,90 @@ long orc_pool_out(long in, int k, int s, int p, int ceil_mode) {
   long o = ceil_mode ? (long)ceilf((float)(in + 2 * p - k) / s) + 1 : (long)floorf((float)(in + 2 * p - k) / s) + 1;
   if (ceil_mode && (o - 1) * s >= in + p) --o;
   return o;
+}
+
+
+/* ---- getImages ------------------------------------------------
+ * ImageTransformer:updateOutput, modules/ImageTransformer.lua:19-33: index by swap (1-based), mul(scale) when
+ * scale ~= 1, add(-mean[i]), div(std[i]) when std — each a separate fp32 tensor op. */
+void orc_image_transform(const float *im, long H, long W, const int *swap /* 1-based, or NULL */, float scale,
+                         const float *mean, const float *std /* or NULL */, float *out) {
+  long n = H * W;
+  for (int c = 0; c < 3; ++c) {
+    const float *src = im + (long)(swap ? swap[c] - 1 : c) * n;
+    float *dst = out + (long)c * n;
+    for (long i = 0; i < n; ++i) dst[i] = src[i];
+  }
+  if (scale != 1.0f)
+    for (long i = 0; i < 3 * n; ++i) out[i] = out[i] * scale;
+  for (int c = 0; c < 3; ++c) {
+    float *dst = out + (long)c * n;
+    float nm = (float)(-(double)mean[c]);
+    for (long i = 0; i < n; ++i) dst[i] = dst[i] + nm;
+    if (std)
+      for (long i = 0; i < n; ++i) dst[i] = dst[i] / std[c];
+  }
+}
+
+/* ImageDetect.lua:31-39 (single scale): im_scale and the size image.scale allocates (Lua numbers truncated to long) */
+void orc_get_images_size(long H0, long W0, double scale, double max_size, long *h, long *w, double *im_scale) {
+  double smin = H0 < W0 ? (double)H0 : (double)W0, smax = H0 < W0 ? (double)W0 : (double)H0;
+  double s = scale / smin;
+  if (floor(s * smax + 0.5) > max_size) s = max_size / smax;      /* torch.round */
+  *h = (long)((double)H0 * s);
+  *w = (long)((double)W0 * s);
+  *im_scale = s;
+}
+
+/* one row or column, torch image generic/image.c scaleLinear_rowcol as recalled: strided in, strided out, the
+ * shrinking branch carries its window state from one output sample to the next */
+static void orc_scale_rowcol(const float *src, long src_stride, long src_len, float *dst, long dst_stride, long dst_len) {
+  if (dst_len > src_len) {
+    if (src_len == 1) {
+      for (long di = 0; di < dst_len; ++di) dst[di * dst_stride] = src[0];
+      return;
+    }
+    float scale = (float)(src_len - 1) / (float)(dst_len - 1);
+    for (long di = 0; di < dst_len - 1; ++di) {
+      float si_f = (float)di * scale;
+      long si_i = (long)si_f;
+      si_f -= (float)si_i;
+      dst[di * dst_stride] = (1 - si_f) * src[si_i * src_stride] + si_f * src[(si_i + 1) * src_stride];
+    }
+    dst[(dst_len - 1) * dst_stride] = src[(src_len - 1) * src_stride];
+  } else if (dst_len < src_len) {
+    long si0_i = 0;
+    float si0_f = 0;
+    float scale = (float)src_len / (float)dst_len;
+    for (long di = 0; di < dst_len; ++di) {
+      float si1_f = (float)(di + 1) * scale;
+      long si1_i = (long)si1_f;
+      si1_f -= (float)si1_i;
+      float acc = (1 - si0_f) * src[si0_i * src_stride];
+      float n = 1 - si0_f;
+      for (long si = si0_i + 1; si < si1_i; ++si) {
+        acc += src[si * src_stride];
+        n += 1;
+      }
+      if (si1_i < src_len) {
+        acc += si1_f * src[si1_i * src_stride];
+        n += si1_f;
+      }
+      dst[di * dst_stride] = acc / n;
+      si0_i = si1_i;
+      si0_f = si1_f;
+    }
+  } else {
+    for (long di = 0; di < dst_len; ++di) dst[di * dst_stride] = src[di * src_stride];
+  }
+}
+
+/* image.scale(src, w, h) 'bilinear' (scaleBilinear): rows to the new width into a temporary, then its columns */
+void orc_image_scale(const float *src, long C, long H, long W, float *dst, long h, long w) {
+  float *tmp = (float *)malloc(sizeof(float) * (size_t)(H * w > 0 ? H * w : 1));
+  for (long c = 0; c < C; ++c) {
+    for (long j = 0; j < H; ++j) orc_scale_rowcol(src + (c * H + j) * W, 1, W, tmp + j * w, 1, w);
+    for (long i = 0; i < w; ++i) orc_scale_rowcol(tmp + i, w, H, dst + c * h * w + i, w, h);
+  }
+  free(tmp);
 }

@@ -192,3 +192,63 @@ def roi_pool(fmap, rois, pw, ph, scale, variant=2, with_argmax=False):
 
 def pool_out(n, k, s, p, ceil_mode):
     return int(orc().orc_pool_out(C.c_long(n), C.c_int(k), C.c_int(s), C.c_int(p), C.c_int(ceil_mode)))
+
+
+# ---- getImages: ImageTransformer + image.scale, "parity unpinned" (third-party `image` package) --------
+_HD = os.path.join(_HERE, "libhd_shim.so")
+_hd = None
+_TRANSFORMERS = {  # model_utils.lua:138-155: (mean, std, scale, swap)
+    "ross": ((102.9801, 115.9465, 122.7717), None, 255.0, (3, 2, 1)),
+    "imagenet": ((0.48462227599918, 0.45624044862054, 0.40588363755159),
+                 (0.22889466674951, 0.22446679341259, 0.22495548344775), 1.0, (1, 2, 3)),
+}
+
+
+def transformer_params(kind):
+    return _TRANSFORMERS[kind]
+
+
+def get_images_size(H0, W0, scale, max_size):
+    """ImageDetect.lua:31-39 -> (h, w, im_scale)"""
+    h, w, s = C.c_long(), C.c_long(), C.c_double()
+    orc().orc_get_images_size(C.c_long(H0), C.c_long(W0), C.c_double(scale), C.c_double(max_size), C.byref(h), C.byref(w), C.byref(s))
+    return int(h.value), int(w.value), float(s.value)
+
+
+def image_transform(im, kind):
+    im = _f(im)
+    mean, std, scale, swap = _TRANSFORMERS[kind]
+    out = np.empty_like(im)
+    m = _f(mean); sd = _f(std) if std is not None else None
+    sw = (C.c_int * 3)(*swap)
+    orc().orc_image_transform(_p(im), C.c_long(im.shape[1]), C.c_long(im.shape[2]), sw, C.c_float(scale), _p(m),
+                              _p(sd) if sd is not None else None, _p(out))
+    return out
+
+
+def image_scale(im, h, w):
+    """image.scale(im, w, h), 'bilinear': two passes with an fp32 temporary, as the original"""
+    im = _f(im)
+    out = np.empty((im.shape[0], h, w), np.float32)
+    orc().orc_image_scale(_p(im), C.c_long(im.shape[0]), C.c_long(im.shape[1]), C.c_long(im.shape[2]), _p(out), C.c_long(h), C.c_long(w))
+    return out
+
+
+def get_images(im, kind, scale=600, max_size=1000):
+    """getImages for the single test scale -> (3 x h x w image, im_scale)"""
+    h, w, s = get_images_size(im.shape[1], im.shape[2], scale, max_size)
+    return image_scale(image_transform(im, kind), h, w), s
+
+
+def hd_get_images(im, kind, h, w):
+    """the product's per-pixel __host__ __device__ arithmetic (csrc/image_scale.cuh), run on the host"""
+    global _hd
+    if _hd is None:
+        _hd = _load(_HD)
+    im = _f(im)
+    mean, std, scale, swap = _TRANSFORMERS[kind]
+    m = _f(mean); sd = _f(std) if std is not None else None
+    out = np.empty((3, h, w), np.float32)
+    _hd.hd_get_images(_p(im), C.c_int(im.shape[1]), C.c_int(im.shape[2]), (C.c_int * 3)(*swap), C.c_float(scale), _p(m),
+                      _p(sd) if sd is not None else None, C.c_int(h), C.c_int(w), _p(out))
+    return out

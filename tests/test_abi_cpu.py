@@ -9,7 +9,7 @@ import pytest
 
 import multipathnet_b200 as mpn
 from multipathnet_b200 import _lib, models, workloads as wl
-from multipathnet_b200.image_detect import ImageDetect, _bilinear_resize
+from multipathnet_b200.image_detect import ImageDetect, _image_scale
 from multipathnet_b200.modules import ImageTransformer
 
 
@@ -49,6 +49,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.CLayer) == 14 * 4
     assert ctypes.sizeof(_lib.CHead) == 5 * 4
     assert ctypes.sizeof(_lib.CTower) == 4 * (2 + 3 + 3 + 6)
+    assert ctypes.sizeof(_lib.CImageTransform) == 4 * (3 + 1 + 3 + 3 + 1)
 
 
 def test_vgg16_flops_match_survey():
@@ -117,11 +118,11 @@ def test_image_detect_scaling_rules():
         ImageDetect(_FakeModel(), ImageTransformer(), [480, 600])
 
 
-def test_bilinear_identity_and_constant():
+def test_image_scale_identity_and_constant():
     im = wl.raw_image(7, 9, 3)
-    assert _bilinear_resize(im, 7, 9) is im
+    assert np.array_equal(_image_scale(im, 7, 9), im)
     c = np.full((3, 5, 5), 2.5, np.float32)
-    assert np.allclose(_bilinear_resize(c, 11, 13), 2.5)
+    assert np.allclose(_image_scale(c, 11, 13), 2.5) and np.allclose(_image_scale(c, 2, 3), 2.5)
 
 
 def test_cfg1_alexnet_cpu_plumbing(oracle_built):
