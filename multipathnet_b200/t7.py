@@ -827,3 +827,124 @@ def model_from_t7(model, name: str = "t7", transformer: str = None, num_classes:
     return ModelSpec(name=name, trunk_layers=tb.layers, towers=towers, cls_heads=cls_heads, bbox_head=bbox_head, num_classes=C,
                      weights=arrays, roi_variant=2, no_softmax=no_softmax, has_bbox_norm=has_norm, bbox_mean=bbox_mean,
                      bbox_std=bbox_std, transformer=transformer or ("imagenet" if has_res else "ross"), taps=taps)
+
+
+# --------------------------------------------------------------------------------- ModelSpec -> nn graph (export)
+def _m(name, **fields):
+    return T7Object(name, fields)
+
+
+def _seq_of(mods):
+    return _m("nn.Sequential", modules=list(mods))
+
+
+def _layers_to_modules(layers, weights, in_slot, out_slot):
+    """A straight chain of Layer records (no residuals) -> nn modules, in order."""
+    from ._lib import MPN_LAYER_AVGPOOL, MPN_LAYER_CONV, MPN_LAYER_FLATTEN, MPN_LAYER_MAXPOOL
+    mods, cur, flat = [], in_slot, False
+    for L in layers:
+        if L.in_slot != cur or L.residual_slot >= 0 or getattr(L, "groups", 1) != 1:
+            raise NotImplementedError("only straight chains of layers can be exported")
+        if L.kind == MPN_LAYER_CONV and not flat:
+            mods.append(_m("cudnn.SpatialConvolution", nInputPlane=L.cin, nOutputPlane=L.cout, kW=L.kw, kH=L.kh, dW=L.stride, dH=L.stride,
+                           padW=L.pad, padH=L.pad, groups=1, weight=_f32(weights[L.weight]).reshape(L.cout, L.cin, L.kh, L.kw),
+                           bias=_f32(weights[L.bias]).reshape(L.cout)))
+        elif L.kind == MPN_LAYER_CONV:
+            mods.append(_m("nn.Linear", weight=_f32(weights[L.weight]).reshape(L.cout, L.cin), bias=_f32(weights[L.bias]).reshape(L.cout)))
+        elif L.kind == MPN_LAYER_MAXPOOL:
+            mods.append(_m("cudnn.SpatialMaxPooling", kW=L.kw, kH=L.kh, dW=L.stride, dH=L.stride, padW=L.pad, padH=L.pad, ceil_mode=bool(L.ceil_mode)))
+        elif L.kind == MPN_LAYER_FLATTEN:
+            mods.append(_m("nn.View", size=[-1], numInputDims=3))
+            flat = True
+        elif L.kind == MPN_LAYER_AVGPOOL:
+            raise NotImplementedError("global average pool needs the pooled size: export ResNet graphs from Torch instead")
+        else:
+            raise NotImplementedError(f"layer kind {L.kind}")
+        if L.kind == MPN_LAYER_CONV and L.relu:
+            mods.append(_m("cudnn.ReLU", inplace=True))
+        cur = L.out_slot
+    if cur != out_slot:
+        raise ValueError("layer chain does not end at the requested slot")
+    return mods
+
+
+def model_to_t7(spec):
+    """ModelSpec -> the nn graph models/vgg.lua:23-31 (one tower, one trunk tap) or models/multipathnet.lua:30-121
+    (skip trunk {conv5, conv4, conv3}, foveal towers, Narrow split) would build around the same weights, as T7Objects
+    ready for `save`. The inverse of `model_from_t7` for straight-chain trunks (VGG-style); residual trunks are not
+    exported. Lets weights produced or converted here go back to Torch, and gives the importer a full-depth round trip."""
+    trunk = list(spec.trunk_layers)
+    ident = lambda: _m("nn.Identity")
+    par = lambda *ms: _m("nn.ParallelTable", modules=list(ms))
+    cat = lambda *ms: _m("nn.ConcatTable", modules=list(ms))
+
+    def chain(a, b):
+        sel, cur = [], b
+        for L in reversed(trunk):                               # walk back from b to a
+            if L.out_slot == cur:
+                sel.append(L)
+                cur = L.in_slot
+                if cur == a:
+                    break
+        if cur != a:
+            raise NotImplementedError("trunk taps are not on one chain")
+        return _layers_to_modules(list(reversed(sel)), spec.weights, a, b)
+
+    tap_slots = []
+    for t in spec.towers:
+        for s, _sc in t.levels:
+            if s not in tap_slots:
+                tap_slots.append(s)
+    order = {L.out_slot: i for i, L in enumerate(trunk)}
+    tap_slots.sort(key=lambda s: -order[s])                      # deepest first: {conv5, conv4, conv3}
+    heads_tail = []
+    C = spec.num_classes
+    lin = lambda h: _m("nn.Linear", weight=_f32(spec.weights[h.weight]).reshape(h.cout, h.col_len), bias=_f32(spec.weights[h.bias]).reshape(h.cout))
+    cls_m = cat(*[lin(h) for h in spec.cls_heads]) if len(spec.cls_heads) > 1 else lin(spec.cls_heads[0])
+    if len(spec.towers) == 1 and len(spec.towers[0].levels) == 1 and not spec.towers[0].normalize:
+        t = spec.towers[0]
+        model = _seq_of([par(_seq_of(chain(0, tap_slots[0])), ident()),
+                         _m("inn.ROIPooling", W=t.pooled_w, H=t.pooled_h, spatial_scale=float(t.levels[0][1]), v2=True)]
+                        + _layers_to_modules(t.layers, spec.weights, 0, t.out_slot) + [cat(cls_m, lin(spec.bbox_head))])
+    else:
+        if len(tap_slots) != 3:
+            raise NotImplementedError("expected the three skip taps of multipathnet.lua")
+        c5, c4, c3 = tap_slots
+        skip = _seq_of(chain(0, c3) + [cat(_seq_of(chain(c3, c4)), ident()), par(cat(_seq_of(chain(c4, c5)), ident()), ident()),
+                                       _m("nn.FlattenTable")])
+        model = _seq_of([par(_m("nn.NoBackprop", modules=[skip]), ident()),
+                         par(ident(), _seq_of([_m("nn.Foveal"), _m("nn.View", size=[-1, 4, 5]), _m("nn.Transpose", permutations=[[1, 2]])]))])
+        regions = _m("nn.ModelParallelTable", dimension=2, modules=[], gpuAssignments=[])
+        nchan = {s: next(L.cout for L in trunk if L.out_slot == s) for s in tap_slots}
+        for t in spec.towers:
+            pools = []
+            for s, sc in t.levels:
+                p = [par(_m("nn.SelectTable", index=tap_slots.index(s) + 1), ident()),
+                     _m("inn.ROIPooling", W=t.pooled_w, H=t.pooled_h, spatial_scale=float(sc), v2=True)]
+                if t.normalize:
+                    n = nchan[s]
+                    p += [_m("nn.View", size=[-1, n * t.pooled_w * t.pooled_h]), _m("nn.Normalize", p=2, eps=1e-10), _m("nn.Contiguous"),
+                          _m("nn.View", size=[-1, n, t.pooled_h, t.pooled_w])]
+                pools.append(_seq_of(p))
+            join = [cat(*pools), _m("nn.JoinTable", dimension=2)] + ([_m("nn.MulConstant", constant_scalar=1000)] if t.normalize else [])
+            rest = _layers_to_modules(t.layers, spec.weights, 0, t.out_slot)          # conv_mix, View, classifier
+            nmix = 1 + (1 if rest[1].typename == "cudnn.ReLU" else 0)
+            regions.fields["modules"].append(_seq_of([par(ident(), _m("nn.Select", dimension=1, index=t.region + 1)),
+                                                      _seq_of(join + rest[:nmix + 1]), _seq_of(rest[nmix + 1:])]))
+        model.fields["modules"].append(regions)
+        hb, hc = spec.bbox_head, spec.cls_heads[0]
+        model.fields["modules"].append(cat(_m("nn.Narrow", dimension=2, index=hc.col_begin + 1, length=hc.col_len),
+                                           _m("nn.Narrow", dimension=2, index=hb.col_begin + 1, length=hb.col_len)))
+        model.fields["modules"].append(par(cls_m, lin(hb)))
+    if len(spec.cls_heads) > 1:                                  # model_utils.lua:275-317
+        K = len(spec.cls_heads)
+        sm = par(*[_seq_of([_m("nn.SoftMax"), _m("nn.View", size=[1, -1, C])]) for _ in range(K)])
+        model.fields["modules"].append(_m("nn.ModeSwitch", train=False, modules=[
+            par(_m("nn.SelectTable", index=1), ident()),
+            _seq_of([par(_seq_of([sm, _m("nn.JoinTable", dimension=1), _m("nn.Mean", dimension=1)]), ident())])]))
+        model.fields["noSoftMax"] = True
+    elif spec.no_softmax:
+        model.fields["noSoftMax"] = True
+    if spec.has_bbox_norm:
+        model.fields["modules"].append(par(ident(), _m("nn.BBoxNorm", mean=_f32(spec.bbox_mean).reshape(1, 4), std=_f32(spec.bbox_std).reshape(1, 4))))
+    return model

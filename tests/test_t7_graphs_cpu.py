@@ -249,3 +249,41 @@ def test_graph_importer_refuses_what_it_cannot_represent():
     m3 = _seq(_par(_seq(_pool(), _relu()), _ident()), O("inn.ROIPooling", W=2, H=2, spatial_scale=0.5))
     with pytest.raises(NotImplementedError):                                          # ReLU with no convolution to ride on
         t7.model_from_t7(m3)
+
+
+def _same_spec(a, b):
+    key = lambda L: (L.kind, L.cin, L.cout, L.kh, L.kw, L.stride, L.pad, L.relu, L.ceil_mode, L.residual_slot >= 0)
+    assert [key(L) for L in a.trunk_layers] == [key(L) for L in b.trunk_layers]
+    assert len(a.towers) == len(b.towers)
+    for ta, tb in zip(a.towers, b.towers):
+        assert (ta.region, ta.pooled_w, ta.pooled_h, ta.normalize, [sc for _, sc in ta.levels]) == (tb.region, tb.pooled_w, tb.pooled_h, tb.normalize, [sc for _, sc in tb.levels])
+        assert [key(L) for L in ta.layers] == [key(L) for L in tb.layers]
+        for La, Lb in zip(ta.layers, tb.layers):
+            if La.weight >= 0:
+                assert np.array_equal(a.weights[La.weight].ravel(), b.weights[Lb.weight].ravel()) and np.array_equal(a.weights[La.bias], b.weights[Lb.bias])
+    for La, Lb in zip(a.trunk_layers, b.trunk_layers):
+        if La.weight >= 0:
+            assert np.array_equal(a.weights[La.weight].ravel(), b.weights[Lb.weight].ravel())
+    for ha, hb in zip(list(a.cls_heads) + [a.bbox_head], list(b.cls_heads) + [b.bbox_head]):
+        assert (ha.col_begin, ha.col_len, ha.cout) == (hb.col_begin, hb.col_len, hb.cout) and np.array_equal(a.weights[ha.weight], b.weights[hb.weight])
+    assert (a.num_classes, a.no_softmax, a.has_bbox_norm) == (b.num_classes, b.no_softmax, b.has_bbox_norm)
+    assert np.allclose(a.bbox_std, b.bbox_std) and np.allclose(a.bbox_mean, b.bbox_mean)
+
+
+@pytest.mark.parametrize("which", ["vgg16_fast_rcnn", "vgg16_multipathnet", "vgg16_multipathnet_integral"])
+def test_full_depth_specs_survive_export_save_load_import(oracle_built, which):
+    """the bench's own graphs (full VGG-16 depth, narrow widths): ModelSpec -> nn graph -> .t7 bytes -> nn graph -> ModelSpec,
+    same layers, same taps in {conv5, conv4, conv3} order, same weights; and the two specs give the same forward."""
+    from multipathnet_b200 import models
+    spec = {"vgg16_fast_rcnn": lambda: models.vgg16_fast_rcnn(21, seed=1, width_div=8, fc_dim=64),
+            "vgg16_multipathnet": lambda: models.vgg16_multipathnet(11, seed=2, width_div=8, fc_dim=32),
+            "vgg16_multipathnet_integral": lambda: models.vgg16_multipathnet(11, seed=3, width_div=8, fc_dim=32, integral_k=3)}[which]()
+    back = t7.model_from_t7(_roundtrip(t7.model_to_t7(spec)))
+    _same_spec(back, spec)
+    if which != "vgg16_fast_rcnn":
+        assert [s for s, _ in back.towers[0].levels] == [back.taps["out1"], back.taps["out2"], back.taps["out3"]]
+    rng = np.random.default_rng(4)
+    img, rois = _inputs(rng, 64, 80, 4)
+    ca, ba = G.heads_forward(spec, G.trunk_forward(spec, img), rois)
+    cb, bb = G.heads_forward(back, G.trunk_forward(back, img), rois)
+    assert np.array_equal(ca, cb) and np.array_equal(ba, bb)
