@@ -36,4 +36,13 @@ np.savez_compressed(os.path.join(here, "ops_golden.npz"), rois=rois, foveal=O.fo
                     roi_v2=O.roi_pool(fmap, rois_neg, 7, 7, 1 / 16, 2), roi_v1=O.roi_pool(fmap, rois_neg, 7, 7, 1 / 16, 1),
                     deltas=deltas, boxes=boxes, decoded=O.convert_from(deltas, boxes), dense_sb=dense_sb,
                     dense_pick=O.nms_dense(dense_sb, 0.3))
+
+# getImages: raw image -> transformer -> image.scale, outputs of the two-pass C restatement (parity unpinned)
+g = {}
+for name, (H0, W0, scale, max_size, kind) in {"grow": (20, 30, 33, 1000, "ross"), "shrink": (40, 56, 17, 1000, "imagenet"),
+                                               "capped": (16, 60, 32, 90, "ross"), "same": (24, 32, 24, 1000, "imagenet")}.items():
+    im = wl.raw_image(H0, W0, 900 + H0)
+    out, s = O.get_images(im, kind, scale, max_size)
+    g[name + "_im"], g[name + "_out"], g[name + "_cfg"] = im, out, np.array([scale, max_size, s, kind == "imagenet"], np.float64)
+np.savez_compressed(os.path.join(here, "getimages_golden.npz"), **g)
 print("golden fixtures written")

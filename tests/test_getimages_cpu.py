@@ -5,6 +5,7 @@ __host__ __device__ code (csrc/image_scale.cuh, the body of get_images_kernel) b
 PARITY UNPINNED against Torch's `image` package itself (third-party, absent): hand-computed known answers below pin the
 recalled algorithm (corner-aligned interpolation when growing, area average when shrinking, rows first)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -94,3 +95,19 @@ def test_image_detect_host_and_device_getimages_paths():
     d2.detect(im, boxes)
     d2.detect(None, boxes, recompute_features=False)
     assert m.calls == [("trunk_image", (3, 60, 80), "ross", 75, 100), ("detect", None, 1.25, False), ("detect", None, 1.25, False)]
+
+
+def test_getimages_golden_fixture(oracle_built):
+    """committed outputs (tests/golden/make_golden.py): any later change to the restatement or the mirrors is caught"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "getimages_golden.npz"))
+    for name in ("grow", "shrink", "capped", "same"):
+        im, out = g[name + "_im"], g[name + "_out"]
+        scale, max_size, s, inet = g[name + "_cfg"]
+        kind = "imagenet" if inet else "ross"
+        o, so = oracle_built.get_images(im, kind, scale, max_size)
+        assert so == s and np.array_equal(o, out)
+        d = ImageDetect(_FakeModel(), ImageTransformer(kind), scale=[scale], max_size=max_size)
+        img, sm = d.getImages(im)
+        assert sm == s and np.array_equal(img, out)
+        assert np.array_equal(oracle_built.hd_get_images(im, kind, out.shape[1], out.shape[2]), out)
+    assert g["capped_out"].shape[2] == 90 and g["same_cfg"][2] == 1.0

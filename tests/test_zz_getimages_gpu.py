@@ -5,6 +5,8 @@ is the __host__ __device__ code the CPU suite already checks bit for bit (tests/
 is the launch itself. Until a GPU run has confirmed them these tests are xfail(strict=False): a pass shows as XPASS, a
 failure as XFAIL, neither hides or breaks the verified suite before it (this file sorts last so that even a faulting
 kernel cannot disturb another test). Drop the marker once a round has seen them pass."""
+import os
+
 import numpy as np
 import pytest
 
@@ -24,6 +26,14 @@ def test_get_images_matches_the_oracle_bit_for_bit(ctx, oracle_built, H0, W0, sc
     out, s = ctx.get_images(im, kind, scale, max_size)
     assert s == s_ref and out.shape == ref.shape
     assert np.array_equal(out, ref)
+
+
+def test_get_images_golden_fixture(ctx):
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "getimages_golden.npz"))
+    for name in ("grow", "shrink", "capped", "same"):
+        scale, max_size, s, inet = g[name + "_cfg"]
+        out, so = ctx.get_images(g[name + "_im"], "imagenet" if inet else "ross", scale, max_size)
+        assert so == s and np.array_equal(out, g[name + "_out"])
 
 
 def test_detect_from_the_raw_image_equals_the_host_getimages_path(ctx):
