@@ -68,3 +68,41 @@ function BBoxNorm:clearState()
    nn.utils.clear(self, '_output')
    return bparent.clearState(self)
 end
+
+-- inn.ROIPooling (imagine-nn; vgg.lua:28, model_utils.lua:215) ------------------------------------
+-- forward{data, rois}: data N x C x H x W, rois R x 5 [batch idx (1-based), x1, y1, x2, y2] -> R x C x H x W pooled,
+-- self.indices = argmax (flat index into the H x W map, -1 for an empty bin). Registered under the same class name so
+-- that saved models load; inference only (the reference trains through imagine-nn's own backward).
+if not inn then inn = {} end
+local ROIPooling, rparent = torch.class('inn.ROIPooling', 'nn.Module')
+function ROIPooling:__init(W, H, spatial_scale)
+   rparent.__init(self)
+   assert(W and H, 'W and H have to be provided')
+   self.W, self.H = W, H
+   self.spatial_scale = spatial_scale or 1
+   self.v2 = true                                           -- post-PR-17 end convention (README.md:202-203)
+   self.indices = torch.IntTensor()
+end
+function ROIPooling:setSpatialScale(scale) self.spatial_scale = scale; return self end
+function ROIPooling:updateOutput(input)
+   assert(#input == 2)
+   local data, rois = input[1], input[2]
+   assert(data:nDimension() == 4 and rois:nDimension() == 2 and rois:size(2) == 5)
+   local R, nC = rois:size(1), data:size(2)
+   local out = torch.FloatTensor(R, nC, self.H, self.W)
+   self.indices:resize(R, nC, self.H, self.W)
+   local d, r = data:float():contiguous(), rois:float():contiguous()
+   local ctx = mpn.ctx()
+   mpn.check(ctx, C.mpn_roi_pool(ctx, mpn.fptr(d), d:size(1), nC, d:size(3), d:size(4), mpn.fptr(r), R, self.W, self.H,
+                                 self.spatial_scale, self.v2 and 2 or 1, mpn.fptr(out), ffi.cast('int32_t*', self.indices:data())),
+             'mpn_roi_pool')
+   self.output = self.output:typeAs(data):resize(out:size()):copy(out)
+   return self.output
+end
+function ROIPooling:updateGradInput()
+   error('inn.ROIPooling (B200 shim) is inference-only: train with the reference modules')
+end
+function ROIPooling:clearState()
+   self.indices:set()
+   return rparent.clearState(self)
+end
