@@ -15,7 +15,9 @@ Tables and torch objects are memoised: an int32 index follows the tag, and a rep
   torch : version string "V 1" (int32 length + bytes), class name string, then the class payload:
           torch.*Tensor  : int32 ndim, int64 size[ndim], int64 stride[ndim], int64 storage offset (1-based), storage object
           torch.*Storage : int64 n, then n raw elements
-          anything else (nn modules, ...): one object (a table) whose pairs become the fields.
+          anything else (nn modules, ...): one object (a table) whose pairs become the fields — except classes with
+          their own __write: nn.ModelParallelTable (ModelParallelTable.lua:607-628) and cunn's nn.DataParallelTable
+          write the gpuAssignments table, the branch modules one by one, then the table of the remaining fields.
 """
 from __future__ import annotations
 
@@ -149,13 +151,56 @@ class _Reader:
                 return a
             o = T7Object(cls)
             self.memo[idx] = o
+            ver = int(version[2:]) if version.startswith("V ") and version[2:].strip().isdigit() else 0
+            if cls.split(".")[-1] in _GPU_TABLES and ver >= 2:
+                self._gpu_table(o)
+                return o
             payload = self.obj()
             if isinstance(payload, dict):
                 o.fields.update(payload)
             elif isinstance(payload, list):
                 o.fields.update({i + 1: v for i, v in enumerate(payload)})
+            if cls.endswith(".NoBackprop") and "modules" not in o.fields and "inner" in o.fields:
+                o.fields["modules"] = [o.fields.pop("inner")]            # NoBackprop.lua:34-46, files older than version 2
             return o
         raise ValueError(f"unknown .t7 type tag {t}")
+
+
+_GPU_TABLES = ("ModelParallelTable", "DataParallelTable", "DPParallelTable")
+
+
+def _reader_gpu_table(self, o: T7Object):
+    """Classes with their own __write (version >= 2). The reference's nn.ModelParallelTable writes (ModelParallelTable.lua:
+    607-628, read back at :544-605): the gpuAssignments table, then every branch module as its own object, then a table
+    of the remaining fields (without `modules` / `gpuAssignments`). cunn's nn.DataParallelTable (third-party, not in
+    /root/reference; test_runner.lua:27 sets its `deserializeNGPUs`, the same scheme) writes gpuAssignments, then — depending
+    on its version — the replicas or nothing, then the field table (which holds `modules` itself in newer versions).
+    Both are read as: gpuAssignments, module objects until a plain table arrives, that table."""
+    gpu = self.obj()
+    gpu = [] if isinstance(gpu, dict) and not gpu else gpu
+    if not isinstance(gpu, list):
+        raise ValueError(f"{o.typename}: expected the gpuAssignments table first")
+    mods: List[Any] = []
+    while True:
+        nxt = self.obj()
+        if isinstance(nxt, T7Object) and nxt.typename != "function":
+            mods.append(nxt)
+            if len(mods) > max(len(gpu), 1):
+                raise ValueError(f"{o.typename}: more branch modules than gpuAssignments")
+            continue
+        break
+    if isinstance(nxt, dict):
+        o.fields.update(nxt)
+    elif isinstance(nxt, list):
+        o.fields.update({i + 1: v for i, v in enumerate(nxt)})
+    elif nxt is not None:
+        raise ValueError(f"{o.typename}: expected the field table after the branches")
+    o.fields["gpuAssignments"] = gpu
+    if mods:
+        o.fields["modules"] = mods
+
+
+_Reader._gpu_table = _reader_gpu_table
 
 
 def load(path_or_file) -> Any:
@@ -230,7 +275,17 @@ class _Writer:
             self.i32(TYPE_TORCH)
             if self._index(o):
                 return
-            self.string("V 1"); self.string(o.typename)
+            if o.typename.split(".")[-1] == "ModelParallelTable":           # ModelParallelTable.lua:607-628 (__version = 2)
+                self.string("V 2"); self.string(o.typename)
+                mods = list(o.fields.get("modules") or [])
+                gpu = o.fields.get("gpuAssignments") or list(range(1, len(mods) + 1))
+                self.obj(list(gpu))
+                for m in mods:
+                    self.obj(m)
+                self._table({k: v for k, v in o.fields.items() if k not in ("modules", "gpuAssignments")}, fresh_index=True)
+                return
+            ver = 2 if o.typename.split(".")[-1] == "NoBackprop" else 1     # NoBackprop.lua:33
+            self.string(f"V {ver}"); self.string(o.typename)
             self._table(o.fields, fresh_index=True)
         elif isinstance(o, (list, tuple)):
             self.i32(TYPE_TABLE)

@@ -150,3 +150,82 @@ def test_proposal_file_boxes_are_permuted_like_DataSetJSON():
                                             "images": ["a.jpg", "b.jpg"]}))
     assert np.array_equal(back["boxes"][0], np.array([[20, 10, 40, 30], [2, 1, 4, 3]], np.float32))
     assert back["boxes"][1].shape == (0, 4) and back["images"] == ["a.jpg", "b.jpg"]
+
+
+def test_functions_are_skipped_and_file_paths_work(tmp_path):
+    """multipathnet.lua:123 stores a Lua function in the model (`model.setPhase2 = ...`): torch.save writes its bytecode
+    and upvalue table; the reader skips the bytecode, keeps the upvalues and the memo index (a second reference to the same
+    function is just the index)."""
+    s = lambda x: struct.pack("<i", t7.TYPE_STRING) + struct.pack("<i", len(x)) + x.encode()
+    num = lambda v: struct.pack("<id", t7.TYPE_NUMBER, v)
+    upvals = struct.pack("<iii", t7.TYPE_TABLE, 3, 1) + num(1.0) + s("captured")
+    body = struct.pack("<iii", t7.TYPE_TABLE, 1, 4)
+    body += s("setPhase2") + struct.pack("<iii", t7.TYPE_RECUR_FUNCTION, 2, 5) + b"\x1bLJ\x02\x00" + upvals
+    body += s("again") + struct.pack("<ii", t7.TYPE_RECUR_FUNCTION, 2)
+    body += s("plain") + struct.pack("<ii", t7.TYPE_FUNCTION, 3) + b"abc" + struct.pack("<i", t7.TYPE_NIL)
+    body += s("phase") + num(1.0)
+    p = tmp_path / "m.t7"
+    p.write_bytes(body)
+    back = t7.load(str(p))
+    assert back["phase"] == 1.0 and back["setPhase2"].typename == "function" and back["again"] is back["setPhase2"]
+    assert back["setPhase2"].upvalues == ["captured"] and back["plain"].upvalues is None
+    t7.save(str(p), {"x": np.arange(3, dtype=np.float32)})
+    assert np.array_equal(t7.load(str(p))["x"], [0, 1, 2])
+    with pytest.raises(ValueError):
+        t7.load(io.BytesIO(struct.pack("<i", 42)))
+    with pytest.raises(AttributeError):
+        T7Object("nn.Linear", {}).weight
+    assert "nn.Linear" in repr(T7Object("nn.Linear", {"weight": 1}))
+
+
+def _pack_obj(idx, version, cls, payload):
+    b = struct.pack("<ii", t7.TYPE_TORCH, idx)
+    for s in (version, cls):
+        b += struct.pack("<i", len(s)) + s.encode()
+    return b + payload
+
+
+def _pack_table(idx, pairs):
+    b = struct.pack("<iii", t7.TYPE_TABLE, idx, len(pairs))
+    for k, v in pairs:
+        b += (struct.pack("<id", t7.TYPE_NUMBER, float(k)) if not isinstance(k, str)
+              else struct.pack("<ii", t7.TYPE_STRING, len(k)) + k.encode()) + v
+    return b
+
+
+def test_model_parallel_table_custom_serialisation():
+    """ModelParallelTable.lua:607-628 (__write, __version 2): gpuAssignments, each branch as its own object, then the table of
+    the remaining fields — packed by hand here, independently of this module's writer."""
+    num = lambda v: struct.pack("<id", t7.TYPE_NUMBER, float(v))
+    ident = lambda idx, tidx: _pack_obj(idx, "V 1", "nn.Identity", _pack_table(tidx, []))
+    gpu = _pack_table(2, [(1, num(1)), (2, num(4))])
+    rest = _pack_table(7, [("dimension", num(2)), ("noGradInput", struct.pack("<ii", t7.TYPE_BOOLEAN, 0))])
+    mpt = _pack_obj(1, "V 2", "nn.ModelParallelTable", gpu + ident(3, 4) + ident(5, 6) + rest)
+    o = t7.load(io.BytesIO(mpt))
+    assert o.typename == "nn.ModelParallelTable" and o.dimension == 2.0 and o.noGradInput is False
+    assert o.gpuAssignments == [1.0, 4.0] and [m.typename for m in o.modules] == ["nn.Identity"] * 2
+    back = _roundtrip(o)                                              # this module's writer emits the same layout
+    assert back.gpuAssignments == [1.0, 4.0] and len(back.modules) == 2 and back.dimension == 2.0
+    buf = io.BytesIO(); t7.save(buf, o)
+    assert b"V 2" in buf.getvalue()
+    # a version-1 file holds the plain field table
+    v1 = _pack_obj(1, "V 1", "nn.ModelParallelTable", _pack_table(2, [("dimension", num(2)), ("modules", _pack_table(3, [(1, ident(4, 5))]))]))
+    o1 = t7.load(io.BytesIO(v1))
+    assert o1.dimension == 2.0 and len(o1.modules) == 1
+    # cunn's DataParallelTable (newer layout): gpuAssignments, then the field table that holds `modules` itself
+    dpt = _pack_obj(1, "V 3", "nn.DataParallelTable", _pack_table(2, [(1, num(1))]) + _pack_table(3, [("dimension", num(1)), ("modules", _pack_table(4, [(1, ident(5, 6))]))]))
+    od = t7.load(io.BytesIO(dpt))
+    assert od.gpuAssignments == [1.0] and len(od.modules) == 1 and od.dimension == 1.0
+    # ... and the older one: gpuAssignments, the replicas, the field table
+    dpt2 = _pack_obj(1, "V 2", "nn.DataParallelTable", _pack_table(2, [(1, num(1)), (2, num(2))]) + ident(3, 4) + ident(5, 6) + _pack_table(7, [("dimension", num(1))]))
+    od2 = t7.load(io.BytesIO(dpt2))
+    assert len(od2.modules) == 2 and t7.flatten_sequential(od2)[0].typename == "nn.Identity"
+    with pytest.raises(ValueError):                                   # three branches for two gpuAssignments, no field table
+        t7.load(io.BytesIO(_pack_obj(1, "V 2", "nn.ModelParallelTable", _pack_table(2, [(1, num(1))]) + ident(3, 4) + ident(5, 6) + ident(7, 8))))
+
+
+def test_nobackprop_legacy_inner_field():
+    """NoBackprop.lua:34-46: files older than version 2 keep the wrapped module in `inner`"""
+    inner = _pack_obj(3, "V 1", "nn.Identity", _pack_table(4, []))
+    o = t7.load(io.BytesIO(_pack_obj(1, "V 1", "nn.NoBackprop", _pack_table(2, [("inner", inner)]))))
+    assert [m.typename for m in o.modules] == ["nn.Identity"] and "inner" not in o.fields
