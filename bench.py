@@ -404,7 +404,8 @@ def main():
     roofline = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (tcgen05 bf16x3 implicit-GEMM, %d launches/step)" % n_tc,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "issued_frac": 3.0 * achieved / peak_tf if peak_tf else None, "peak_source": peak_src,
-                "traffic": traffic_from_profiles(args.config),
+                "traffic": (traffic_from_profiles(args.config) or {}).get("dram_bytes_per_launch"),   # bytes, or None
+                "traffic_detail": traffic_from_profiles(args.config),
                 "algorithmic_tflop_per_step": tflop_step, "kernel_ms_per_step": tc_ms_step,
                 "by_category_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     # ROI pooling (HBM-bound secondary kernel): algorithmic bytes = feature map once + rois + pooled output
