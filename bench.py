@@ -173,6 +173,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pick_cpu_threads(torch):
+    """The CPU legs should be the host at its best, and oneDNN / MKL on a many-core box are not fastest with every
+    logical CPU on this batch-1 workload (128 threads were 2x slower than 8 on another host): time a proxy of the two
+    dominant layers (conv3_2, fc6) at a few thread counts and keep the fastest. Returns (threads, {threads: seconds})."""
+    import torch.nn.functional as F
+    n = os.cpu_count() or 1
+    cands = sorted({max(min(n, 4), n >> s) for s in range(4)}, reverse=True)
+    x, w = torch.randn(1, 256, 150, 200), torch.randn(256, 256, 3, 3)
+    a, b = torch.randn(1000, 25088), torch.randn(4096, 25088)
+    tried = {}
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            F.conv2d(x, w, padding=1); F.linear(a[:64], b)                 # primitive creation / first touch
+            t0 = time.perf_counter()
+            F.conv2d(x, w, padding=1); F.linear(a, b)
+            tried[c] = round(time.perf_counter() - t0, 3)
+    best = min(tried, key=tried.get)
+    torch.set_num_threads(best)
+    return best, tried
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the host cores. Torch-7 cannot run
     here, so the nn graph is the oracle port (PyTorch-CPU fp32 + C restatement) and NMS is the LITERAL nms.c."""
@@ -183,8 +205,7 @@ def run_reference(args, rank, world):
     from multipathnet_b200 import models, workloads as wl
     from oracle import graphs as G, ref as O
     O.build()
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores, tried = pick_cpu_threads(torch)
     spec = models.vgg16_fast_rcnn(C, seed=1234)
     use_lit = O.ref_available()
 
@@ -215,7 +236,8 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "steps_timed": len(ts), "warmup_run": 1 if t_first is not None else 0,
             "ms_per_step": 1e3 * total / len(ts), "ms_per_image_p50": 1e3 * statistics.median(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "host": "CPU only", "threads": cores},
+            "config": {"workload": WORKLOAD, "host": "CPU only", "threads": cores, "logical_cpus": os.cpu_count(),
+                       "thread_count_proxy_s": tried},
             "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores,
                              "kind": "port", "sample": f"{len(ts)} full images (1000 ROIs each); dense layers PyTorch-CPU fp32, "
                                                        f"ROI/decode C restatement, NMS {'literal nms.c' if use_lit else 'nms.c restatement'}"},
@@ -431,14 +453,14 @@ def main():
         # bounded CPU sample: ONE full image (1000 ROIs) through the oracle port on all host cores
         from oracle import graphs as G, ref as O
         O.build()
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        cores, tried = pick_cpu_threads(torch)
         use_lit = O.ref_available()
         nms_fn = (lambda sb, thr: np.arange(len(O.ref_nms_rows(sb, thr)))) if use_lit else None
         t0 = time.perf_counter()
         G.test_one(spec, imgs_h[0], boxes_h[0], 1.0, W, H, -1.5, 0.3, nms_fn=nms_fn)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": R / dt, "unit": "proposals/s", "cores": cores, "kind": "port",
+                                "logical_cpus": os.cpu_count(), "thread_count_proxy_s": tried,
                                 "sample": f"1 full image (1000 ROIs), {dt:.1f} s; dense layers PyTorch-CPU fp32, ROI/decode C restatement, "
                                           f"NMS {'literal nms.c' if use_lit else 'nms.c restatement'}"}
     if rank == 0:
