@@ -1519,7 +1519,11 @@ static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, C
     const char *env = getenv("MPN_TC_CTA_GROUP");                 // debug knobs: force the single-CTA / generic engines
     const int max_cg = (env && env[0] == '1') ? 1 : 2;
     const char *env3 = getenv("MPN_TC_R3");
-    const int max_mode = (r3_ok && !(env3 && env3[0] == '0')) ? 1 : 0;
+    // experiment knob: maps with fewer output pixels than MPN_TC_R3_MINPIX take the generic kernel (the 16 x 8 patches of
+    // the A-reuse kernel pad a 38 x 50 map by 29 %: profiles/r01h_layer_efficiency.md); unset = 0 = no effect
+    const char *env3m = getenv("MPN_TC_R3_MINPIX");
+    const long long r3_minpix = env3m ? atoll(env3m) : 0;
+    const int max_mode = (r3_ok && !(env3 && env3[0] == '0') && (long long)p.x.N * p.x.H * p.x.W >= r3_minpix) ? 1 : 0;
     const int taps = p.kh * p.kw;
     double best = 1e300; int best_bn = 64, best_cg = 1, best_mode = 0, best_sk = 0;
     const double cblocks = (double)(p.x.C / BK);

@@ -270,3 +270,18 @@ def test_planner_keeps_per_roi_rounding_independent_of_row_count(Cout, K):
         assert pl["streamk"] == 0
         seen.add((acc(pl["bn"]), pl["splitk"]))
     assert len(seen) == 1, seen
+
+
+def test_planner_r3_minpix_knob_moves_only_small_maps(monkeypatch):
+    """MPN_TC_R3_MINPIX (experiment knob for the 38 x 50 conv5 maps, profiles/r01h_layer_efficiency.md): unset it changes
+    nothing; set to 2000 pixels only conv5 leaves the 3x3 A-reuse kernel."""
+    lib = mpn.load_library()
+    conv5, conv4 = (1, 512, 38, 50, 512), (1, 512, 75, 100, 512)
+    monkeypatch.delenv("MPN_TC_R3_MINPIX", raising=False)
+    base5, base4 = _plan(lib, *conv5), _plan(lib, *conv4)
+    assert base5["mode"] == 1 and base4["mode"] == 1
+    monkeypatch.setenv("MPN_TC_R3_MINPIX", "2000")
+    k5, k4 = _plan(lib, *conv5), _plan(lib, *conv4)
+    assert k5["mode"] == 0 and k5["streamk"] == 0 and k4 == base4
+    monkeypatch.setenv("MPN_TC_R3_MINPIX", "0")
+    assert _plan(lib, *conv5) == base5
