@@ -1,10 +1,11 @@
 #!/bin/bash
 # First GPU call of the next round (one B200, ~6 min of box time):
-#   1. the whole GPU suite with the xfail/xpass lines shown: confirms get_images_kernel (tests/test_zz_getimages_gpu.py),
+#   1. the whole GPU suite with the xfail/xpass lines shown: confirms get_images_kernel (tests/test_zz_pending_gpu.py),
 #      written after round 1's GPU budget was spent;
 #   2. smoke();
 #   3. the default bench line, then the same with conv5 on the generic kernel (MPN_TC_R3_MINPIX=2000: the 16 x 8 patches
 #      pad the 38 x 50 maps by 29 %, profiles/r01h_layer_efficiency.md), same box, back to back;
+#   3b. MultiPathNet with MPN_ROI_NORM_SPLIT=1 against the default ROI kernel;
 #   4. getImages on the device: time for a 480 x 640 -> 600 x 800 image (CUDA events around mpn_get_images_dev).
 mkdir -p gpurun_out; : > gpurun_out/summary.txt
 timeout 1200 python -m pytest tests -q -m gpu -rxX -p no:cacheprovider > gpurun_out/all_gpu_tests.log 2>&1
@@ -24,6 +25,19 @@ PY
 run default X=1
 run conv5_generic MPN_TC_R3_MINPIX=2000
 run default_repeat X=1
+# MultiPathNet (BASELINE configs[2]): ROI stage with the two-pass normalisation (default off) against the staged kernel
+runc() {  # name, env...
+  name=$1; shift
+  out=$(env "$@" python bench.py --config multipathnet --steps 60 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1)
+  echo "$out" > "gpurun_out/bench_${name}.json"
+  python - "$name" "$out" <<'PY' | tee -a gpurun_out/summary.txt
+import json,sys
+d=json.loads(sys.argv[2])
+print(f"{sys.argv[1]:24s} value {d['value']:9.0f}  ms/step {d['ms_per_step']:.4f}  roi_pool ms {d['roofline']['by_category_ms_per_step']['roi_pool']:.3f}")
+PY
+}
+runc mpn_default X=1
+runc mpn_roi_norm_split MPN_ROI_NORM_SPLIT=1
 python - <<'PY' 2>&1 | tee -a gpurun_out/summary.txt
 import ctypes as C, numpy as np, torch
 import multipathnet_b200 as mpn
