@@ -5,7 +5,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v
 CSRC := multipathnet_b200/csrc
-SRCS := $(CSRC)/abi.cu $(CSRC)/nms.cu $(CSRC)/roi.cu $(CSRC)/elementwise.cu $(CSRC)/preproc.cu $(CSRC)/conv_simt.cu $(CSRC)/gemm_tc.cu $(CSRC)/model.cu
+SRCS := $(CSRC)/abi.cu $(CSRC)/nms.cu $(CSRC)/roi.cu $(CSRC)/elementwise.cu $(CSRC)/preproc.cu $(CSRC)/post.cu $(CSRC)/dist.cu $(CSRC)/conv_simt.cu $(CSRC)/gemm_tc.cu $(CSRC)/model.cu
 OBJS := $(SRCS:.cu=.o)
 LIB := multipathnet_b200/libmpn_b200.so
 
@@ -17,7 +17,7 @@ $(CSRC)/nms.o: NVFLAGS += -fmad=false
 # preproc.cu reproduces image.scale's unfused fp32 arithmetic (image_scale.cuh uses *_rn intrinsics; belt and braces)
 $(CSRC)/preproc.o: NVFLAGS += -fmad=false
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 oracle:
 	$(MAKE) -C oracle
 clean:

@@ -124,6 +124,16 @@ def run_nms_sweep(args, rank, world, local_rank):
                           "config": {"workload": "NMS sweep N x 80 classes, thr 0.3 (BASELINE configs[4])"}, "sweep": res}))
 
 
+def bench_config(world):
+    """`config` of the JSON line: ONE dict for both arms (ours / --impl reference) so the driver's same-config check holds;
+    arm-specific facts (CPU thread count, ...) live in other keys of the line."""
+    return {"workload": WORKLOAD,
+            "parallelism": (f"images sharded over {world} rank(s), one NCCL all-gather of the packed top-100 detection records at the end"
+                            if world > 1 else "single GPU"),
+            "l2": "GPU arm: inputs larger than L2, each step streams 0.55 GB of weights + ~1 GB of activations (L2 = 126 MB); CPU arm: n/a",
+            "nms_thr": 0.3, "score_thresh": -1.5, "roi_variant": 2, "top_k_per_image": 100}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -236,8 +246,8 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "steps_timed": len(ts), "warmup_run": 1 if t_first is not None else 0,
             "ms_per_step": 1e3 * total / len(ts), "ms_per_image_p50": 1e3 * statistics.median(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "host": "CPU only", "threads": cores, "logical_cpus": os.cpu_count(),
-                       "thread_count_proxy_s": tried},
+            "config": bench_config(args.gpus),
+            "host": {"arm": "CPU only", "threads": cores, "logical_cpus": os.cpu_count(), "thread_count_proxy_s": tried},
             "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores,
                              "kind": "port", "sample": f"{len(ts)} full images (1000 ROIs each); dense layers PyTorch-CPU fp32, "
                                                        f"ROI/decode C restatement, NMS {'literal nms.c' if use_lit else 'nms.c restatement'}"},
@@ -305,13 +315,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- the path's ONE collective, issued by the library (mpn_dist_*, csrc/dist.cu): every detect+NMS pass also packs the
+    # image's record (keep_top_k 100 + fixed-size layout, csrc/post.cu) into `records_d`; after the last image ONE ncclAllGather
+    # of (steps x MPN_REC_FLOATS) floats per rank. At N = 1 the same calls run (the gather degenerates to a copy).
+    REC = mpn.MPN_REC_FLOATS
+    n_rec = max(args.steps, args.warmup, 3)
+    records_d = torch.zeros((n_rec, REC), dtype=torch.float32, device=dev)
+    gathered_d = torch.zeros((world, args.steps, REC), dtype=torch.float32, device=dev)
+    gathered_h = torch.empty((world, args.steps, REC), dtype=torch.float32).pin_memory()
+    if world > 1:
+        idt = torch.zeros(mpn.MPN_DIST_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(ctx.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.dist_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    def gather_dev():
+        ctx.dist_all_gather_dev(records_d, args.steps * REC, gathered_d)
+
+    # warm-up: the exact sequence of the timed region (steps with the sink on, then the collective: the first NCCL call on a
+    # communicator sets up its channels — tens of ms that are not part of a steady-state run)
+    model.set_detection_sink(records_d, n_rec, 100)
     for i in range(args.warmup):
         step_dev(i)
-    if world > 1:
-        # warm the path's one collective too (the first NCCL call builds the communicator: tens of ms that are not
-        # part of a steady-state step); the timed region below runs the same all-gather once more
-        rec_w = torch.zeros((1, mdist.REC), dtype=torch.float32, device=dev)
-        dist.all_gather([torch.empty_like(rec_w) for _ in range(world)], rec_w)
+    gather_dev()
     barrier()
 
     # ---- timed region 1: device-resident throughput (`value`)
@@ -319,24 +346,19 @@ def main():
     if rank == 0:
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    model.set_detection_sink(records_d, n_rec, 100)                  # resets the record count
     launches0 = ctx.launch_count
     barrier()
     ev[0].record(stream)
     for i in range(args.steps):
         step_dev(i)
         ev[i + 1].record(stream)
-    if world > 1:
-        # the path's ONE collective: all-gather of this rank's final detections (fixed-size padded records)
-        k = counts_d.clamp(max=mdist.MAX_DET // (C - 1)).to(torch.float32)
-        rec = torch.zeros((1, mdist.REC), dtype=torch.float32, device=dev)
-        rec[0, 0] = k.sum()
-        out = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(out, rec)
+    gather_dev()                                                     # THE collective of the path, inside the timed region
     end_ev = torch.cuda.Event(enable_timing=True); end_ev.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(end_ev)
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    collective_ms = ev[args.steps].elapsed_time(end_ev)              # the all-gather incl. the wait for the slowest rank
     launches = ctx.launch_count - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     loop_ms = ev[0].elapsed_time(ev[args.steps])                      # this rank's K steps alone, before the collective
@@ -345,12 +367,30 @@ def main():
         tl_ = torch.tensor([loop_ms], dtype=torch.float64, device=dev)
         allt = [torch.empty_like(tl_) for _ in range(world)]
         dist.all_gather(allt, tl_)
-        # diagnostics: each rank's own loop time (the job total below also contains the wait for the slowest GPU in the
+        # diagnostics: each rank's own loop time (the job total also contains the wait for the slowest GPU in the
         # one all-gather: GPUs of one box differ by several % under the power cap)
         per_rank_ms = [float(x.item()) / args.steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = world * R * args.steps / (total_ms_max / 1e3)
+    # what was gathered: every rank's records, real detections (count field = rows kept by keep_top_k, <= MPN_MAX_DET)
+    g = gathered_d.cpu().numpy()
+    det_counts = g[:, :, 0]
+    assert np.array_equal(g[rank], records_d[:args.steps].cpu().numpy()), "gathered records differ from this rank's own"
+    assert det_counts.min() >= 1 and det_counts.max() <= mpn.MPN_MAX_DET, "gathered detection records are empty or overflowed"
+
+    # ---- p50 latency over a fixed >= 200-image loop, whatever --steps says
+    model.set_detection_sink(None, 0, 100)
+    P50_STEPS, P50_WARM = max(200, args.steps), 20
+    for i in range(P50_WARM):
+        step_dev(i)
+    evp = [torch.cuda.Event(enable_timing=True) for _ in range(P50_STEPS + 1)]
+    evp[0].record(stream)
+    for i in range(P50_STEPS):
+        step_dev(i)
+        evp[i + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    per_step = [evp[i].elapsed_time(evp[i + 1]) for i in range(P50_STEPS)]
 
     # ---- timed region 2: end to end through the host-buffer C-ABI call (`e2e`)
     pin_img = [torch.from_numpy(x).pin_memory() for x in imgs_h]
@@ -398,18 +438,26 @@ def main():
             prev = cur
         ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
 
+    def gather_host():       # the collective + the gathered records to (pinned) host memory, synchronous
+        ctx.check(lib.mpn_dist_all_gather(ctx.h, records_d.data_ptr(), args.steps * REC, gathered_h.data_ptr()), "mpn_dist_all_gather")
+
+    model.set_detection_sink(records_d, n_rec, 100)
     run_pipelined(3)
+    gather_host()
     barrier()
+    model.set_detection_sink(records_d, n_rec, 100)
     t0 = time.perf_counter()
     run_pipelined(args.steps)
+    gather_host()
     e2e_s = time.perf_counter() - t0
+    model.set_detection_sink(None, 0, 100)
     t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * R * args.steps / float(t[0].item())
     e2e_sync_value = world * R * args.steps / float(t[1].item())
     h2d = 3 * H * W * 4 + R * 4 * 4
-    d2h = R * C * 4 + R * 4 * C * 4 + (C - 1) * R * 4 + (C - 1) * 4
+    d2h = R * C * 4 + R * 4 * C * 4 + (C - 1) * R * 4 + (C - 1) * 4 + world * REC * 4      # + this image's share of the gathered records
 
     # ---- per-kernel-category CUDA-event timing of the same steps (roofline numerators)
     ctx.profile_begin()
@@ -438,14 +486,16 @@ def main():
                             "algorithmic_bytes": roi_bytes}
 
     line = {"metric": "proposals/sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "ms_per_image_p50": statistics.median(per_step), "per_rank_loop_ms_per_step": per_rank_ms,
+            "ms_per_step": total_ms_max / args.steps, "ms_per_image_p50": statistics.median(per_step), "p50_steps": P50_STEPS,
+            "per_rank_loop_ms_per_step": per_rank_ms,
+            "collective": {"api": "mpn_dist_all_gather_dev (ncclAllGather issued by libmpn_b200.so on the ctx stream)" if world > 1 else "world of 1: device copy",
+                           "ms": collective_ms, "bytes_per_rank": args.steps * REC * 4, "in_timed_region": True, "in_e2e_region": True,
+                           "detections_per_image_mean": float(det_counts.mean())},
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"images sharded over {world} rank(s), 1 all-gather of detections" if world > 1 else "single GPU",
-                       "l2": "inputs larger than L2: each step streams 0.55 GB of weights + ~1 GB of activations (L2 = 126 MB)",
-                       "nms_thr": 0.3, "score_thresh": -1.5, "roi_variant": 2},
+            "config": bench_config(world),
             "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight)",
+                    "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight) + mpn_dist_all_gather (records to host) at the end",
                     "sync_value": e2e_sync_value, "sync_api": "mpn_model_detect_nms (host buffers, one blocking call per image)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
@@ -466,6 +516,7 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        ctx.dist_destroy()
         dist.destroy_process_group()
 
 

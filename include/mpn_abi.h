@@ -42,6 +42,11 @@ int mpn_ctx_synchronize(mpn_ctx *ctx);
 /* number of kernels THIS library launched on ctx since creation (bench.py's gpu_launches) */
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx);
 const char *mpn_version(void);
+/* run-time knobs of the product kernels, so that tests can cover every variant in one process; value < 0 restores the
+ * default (the environment variable of the same meaning, else the built-in choice). Names:
+ *   "roi_norm_split"  1: L2-normalised ROI levels by a sum-of-squares pre-pass + an unstaged writing pass
+ *                     (MPN_ROI_NORM_SPLIT), 0: one block stages the level's vector in shared memory.           */
+int mpn_ctx_set_option(mpn_ctx *ctx, const char *name, int64_t value);
 /* per-category kernel timing for roofline reporting: between begin and end every launch group is
  * bracketed by CUDA events on the ctx stream. ms_by_cat[6] = {conv/GEMM tcgen05, first-layer direct conv,
  * fused ROI pooling, NMS, elementwise glue, max/avg pooling}; launches_by_cat likewise (may be NULL). */
@@ -237,6 +242,57 @@ int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, in
                              float score_thresh, float nms_thr, float *scores_dev,
                              float *bboxes_dev, int32_t *keep_idx_dev, int32_t *keep_counts_dev);
 
+/* ---- after NMS, on the device --------------------------------------------------------------
+ * Detection record of one image = the result of utils.keep_top_k (utils.lua:75-96; Tester:keepTopKPerImage,
+ * Tester_FRCNN.lua:163-168, test_runner.lua:121) over the image's per-class NMS output, in a fixed size so that the
+ * end-of-run all-gather needs no size exchange: MPN_REC_FLOATS floats = [count, MPN_MAX_DET x (x1,y1,x2,y2,score,class)],
+ * class = 1-based foreground class (the index of the reference's per-class table), rows class-major and in NMS
+ * emission order inside a class (= the reference's tables after keep_top_k), unused rows zero. keep_top_k keeps every
+ * row with score >= the top_k-th largest score, so ties at the cut make count exceed top_k; count > MPN_MAX_DET means
+ * the record overflowed (rows beyond MPN_MAX_DET are dropped; the host mirrors raise).                              */
+enum { MPN_MAX_DET = 128, MPN_REC_FLOATS = 769, MPN_DIST_ID_BYTES = 128 };
+/* scores R x C, bboxes R x 4C (detect outputs), keep_idx (C-1) x cap proposal rows in emission order, keep_counts C-1
+ * (the outputs of mpn_model_detect_nms*, cap = R there). Device buffers, stream-ordered; host form synchronous.   */
+int mpn_pack_detections_dev(mpn_ctx *ctx, const float *scores_dev, const float *bboxes_dev, int64_t R, int32_t C,
+                            const int32_t *keep_idx_dev, const int32_t *keep_counts_dev, int64_t cap, int32_t top_k,
+                            float *record_dev);
+int mpn_pack_detections(mpn_ctx *ctx, const float *scores, const float *bboxes, int64_t R, int32_t C,
+                        const int32_t *keep_idx, const int32_t *keep_counts, int64_t cap, int32_t top_k, float *record);
+/* nn.SelectBoxes:updateOutput (modules/SelectBoxes.lua:26-56; Tester_FRCNN.lua:82-90): out[r] = the 4 box values of
+ * the class with the largest score in row r (first maximum, background included), * std4 + mean4 when both are given
+ * (NULL, NULL: the "dry run" of SelectBoxes.lua:46-47). classes R x C, ys R x 4C, out R x 4.                      */
+int mpn_select_boxes(mpn_ctx *ctx, const float *classes, const float *ys, int64_t R, int32_t C, const float *mean4,
+                     const float *std4, float *out);
+int mpn_select_boxes_dev(mpn_ctx *ctx, const float *classes_dev, const float *ys_dev, int64_t R, int32_t C,
+                         const float *mean4, const float *std4, float *out_dev);
+/* From now on every mpn_model_detect_nms / _dev / _submit call also packs the image's record (top_k, normally 100)
+ * into records_dev[n * MPN_REC_FLOATS], n = 0, 1, ... (stream-ordered, one extra launch per image); the call fails
+ * once `capacity` records were written. records_dev = NULL switches the sink off; setting it resets the count.      */
+int mpn_model_set_detection_sink(mpn_model *m, float *records_dev, int64_t capacity, int32_t top_k);
+int mpn_model_detection_sink_count(const mpn_model *m, int64_t *n_records);
+
+/* ---- the path's ONE collective (test_runner.lua:96-103,121-122 joins the per-image results of all
+ * replicas): an NCCL all-gather of the packed records, issued by the library on the ctx stream. One process (or
+ * thread) per GPU: rank 0 calls mpn_dist_unique_id and hands the MPN_DIST_ID_BYTES bytes to every rank by whatever
+ * channel the host has (torch.distributed / a file / threads' shared memory), then every rank calls mpn_dist_init
+ * concurrently. NCCL is bound at run time (the libnccl.so.2 already in the process, else the system one); without
+ * it these calls fail with a message and nothing else is affected. A ctx without a communicator is a world of 1.    */
+int mpn_dist_unique_id(mpn_ctx *ctx, uint8_t *id);
+int mpn_dist_init(mpn_ctx *ctx, const uint8_t *id, int32_t rank, int32_t world);
+int mpn_dist_world(const mpn_ctx *ctx, int32_t *rank, int32_t *world);
+/* recv = world x n_floats, rank-major; every rank contributes n_floats (its records, padded to the same count).
+ * _dev: device buffers, stream-ordered (send may alias its own slot of recv). Host form: recv_host, synchronous.    */
+int mpn_dist_all_gather_dev(mpn_ctx *ctx, const float *send_dev, int64_t n_floats, float *recv_dev);
+int mpn_dist_all_gather(mpn_ctx *ctx, const float *send_dev, int64_t n_floats, float *recv_host);
+int mpn_dist_destroy(mpn_ctx *ctx);
+int mpn_dist_nccl_version(mpn_ctx *ctx, int32_t *version);
+
+/* introspection for tests: rows [r0, r0 + n) of the pooled tensor the LAST heads / detect call fed to tower `tower` —
+ * the output of the fused Foveal + ROI pooling (+ per-level L2 normalise x 1000) kernel on the product path — as fp32
+ * n x (PH*PW) x Ctot (channels-last, levels concatenated along channels; value = hi + lo of the split planes).
+ * out may be NULL to query *R_total / *bins / *Ctot only. Host buffer, synchronous.                                 */
+int mpn_model_get_pooled(mpn_model *m, int32_t tower, int64_t r0, int64_t n, float *out, int64_t capacity,
+                         int64_t *R_total, int32_t *bins, int32_t *Ctot);
 /* introspection for tests/profiling: copy a trunk slot to host as N x C x H x W fp32 */
 int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_t capacity,
                              int32_t *C, int32_t *H, int32_t *W);

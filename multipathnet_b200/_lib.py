@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libmpn_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mpn_abi.h")
 
 MPN_LAYER_CONV, MPN_LAYER_MAXPOOL, MPN_LAYER_AVGPOOL, MPN_LAYER_FLATTEN = 1, 2, 3, 4
+MPN_MAX_DET, MPN_REC_FLOATS, MPN_DIST_ID_BYTES = 128, 769, 128      # include/mpn_abi.h
 MPN_LAYER_LRN = 5       # CaffeNet local response norm: CPU-oracle plumbing config only (BASELINE configs[0]), not on the B200 path
 
 
@@ -84,6 +85,7 @@ SIGNATURES = {
     "mpn_ctx_synchronize": (C.c_int, [_vp]),
     "mpn_ctx_launch_count": (C.c_int64, [_vp]),
     "mpn_version": (C.c_char_p, []),
+    "mpn_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "mpn_ctx_profile_begin": (C.c_int, [_vp]),
     "mpn_ctx_profile_end": (C.c_int, [_vp, C.POINTER(C.c_double), _i64p]),
     "mpn_ctx_timeline_begin": (C.c_int, [_vp, C.c_int32]),
@@ -119,6 +121,20 @@ SIGNATURES = {
     "mpn_model_detect_nms_wait": (C.c_int, [_vp, C.c_int32]),
     "mpn_model_detect_nms_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "mpn_pack_detections_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int64, C.c_int32, _vp]),
+    "mpn_pack_detections": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int64, C.c_int32, _vp]),
+    "mpn_select_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),
+    "mpn_select_boxes_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),
+    "mpn_model_set_detection_sink": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32]),
+    "mpn_model_detection_sink_count": (C.c_int, [_vp, _i64p]),
+    "mpn_dist_unique_id": (C.c_int, [_vp, _vp]),
+    "mpn_dist_init": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32]),
+    "mpn_dist_world": (C.c_int, [_vp, _i32p, _i32p]),
+    "mpn_dist_all_gather_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "mpn_dist_all_gather": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "mpn_dist_destroy": (C.c_int, [_vp]),
+    "mpn_dist_nccl_version": (C.c_int, [_vp, _i32p]),
+    "mpn_model_get_pooled": (C.c_int, [_vp, C.c_int32, C.c_int64, C.c_int64, _vp, C.c_int64, _i64p, _i32p, _i32p]),
     "mpn_model_get_trunk_slot": (C.c_int, [_vp, C.c_int32, _vp, C.c_int64, _i32p, _i32p, _i32p]),
     "mpn_model_set_conv_impl": (C.c_int, [_vp, C.c_int32]),
     "mpn_model_last_flops": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -182,6 +198,7 @@ class Context:
             raise MpnError(f"mpn_ctx_create failed ({rc}): {self.lib.mpn_last_error(None).decode()}")
         self.h = h
         self.device = device
+        self._models = []          # weak references to the live Models: closed before the ctx (they dereference it)
 
     def check(self, rc: int, what: str = ""):
         if rc != 0:
@@ -189,6 +206,9 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.mpn_ctx_synchronize(self.h), "synchronize")
+
+    def set_option(self, name: str, value: int):
+        self.check(self.lib.mpn_ctx_set_option(self.h, name.encode(), int(value)), "mpn_ctx_set_option")
 
     @property
     def launch_count(self) -> int:
@@ -207,6 +227,11 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for ref in list(getattr(self, "_models", [])):      # mpn_model_destroy touches the ctx: models go first
+                m = ref()
+                if m is not None:
+                    m.close()
+            self._models = []
             self.lib.mpn_ctx_destroy(self.h)
             self.h = None
 
@@ -215,6 +240,56 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    # ---- the end-of-run collective ----------------------------------------------
+    def dist_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * MPN_DIST_ID_BYTES)()
+        self.check(self.lib.mpn_dist_unique_id(self.h, buf), "mpn_dist_unique_id")
+        return bytes(buf)
+
+    def dist_init(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == MPN_DIST_ID_BYTES
+        buf = (C.c_uint8 * MPN_DIST_ID_BYTES).from_buffer_copy(unique_id)
+        self.check(self.lib.mpn_dist_init(self.h, buf, int(rank), int(world)), "mpn_dist_init")
+
+    def dist_world(self):
+        r, w = C.c_int32(), C.c_int32()
+        self.check(self.lib.mpn_dist_world(self.h, C.byref(r), C.byref(w)), "mpn_dist_world")
+        return r.value, w.value
+
+    def dist_all_gather_dev(self, send_dev, n_floats: int, recv_dev):
+        self.check(self.lib.mpn_dist_all_gather_dev(self.h, _ptr(send_dev), int(n_floats), _ptr(recv_dev)), "mpn_dist_all_gather_dev")
+
+    def dist_all_gather(self, send_dev, n_floats: int) -> np.ndarray:
+        """device records of this rank -> host array world x n_floats (synchronous)"""
+        _, w = self.dist_world()
+        out = np.empty((w, int(n_floats)), np.float32)
+        self.check(self.lib.mpn_dist_all_gather(self.h, _ptr(send_dev), int(n_floats), _ptr(out)), "mpn_dist_all_gather")
+        return out
+
+    def dist_destroy(self):
+        self.check(self.lib.mpn_dist_destroy(self.h), "mpn_dist_destroy")
+
+    # ---- after NMS ---------------------------------------------------------------------------
+    def pack_detections(self, scores, bboxes, keep_idx, keep_counts, top_k: int = 100) -> np.ndarray:
+        """utils.keep_top_k + the fixed-size record (include/mpn_abi.h): scores R x C, bboxes R x 4C, keep_idx (C-1) x cap,
+        keep_counts C-1 -> MPN_REC_FLOATS floats"""
+        s, b = _f32(scores), _f32(bboxes)
+        k = np.ascontiguousarray(keep_idx, dtype=np.int32); c = np.ascontiguousarray(keep_counts, dtype=np.int32)
+        rec = np.empty(MPN_REC_FLOATS, np.float32)
+        self.check(self.lib.mpn_pack_detections(self.h, _ptr(s), _ptr(b), s.shape[0], s.shape[1], _ptr(k), _ptr(c), k.shape[1],
+                                                int(top_k), _ptr(rec)), "mpn_pack_detections")
+        return rec
+
+    def select_boxes(self, classes, ys, mean=None, std=None) -> np.ndarray:
+        """nn.SelectBoxes:updateOutput (modules/SelectBoxes.lua:26-56)"""
+        s, y = _f32(classes), _f32(ys)
+        out = np.empty((s.shape[0], 4), np.float32)
+        m = None if mean is None else _f32(mean).reshape(4)
+        sd = None if std is None else _f32(std).reshape(4)
+        self.check(self.lib.mpn_select_boxes(self.h, _ptr(s), _ptr(y), s.shape[0], s.shape[1], _ptr(m), _ptr(sd), _ptr(out)),
+                   "mpn_select_boxes")
+        return out
 
     # ---- NMS family -------------------------------------------------------------------------
     def nms(self, scored_boxes, thr: float) -> np.ndarray:
@@ -449,11 +524,34 @@ class Model:
                   "mpn_model_create")
         self.h = h
         self.C = spec.num_classes
+        import weakref
+        ctx._models.append(weakref.ref(self))
 
     def close(self):
         if getattr(self, "h", None):
-            self.ctx.lib.mpn_model_destroy(self.h)
+            if getattr(self.ctx, "h", None):               # a closed ctx has already closed its models
+                self.ctx.lib.mpn_model_destroy(self.h)
             self.h = None
+
+    def set_detection_sink(self, records_dev, capacity: int, top_k: int = 100):
+        """every later detect_nms* call appends the image's packed record to records_dev (a CUDA tensor / address)"""
+        self.ctx.check(self.ctx.lib.mpn_model_set_detection_sink(self.h, _ptr(records_dev), int(capacity), int(top_k)),
+                       "mpn_model_set_detection_sink")
+
+    def detection_sink_count(self) -> int:
+        n = C.c_int64()
+        self.ctx.check(self.ctx.lib.mpn_model_detection_sink_count(self.h, C.byref(n)), "mpn_model_detection_sink_count")
+        return int(n.value)
+
+    def pooled(self, tower: int, r0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """rows [r0, r0+n) of the pooled tensor the last heads/detect call fed to `tower`: n x bins x Ctot fp32"""
+        R, bins, ct = C.c_int64(), C.c_int32(), C.c_int32()
+        self.ctx.check(self.ctx.lib.mpn_model_get_pooled(self.h, tower, 0, 0, None, 0, C.byref(R), C.byref(bins), C.byref(ct)), "get_pooled")
+        n = R.value - r0 if n is None else n
+        out = np.empty((n, bins.value, ct.value), np.float32)
+        self.ctx.check(self.ctx.lib.mpn_model_get_pooled(self.h, tower, r0, n, _ptr(out), out.size, C.byref(R), C.byref(bins), C.byref(ct)),
+                       "get_pooled")
+        return out
 
     def __del__(self):
         try:

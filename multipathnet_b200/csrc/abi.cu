@@ -9,6 +9,8 @@
 int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
 int mpn_nms_dense_launch(mpn_ctx *, const float *, int, float, int32_t *, int32_t *);
 int mpn_bbox_vote_launch(mpn_ctx *, const float *, int, const float *, int, float, float *);
+int mpn_pack_detections_launch(mpn_ctx *, const float *, const float *, int, const int32_t *, const int32_t *, int, int, float *);
+int mpn_select_boxes_launch(mpn_ctx *, const float *, const float *, int64_t, int, const float *, const float *, float *);
 int mpn_foveal_launch(mpn_ctx *, const float *, int64_t, float *);
 int mpn_context_region_launch(mpn_ctx *, const float *, int64_t, float, float *);
 int mpn_get_images_launch(mpn_ctx *, const float *, int32_t, int32_t, const mpn_image_transform *, int32_t, int32_t, float *);
@@ -86,6 +88,7 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  mpn_dist_destroy(ctx);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
   if (ctx->scratch3) cudaFree(ctx->scratch3);
@@ -111,6 +114,12 @@ int mpn_ctx_synchronize(mpn_ctx *ctx) {
 }
 
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int mpn_ctx_set_option(mpn_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return MPN_ERR_ARG;
+  if (!strcmp(name, "roi_norm_split")) { ctx->opt_roi_norm_split = value < 0 ? -1 : (value ? 1 : 0); return MPN_OK; }
+  return mpn_fail(ctx, MPN_ERR_ARG, std::string("unknown option: ") + name);
+}
 
 int mpn_ctx_timeline_begin(mpn_ctx *ctx, int32_t max_launches) {
   if (!ctx || max_launches <= 0) return MPN_ERR_ARG;
@@ -265,6 +274,64 @@ int mpn_bbox_vote(mpn_ctx *ctx, const float *nms_boxes, int64_t K, const float *
   if (N) MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_s), scored_boxes, sizeof(float) * 5 * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
   MPN_TRY(mpn_bbox_vote_launch(ctx, a.at<float>(o_n), (int)K, a.at<float>(o_s), (int)N, thr, a.at<float>(o_r)));
   MPN_CUDA(ctx, cudaMemcpyAsync(res, a.at<float>(o_r), sizeof(float) * 5 * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+// ------------------------------------------------------------------ after NMS (post.cu)
+int mpn_pack_detections_dev(mpn_ctx *ctx, const float *scores_dev, const float *bboxes_dev, int64_t R, int32_t C,
+                            const int32_t *keep_idx_dev, const int32_t *keep_counts_dev, int64_t cap, int32_t top_k, float *record_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, scores_dev && bboxes_dev && keep_idx_dev && keep_counts_dev && record_dev && R > 0 && cap > 0, "buffers missing");
+  return mpn_pack_detections_launch(ctx, scores_dev, bboxes_dev, C, keep_idx_dev, keep_counts_dev, (int)cap, top_k, record_dev);
+}
+
+int mpn_pack_detections(mpn_ctx *ctx, const float *scores, const float *bboxes, int64_t R, int32_t C, const int32_t *keep_idx,
+                        const int32_t *keep_counts, int64_t cap, int32_t top_k, float *record) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, scores && bboxes && keep_idx && keep_counts && record && R > 0 && C >= 2 && cap > 0, "buffers missing");
+  Arena a{ctx};
+  const size_t bs = sizeof(float) * (size_t)R * C, bb = sizeof(float) * (size_t)R * 4 * C, bk = sizeof(int32_t) * (size_t)(C - 1) * cap,
+               bc = sizeof(int32_t) * (size_t)(C - 1), br = sizeof(float) * MPN_REC_FLOATS;
+  size_t o_s = a.reserve(bs), o_b = a.reserve(bb), o_k = a.reserve(bk), o_c = a.reserve(bc), o_r = a.reserve(br);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_s), scores, bs, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_b), bboxes, bb, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<int32_t>(o_k), keep_idx, bk, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<int32_t>(o_c), keep_counts, bc, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_pack_detections_launch(ctx, a.at<float>(o_s), a.at<float>(o_b), C, a.at<int32_t>(o_k), a.at<int32_t>(o_c), (int)cap, top_k,
+                                     a.at<float>(o_r)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(record, a.at<float>(o_r), br, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return MPN_OK;
+}
+
+int mpn_select_boxes_dev(mpn_ctx *ctx, const float *classes_dev, const float *ys_dev, int64_t R, int32_t C, const float *mean4,
+                         const float *std4, float *out_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0 && C >= 1 && (R == 0 || (classes_dev && ys_dev && out_dev)), "buffers missing");
+  MPN_CHECK_ARG(ctx, (mean4 == nullptr) == (std4 == nullptr), "mean4 and std4 go together");
+  return mpn_select_boxes_launch(ctx, classes_dev, ys_dev, R, C, mean4, std4, out_dev);
+}
+
+int mpn_select_boxes(mpn_ctx *ctx, const float *classes, const float *ys, int64_t R, int32_t C, const float *mean4, const float *std4,
+                     float *out) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0 && C >= 1, "bad arguments");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, classes && ys && out, "buffers missing");
+  Arena a{ctx};
+  const size_t bs = sizeof(float) * (size_t)R * C, bb = sizeof(float) * (size_t)R * 4 * C, bo = sizeof(float) * (size_t)R * 4;
+  size_t o_s = a.reserve(bs), o_b = a.reserve(bb), o_o = a.reserve(bo);
+  MPN_TRY(a.commit());
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_s), classes, bs, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(a.at<float>(o_b), ys, bb, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_select_boxes_dev(ctx, a.at<float>(o_s), a.at<float>(o_b), R, C, mean4, std4, a.at<float>(o_o)));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, a.at<float>(o_o), bo, cudaMemcpyDeviceToHost, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPN_OK;
 }

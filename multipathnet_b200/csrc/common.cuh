@@ -27,13 +27,17 @@ struct mpn_ctx {
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
-  uint8_t tc_attr_set[16] = {0};
+  uint8_t tc_attr_set[32] = {0};
   // stream-K (gemm_tc.cu): per-CTA partial-tile slots + per-(CTA, epilogue warp) flags holding the launch epoch
   float *sk_ws = nullptr; unsigned *sk_flags = nullptr; unsigned sk_epoch = 0;
   // NMS tie flags live in scratch2 and are reset by their last reader; (pointer, count) of the region known to be zero
   void *nms_tie_ptr = nullptr; int nms_tie_n = 0;
   // in-kernel timeline of the tcgen05 launches (diagnostics, mpn_ctx_timeline_begin/end): per launch 4 min- and 4 max-stamps
   unsigned long long *tl_min = nullptr, *tl_max = nullptr; int tl_cap = 0, tl_n = 0, tl_on = 0;
+  // the end-of-run all-gather (dist.cu): an ncclComm_t bound at run time, this ctx's rank / world, collectives issued
+  // run-time knobs (mpn_ctx_set_option); -1 = take the environment default
+  int opt_roi_norm_split = -1;
+  void *dist_comm = nullptr; int dist_rank = 0, dist_world = 1; int64_t collectives = 0;
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };

@@ -30,6 +30,8 @@ int mpn_detect_tail_launch(mpn_ctx *, const float *, int64_t, int, int, int, flo
                            float *, int, const float *, const float *);
 int mpn_gather_scored_launch(mpn_ctx *, const float *, const float *, int, int, float, float *, int32_t *, int32_t *);
 int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
+int mpn_pack_detections_launch(mpn_ctx *, const float *, const float *, int, const int32_t *, const int32_t *, int, int, float *);
+int mpn_join_rows_launch(mpn_ctx *, const __nv_bfloat16 *, const __nv_bfloat16 *, int64_t, int64_t, int64_t, float *);
 
 namespace {
 
@@ -125,6 +127,8 @@ struct mpn_model {
   PipeSlot pipe[2];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   int next_ticket = 0;
+  // ---- detection sink (mpn_model_set_detection_sink): every detect+NMS pass also packs the image's record
+  float *sink = nullptr; int64_t sink_cap = 0, sink_n = 0; int sink_top_k = 100;
   ~mpn_model() {
     for (auto &q : pipe) { if (q.h2d) cudaEventDestroy(q.h2d); if (q.compute) cudaEventDestroy(q.compute); if (q.done) cudaEventDestroy(q.done); }
     if (s_h2d) cudaStreamDestroy(s_h2d);
@@ -732,6 +736,13 @@ static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, floa
     MPN_TRY(mpn_nms_launch(ctx, (const float *)m->sb_dev.p, (int)R, C - 1, (const int32_t *)m->counts_dev.p,
                            (const int32_t *)m->src_idx_dev.p, nms_thr, (int32_t *)m->keep_idx_dev.p,
                            (int32_t *)m->keep_counts_dev.p));
+    if (m->sink) {     // keep_top_k + fixed-size record of this image, appended to the caller's sink
+      MPN_CHECK_ARG(ctx, m->sink_n < m->sink_cap, "detection sink is full (mpn_model_set_detection_sink capacity)");
+      MPN_TRY(mpn_pack_detections_launch(ctx, (const float *)m->scores_dev.p, (const float *)m->bboxes_dev.p, C,
+                                         (const int32_t *)m->keep_idx_dev.p, (const int32_t *)m->keep_counts_dev.p, (int)R,
+                                         m->sink_top_k, m->sink + (size_t)m->sink_n * MPN_REC_FLOATS));
+      ++m->sink_n;
+    }
   }
   return MPN_OK;
 }
@@ -855,6 +866,41 @@ int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket) {
   MPN_CHECK_ARG(ctx, ticket >= 0 && q.busy && q.ticket == ticket, "unknown or already completed ticket");
   MPN_CUDA(ctx, cudaEventSynchronize(q.done));
   q.busy = false;
+  return MPN_OK;
+}
+
+int mpn_model_set_detection_sink(mpn_model *m, float *records_dev, int64_t capacity, int32_t top_k) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CHECK_ARG(ctx, !records_dev || (capacity > 0 && top_k >= 1 && top_k <= MPN_MAX_DET), "detection sink: capacity > 0 and 1 <= top_k <= MPN_MAX_DET");
+  m->sink = records_dev; m->sink_cap = records_dev ? capacity : 0; m->sink_n = 0; m->sink_top_k = records_dev ? top_k : 100;
+  return MPN_OK;
+}
+
+int mpn_model_detection_sink_count(const mpn_model *m, int64_t *n_records) {
+  if (!m || !n_records) return MPN_ERR_ARG;
+  *n_records = m->sink_n;
+  return MPN_OK;
+}
+
+int mpn_model_get_pooled(mpn_model *m, int32_t tower, int64_t r0, int64_t n, float *out, int64_t capacity, int64_t *R_total,
+                         int32_t *bins, int32_t *Ctot) {
+  if (!m) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, m->heads_planned && tower >= 0 && tower < (int)m->tex.size(), "no heads pass yet, or unknown tower");
+  const DTensor &t = m->tex[tower].pooled;
+  const int64_t row = t.H * t.W * t.C;
+  if (R_total) *R_total = t.N;
+  if (bins) *bins = (int32_t)(t.H * t.W);
+  if (Ctot) *Ctot = (int32_t)t.C;
+  if (!out) return MPN_OK;
+  MPN_CHECK_ARG(ctx, r0 >= 0 && n > 0 && r0 + n <= t.N && capacity >= n * row, "row range outside the pooled tensor, or buffer too small");
+  void *tmp = nullptr;
+  MPN_TRY(mpn_scratch(ctx, sizeof(float) * (size_t)(n * row), &tmp));
+  MPN_TRY(mpn_join_rows_launch(ctx, t.hi + r0 * row, t.lo + r0 * row, n, row, row, (float *)tmp));
+  MPN_CUDA(ctx, cudaMemcpyAsync(out, tmp, sizeof(float) * (size_t)(n * row), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPN_OK;
 }
 

@@ -48,12 +48,30 @@ def test_shard_and_allgather_world2():
 
 
 def test_pack_unpack_roundtrip():
+    """pack_record == utils.keep_top_k (utils.lua:75-96) in a fixed-size record: `>=` the 100th score, order preserved,
+    ties at the cut all survive (may exceed 100), more than MAX_DET raises; host mirror of pack_detections_kernel"""
+    import pytest
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    from multipathnet_b200 import dist as mdist
+    from multipathnet_b200 import dist as mdist, utils as U
     rng = np.random.default_rng(0)
     d = rng.random((150, 6)).astype(np.float32)
-    rec = mdist.pack_record(d)                                           # top-100 by score (Tester_FRCNN.lua:163)
-    out = mdist.unpack_record(rec)
-    assert out.shape[0] == 100
-    assert np.all(np.diff(out[:, 4]) <= 0)
+    d[:, 5] = np.sort(rng.integers(1, 21, 150))                          # class-major, as testOne returns the tables
+    out = mdist.unpack_record(mdist.pack_record(d))
+    thr = np.sort(d[:, 4])[::-1][99]
+    assert out.shape[0] == 100 and np.array_equal(out, d[d[:, 4] >= thr])        # row order preserved, not re-sorted
+    # same thing through the reference-shaped API: per-class tables -> keep_top_k
+    tables = [d[d[:, 5] == j, :5] for j in range(1, 21)]
+    kept, _ = U.keep_top_k([t.copy() for t in tables], 100)
+    back = mdist.record_to_tables(mdist.pack_record(mdist.tables_to_dets(tables)), 21)
+    assert all(np.array_equal(a, b) for a, b in zip(kept, back))
+    # ties at the cut: scores quantised to 1/8 -> everything >= the 100th score survives
+    q = d.copy(); q[:, 4] = np.floor(q[:, 4] * 8) / 8
+    thr = np.sort(q[:, 4])[::-1][99]
+    n = int((q[:, 4] >= thr).sum())
+    assert n > 100
+    if n <= mdist.MAX_DET:
+        assert mdist.unpack_record(mdist.pack_record(q)).shape[0] == n
+    q[:, 4] = 0.5                                                        # 150 tied rows: overflow is loud
+    with pytest.raises(OverflowError):
+        mdist.pack_record(q)
     assert mdist.unpack_record(mdist.pack_record(np.zeros((0, 6), np.float32))).shape == (0, 6)

@@ -1,10 +1,7 @@
-"""GPU suite, last file on purpose: code written after round 1's GPU budget was spent, so NOT yet run on a B200 —
-  * getImages on the device (mpn_get_images / mpn_model_trunk_image): its per-pixel arithmetic is the
-    __host__ __device__ code the CPU suite already checks bit for bit (tests/test_getimages_cpu.py), what is untested is
-    the launch itself;
-  * the default-off two-pass normalisation of the fused ROI pooling (MPN_ROI_NORM_SPLIT=1, csrc/roi.cu). Until a GPU run has confirmed them these tests are xfail(strict=False): a pass shows as XPASS, a
-failure as XFAIL, neither hides or breaks the verified suite before it (this file sorts last so that even a faulting
-kernel cannot disturb another test). Drop the marker once a round has seen them pass."""
+"""GPU suite: getImages on the device (mpn_get_images / mpn_model_trunk_image; ImageDetect.lua:22-52 +
+modules/ImageTransformer.lua:19-33) — bit-exact against the two-pass oracle and the committed golden fixture, and the
+raw-image detect path against the host getImages path. (First ran on a B200 in round 2: all green; the xfail markers of
+round 1 are gone.) Also the two normalisation variants of the fused ROI pooling through the environment knob."""
 import os
 import subprocess
 import sys
@@ -17,7 +14,7 @@ from multipathnet_b200 import models, workloads as wl
 from multipathnet_b200.image_detect import ImageDetect
 from multipathnet_b200.modules import ImageTransformer
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run of code written after round 1's GPU budget was spent")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("H0,W0,scale,max_size", [(60, 80, 60, 100), (48, 64, 75, 1000), (120, 90, 60, 1000), (50, 200, 100, 300), (333, 500, 600, 1000)])

@@ -13,6 +13,18 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-3
 
 
+def assert_nms_every_class(scores, bboxes, keeps, thr=0.3):
+    """the GPU keep lists of EVERY foreground class against the LITERAL reference nms.c (oracle/_ref, built from
+    /root/reference/nms.c) run on the GPU's own clamped boxes / scores: same kept rows in the same emission order, bit for
+    bit; and against the C restatement's index lists (which the literal build pins in tests/test_oracle_cpu.py)."""
+    lit = O.ref_available()
+    for j in range(1, scores.shape[1]):
+        sb = np.ascontiguousarray(np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1), np.float32)
+        assert np.array_equal(keeps[j - 1], O.nms(sb, thr)), f"class {j}: keep indices differ from nms.c's"
+        if lit:
+            assert np.array_equal(sb[keeps[j - 1]], O.ref_nms_rows(sb, thr)), f"class {j}: kept rows differ from the literal nms.c"
+
+
 def _inputs(spec, H, W, R, seed, sharp=False):
     img = wl.transform(wl.raw_image(H, W, seed), spec.transformer)
     boxes = (wl.sharpmask_boxes if sharp else wl.random_boxes)(R, H, W, seed)
@@ -158,9 +170,7 @@ def test_vgg16_full_size_cfg2(ctx):
     scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
     rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600)
     assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
-    for j in (1, 7, 20):
-        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
-        assert np.array_equal(keeps[j - 1], O.nms(sb, 0.3))
+    assert_nms_every_class(scores, bboxes, keeps)
     tf, hf = m.last_flops()
     assert abs(tf / 1e9 - 294.0) < 0.1 and abs(hf / 1e9 - 239.9) < 0.2
     m.close()
@@ -192,9 +202,7 @@ def test_multipathnet_full_size_cfg3(ctx):
     scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
     rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600)
     assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
-    for j in (1, 40, 80):
-        sb = np.concatenate([bboxes[:, 4 * j:4 * j + 4], scores[:, j:j + 1]], 1).astype(np.float32)
-        assert np.array_equal(keeps[j - 1], O.nms(sb, 0.3))
+    assert_nms_every_class(scores, bboxes, keeps)
     tf, hf = m.last_flops()
     assert abs(hf / 1e12 - 1.458) < 0.01                     # 1.458 GFLOP/ROI x 1000
     m.close()
@@ -205,9 +213,10 @@ def test_resnet50_full_size_cfg4(ctx):
     spec = models.resnet50_fast_rcnn(81, seed=1234, integral_k=6)
     m = mpn.Model(ctx, spec, max_rois=2048, max_h=808, max_w=1000)
     img, boxes = _inputs(spec, 800, 1000, 2000, 4, sharp=True)
-    scores, bboxes = m.detect(img, boxes, 1.0)
-    rs, rb = G.detect(spec, img, boxes, 1.0)
+    scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 1000, 800, -1.5, 0.3)
+    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 1000, 800, nms_fn=lambda sb, thr: np.zeros(0, np.int64))
     assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    assert_nms_every_class(scores, bboxes, keeps)                       # 80 classes x 2000 boxes
     tf, hf = m.last_flops()
     assert abs(tf / 1e9 - 104.9) < 1.5 and abs(hf / 2000 / 1e9 - 1.62) < 0.02
     m.close()
