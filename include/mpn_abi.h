@@ -44,8 +44,11 @@ int64_t mpn_ctx_launch_count(const mpn_ctx *ctx);
 const char *mpn_version(void);
 /* run-time knobs of the product kernels, so that tests can cover every variant in one process; value < 0 restores the
  * default (the environment variable of the same meaning, else the built-in choice). Names:
- *   "roi_norm_split"  1: L2-normalised ROI levels by a sum-of-squares pre-pass + an unstaged writing pass
- *                     (MPN_ROI_NORM_SPLIT), 0: one block stages the level's vector in shared memory.           */
+ *   "roi_impl"        fused Foveal + ROI pooling kernel: 0 = roi_pool_cluster_kernel (default: 4-CTA clusters, the
+ *                     L2 norm reduced over distributed shared memory), 1 = the round-1 kernel (one block stages a
+ *                     normalised level's whole vector), 2 = the round-1 two-pass variant (sum-of-squares pre-pass +
+ *                     unstaged writing pass). Environment: MPN_ROI_IMPL.
+ *   "roi_norm_split"  older spelling: 1 selects roi_impl 2, 0 selects roi_impl 1 (MPN_ROI_NORM_SPLIT).          */
 int mpn_ctx_set_option(mpn_ctx *ctx, const char *name, int64_t value);
 /* per-category kernel timing for roofline reporting: between begin and end every launch group is
  * bracketed by CUDA events on the ctx stream. ms_by_cat[6] = {conv/GEMM tcgen05, first-layer direct conv,

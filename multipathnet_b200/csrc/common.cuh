@@ -36,7 +36,7 @@ struct mpn_ctx {
   unsigned long long *tl_min = nullptr, *tl_max = nullptr; int tl_cap = 0, tl_n = 0, tl_on = 0;
   // the end-of-run all-gather (dist.cu): an ncclComm_t bound at run time, this ctx's rank / world, collectives issued
   // run-time knobs (mpn_ctx_set_option); -1 = take the environment default
-  int opt_roi_norm_split = -1;
+  int opt_roi_norm_split = -1, opt_roi_impl = -1;
   void *dist_comm = nullptr; int dist_rank = 0, dist_world = 1; int64_t collectives = 0;
 };
 

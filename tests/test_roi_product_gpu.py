@@ -1,5 +1,5 @@
 """GPU parity of the kernels the benchmark actually times on the ROI stage:
-`roi_pool_fused_kernel` / `roi_pool_split_kernel` on the fp32 max pyramid (`maxpyr_*`), with the fused Foveal region
+`roi_pool_cluster_kernel` (default) and the round-1 `roi_pool_fused_kernel` / `roi_pool_split_kernel` on the fp32 max pyramid (`maxpyr_*`), with the fused Foveal region
 and the per-level L2 normalise x 1000 — checked on the POOLED TENSOR itself (mpn_model_get_pooled), not through the
 whole-graph 1e-3 bar. The oracle runs on the GPU's OWN feature maps (mpn_model_get_trunk_slot), so the comparison isolates
 the ROI stage:   orc_foveal (Foveal.lua:26-39) -> orc_roi_pool (imagine-nn) [-> orc_l2_normalize, x 1000
@@ -51,10 +51,10 @@ def oracle_pooled(spec, m, rois, tower, rows):
     return np.ascontiguousarray(x.reshape(n, x.shape[1], -1).transpose(0, 2, 1))
 
 
-def check_tower(spec, m, rois, tower, rows):
+def check_tower(spec, m, rois, tower, rows, ref=None):
     t = spec.towers[tower]
     got = m.pooled(tower, rows.start, rows.stop - rows.start)
-    ref = oracle_pooled(spec, m, rois, tower, rows)
+    ref = oracle_pooled(spec, m, rois, tower, rows) if ref is None else ref
     assert got.shape == ref.shape
     if not t.normalize:
         assert np.array_equal(got, ref), f"tower {tower}: {np.count_nonzero(got != ref)} of {got.size} pooled values differ"
@@ -89,44 +89,53 @@ def test_fused_roi_small_unnormalised_and_regions_leaving_the_image(ctx):
     m.close()
 
 
-@pytest.mark.parametrize("norm_split", [0, 1])
-def test_fused_roi_multipathnet_small_all_towers(ctx, norm_split):
+@pytest.mark.parametrize("roi_impl", [0, 1, 2])
+def test_fused_roi_multipathnet_small_all_towers(ctx, roi_impl):
     """cfg 3 structure at reduced width: towers 0..3 = Foveal regions x1, x1.5, x2, x4 on conv5|conv4|conv3 with per-level
-    L2 normalise, both normalisation variants of the product kernel"""
+    L2 normalise; every implementation of the stage (0 = roi_pool_cluster_kernel, the default; 1 / 2 = the round-1 kernels)"""
     spec = models.vgg16_multipathnet(21, seed=11, width_div=4, fc_dim=256)
     m = mpn.Model(ctx, spec, max_rois=256, max_h=256, max_w=320)
-    ctx.set_option("roi_norm_split", norm_split)
+    ctx.set_option("roi_impl", roi_impl)
     try:
         rois = run_detect(m, spec, 160, 208, 128, 6, sharp=True)
         for t in range(len(spec.towers)):
             check_tower(spec, m, rois, t, slice(0, 128))
     finally:
-        ctx.set_option("roi_norm_split", -1)
+        ctx.set_option("roi_impl", -1)
         m.close()
 
 
-def test_fused_roi_full_size_cfg2(ctx):
+@pytest.mark.parametrize("roi_impl", [0, 1])
+def test_fused_roi_full_size_cfg2(ctx, roi_impl):
     """BASELINE configs[1]: VGG-16 600x800, R=1000, 7x7 bins on conv5 — every pooled value of the timed kernel, bit-exact"""
     spec = models.vgg16_fast_rcnn(21, seed=1234)
     m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
-    rois = run_detect(m, spec, 600, 800, 1000, 2, sharp=False)
-    check_tower(spec, m, rois, 0, slice(0, 1000))
-    m.close()
+    ctx.set_option("roi_impl", roi_impl)
+    try:
+        rois = run_detect(m, spec, 600, 800, 1000, 2, sharp=False)
+        check_tower(spec, m, rois, 0, slice(0, 1000))
+    finally:
+        ctx.set_option("roi_impl", -1)
+        m.close()
 
 
-@pytest.mark.parametrize("norm_split", [0, 1])
-def test_fused_roi_full_size_cfg3_all_towers(ctx, norm_split):
-    """BASELINE configs[2]: all five MultiPathNet towers at full size (regions leaving the image)"""
+def test_fused_roi_full_size_cfg3_all_towers(ctx):
+    """BASELINE configs[2]: all five MultiPathNet towers at full size (regions leaving the image), every
+    implementation of the stage against ONE oracle evaluation (the trunk is deterministic: same feature maps every run)"""
     spec = models.vgg16_multipathnet(81, seed=1234)
     m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
-    ctx.set_option("roi_norm_split", norm_split)
     try:
         rois = run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
-        for t in range(len(spec.towers)):
-            for rows in (slice(0, 200), slice(800, 1000)):          # 400 of the 1000 ROIs per tower: ~30 s of oracle time in all
-                check_tower(spec, m, rois, t, rows)
+        blocks = (slice(0, 200), slice(800, 1000))                  # 400 of the 1000 ROIs per tower: ~30 s of oracle time in all
+        refs = {(t, b.start): oracle_pooled(spec, m, rois, t, b) for t in range(len(spec.towers)) for b in blocks}
+        for impl in (0, 1, 2):
+            ctx.set_option("roi_impl", impl)
+            run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
+            for t in range(len(spec.towers)):
+                for b in blocks:
+                    check_tower(spec, m, rois, t, b, refs[(t, b.start)])
     finally:
-        ctx.set_option("roi_norm_split", -1)
+        ctx.set_option("roi_impl", -1)
         m.close()
 
 
