@@ -44,6 +44,10 @@ int64_t mpn_ctx_launch_count(const mpn_ctx *ctx);
 const char *mpn_version(void);
 /* run-time knobs of the product kernels, so that tests can cover every variant in one process; value < 0 restores the
  * default (the environment variable of the same meaning, else the built-in choice). Names:
+ *   "fc_w16"          numerics of the big per-ROI Linears (fc6 / fc7: K >= 2048, >= 1024 outputs), read when a model plans
+ *                     its heads: 1 (default) = weight as ONE fp16 plane scaled by a power of two, two tensor-core
+ *                     products per MAC (A_hi x W + A_lo x W); 0 = the three-product bf16 split every other layer uses.
+ *                     Environment: MPN_FC_W16.
  *   "roi_impl"        fused Foveal + ROI pooling kernel: 0 = roi_pool_cluster_kernel (default: 4-CTA clusters, the
  *                     L2 norm reduced over distributed shared memory), 1 = the round-1 kernel (one block stages a
  *                     normalised level's whole vector), 2 = the round-1 two-pass variant (sum-of-squares pre-pass +
@@ -245,6 +249,17 @@ int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, in
                              float score_thresh, float nms_thr, float *scores_dev,
                              float *bboxes_dev, int32_t *keep_idx_dev, int32_t *keep_counts_dev);
 
+/* ---- the detect tail after the network for a RANGE of classes (BASELINE configs[4], "NMS + BBoxNorm sweep": classes
+ * shard across GPUs): nn.BBoxNorm (modules/BBoxNorm.lua:18-32; mean4 / std4 NULL = none) + utils.convertFrom per class
+ * block (utils.lua:226-246) + clamp to [1,W0] x [1,H0] (Tester_FRCNN.lua:75-78) of deltas R x 4C against boxes R x 4
+ * -> bboxes R x 4C, then for the foreground classes c in [c_begin, c_end) (1 <= c < C): rows with scores[:, c] >
+ * score_thresh gathered and NMS'ed (Tester_FRCNN.lua:106-117). keep_idx (c_end - c_begin) x R proposal rows in emission
+ * order, keep_counts c_end - c_begin. Device buffers, stream-ordered.                                              */
+int mpn_post_detect_dev(mpn_ctx *ctx, const float *scores_dev, const float *deltas_dev, const float *boxes_dev, int64_t R,
+                        int32_t C, const float *mean4, const float *std4, float W0, float H0, float score_thresh,
+                        float nms_thr, int32_t c_begin, int32_t c_end, float *bboxes_dev, int32_t *keep_idx_dev,
+                        int32_t *keep_counts_dev);
+
 /* ---- after NMS, on the device --------------------------------------------------------------
  * Detection record of one image = the result of utils.keep_top_k (utils.lua:75-96; Tester:keepTopKPerImage,
  * Tester_FRCNN.lua:163-168, test_runner.lua:121) over the image's per-class NMS output, in a fixed size so that the
@@ -308,7 +323,8 @@ int mpn_model_set_conv_impl(mpn_model *m, int32_t impl);
 int mpn_model_last_flops(const mpn_model *m, double *trunk_flops, double *head_flops);
 
 /* standalone GEMM check entry (tests): C[M,N] = A[M,K] * B[N,K]^T + bias, fp32 host
- * buffers, computed with the same split-bf16 tcgen05 kernel the model uses.  */
+ * buffers, computed with the same split-bf16 tcgen05 kernel the model uses (impl 0), the CUDA-core fp32 check kernel
+ * (impl 1), or the fp16-weight two-product kernels of fc6 / fc7 (impl 2; needs N >= 1024).  */
 int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bias, int64_t M,
                    int64_t N, int64_t K, int32_t relu, int32_t impl, float *C);
 /* engine microbenchmark (diagnostics, tools/engine_sweep.py): times `iters` back-to-back launches of the tcgen05 engine on

@@ -121,6 +121,8 @@ SIGNATURES = {
     "mpn_model_detect_nms_wait": (C.c_int, [_vp, C.c_int32]),
     "mpn_model_detect_nms_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    "mpn_post_detect_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "mpn_pack_detections_dev": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int64, C.c_int32, _vp]),
     "mpn_pack_detections": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_int64, C.c_int32, _vp]),
     "mpn_select_boxes": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp]),

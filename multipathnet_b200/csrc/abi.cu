@@ -10,6 +10,8 @@ int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const in
 int mpn_nms_dense_launch(mpn_ctx *, const float *, int, float, int32_t *, int32_t *);
 int mpn_bbox_vote_launch(mpn_ctx *, const float *, int, const float *, int, float, float *);
 int mpn_pack_detections_launch(mpn_ctx *, const float *, const float *, int, const int32_t *, const int32_t *, int, int, float *);
+int mpn_gather_scored_range_launch(mpn_ctx *, const float *, const float *, int, int, int, int, float, float *, int32_t *, int32_t *);
+int mpn_bbox_norm_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *, const float *, const float *);
 int mpn_select_boxes_launch(mpn_ctx *, const float *, const float *, int64_t, int, const float *, const float *, float *);
 int mpn_foveal_launch(mpn_ctx *, const float *, int64_t, float *);
 int mpn_context_region_launch(mpn_ctx *, const float *, int64_t, float, float *);
@@ -21,6 +23,8 @@ int mpn_split_rows_launch(mpn_ctx *, const float *, int64_t, int64_t, int64_t, _
 int mpn_nchw_to_nhwc_split_launch(mpn_ctx *, const float *, int, int, int, int, DTensor &);
 int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
 int mpn_weight_permute_split_launch(mpn_ctx *, const float *, int64_t, int, int, int, __nv_bfloat16 *, __nv_bfloat16 *);
+int mpn_absmax(mpn_ctx *, const float *, int64_t, float *);
+int mpn_weight_permute_half_launch(mpn_ctx *, const float *, int64_t, int, int, int, float, void *);
 
 static std::string g_create_err;
 static std::mutex g_create_mu;
@@ -92,6 +96,7 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->scratch2) cudaFree(ctx->scratch2);
   if (ctx->scratch3) cudaFree(ctx->scratch3);
+  if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->sk_ws) cudaFree(ctx->sk_ws);
   if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   if (ctx->tl_min) cudaFree(ctx->tl_min);
@@ -118,6 +123,7 @@ int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : 
 int mpn_ctx_set_option(mpn_ctx *ctx, const char *name, int64_t value) {
   if (!ctx || !name) return MPN_ERR_ARG;
   if (!strcmp(name, "roi_norm_split")) { ctx->opt_roi_norm_split = value < 0 ? -1 : (value ? 1 : 0); return MPN_OK; }
+  if (!strcmp(name, "fc_w16")) { ctx->opt_fc_w16 = value < 0 ? -1 : (value ? 1 : 0); return MPN_OK; }
   if (!strcmp(name, "roi_impl")) {
     MPN_CHECK_ARG(ctx, value <= 2, "roi_impl: 0 = cluster kernel, 1 = legacy staged, 2 = legacy two-pass");
     ctx->opt_roi_impl = value < 0 ? -1 : (int)value; return MPN_OK;
@@ -280,6 +286,30 @@ int mpn_bbox_vote(mpn_ctx *ctx, const float *nms_boxes, int64_t K, const float *
   MPN_CUDA(ctx, cudaMemcpyAsync(res, a.at<float>(o_r), sizeof(float) * 5 * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPN_OK;
+}
+
+// ------------------------------------------------------------------ the detect tail for a class range (BASELINE configs[4])
+int mpn_post_detect_dev(mpn_ctx *ctx, const float *scores_dev, const float *deltas_dev, const float *boxes_dev, int64_t R, int32_t C,
+                        const float *mean4, const float *std4, float W0, float H0, float score_thresh, float nms_thr, int32_t c_begin,
+                        int32_t c_end, float *bboxes_dev, int32_t *keep_idx_dev, int32_t *keep_counts_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, scores_dev && deltas_dev && boxes_dev && bboxes_dev && keep_idx_dev && keep_counts_dev && R > 0 && C >= 2, "buffers missing");
+  MPN_CHECK_ARG(ctx, c_begin >= 1 && c_end <= C && c_begin < c_end, "class range must lie in [1, C)");
+  MPN_CHECK_ARG(ctx, (mean4 == nullptr) == (std4 == nullptr), "mean4 and std4 go together");
+  MPN_CHECK_ARG(ctx, R < (1ll << 31), "too many boxes");
+  const int nseg = c_end - c_begin;
+  // BBoxNorm + convertFrom + clamp of every class block (the decode is class-independent work: a rank that owns a class
+  // range still decodes all of it only once per call; bytes are negligible next to the NMS)
+  MPN_TRY(mpn_bbox_norm_decode_launch(ctx, deltas_dev, boxes_dev, R, C, 1, W0, H0, bboxes_dev, mean4, std4));
+  // gather + NMS workspaces for this class range: scratch slot 1
+  Arena a{ctx};
+  size_t o_sb = a.reserve(sizeof(float) * 5 * (size_t)nseg * R), o_src = a.reserve(sizeof(int32_t) * (size_t)nseg * R),
+         o_cnt = a.reserve(sizeof(int32_t) * (size_t)nseg);
+  MPN_TRY(a.commit());
+  MPN_TRY(mpn_gather_scored_range_launch(ctx, scores_dev, bboxes_dev, (int)R, C, c_begin, nseg, score_thresh, a.at<float>(o_sb),
+                                         a.at<int32_t>(o_src), a.at<int32_t>(o_cnt)));
+  return mpn_nms_launch(ctx, a.at<float>(o_sb), (int)R, nseg, a.at<int32_t>(o_cnt), a.at<int32_t>(o_src), nms_thr, keep_idx_dev, keep_counts_dev);
 }
 
 // ------------------------------------------------------------------ after NMS (post.cu)
@@ -606,7 +636,18 @@ int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bi
   p.m_invariant = 1;     // a Linear over independent rows: the result of a row must not depend on M
   p.y.f32 = a.at<float>(o_c); p.y.N = M; p.y.H = 1; p.y.W = 1; p.y.C = N; p.y.ld = N; p.y_f32_ld = N;
   if (impl == 1) { MPN_TRY(conv_ref_launch(ctx, p)); }
-  else { ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl)); }
+  else {
+    if (impl == 2) {      // the fp16-weight ("w16") kernels: B as ONE fp16 plane of B * 2^e
+      float amax = 0.f;
+      MPN_TRY(mpn_absmax(ctx, a.at<float>(o_b), (int64_t)nb, &amax));
+      int e = 0;
+      if (amax > 0.f) { (void)frexpf(amax, &e); e = 14 - e; }
+      const float sc = ldexpf(1.0f, e);
+      MPN_TRY(mpn_weight_permute_half_launch(ctx, a.at<float>(o_b), N, (int)K, 1, 1, sc, a.at<void>(o_bh)));
+      p.w16 = a.at<void>(o_bh); p.w16_inv_scale = 1.0f / sc; p.w_hi = p.w_lo = nullptr;
+    }
+    ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl));
+  }
   MPN_CUDA(ctx, cudaMemcpyAsync(C, a.at<float>(o_c), 4 * nc, cudaMemcpyDeviceToHost, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return MPN_OK;

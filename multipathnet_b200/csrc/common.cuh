@@ -22,6 +22,7 @@ struct mpn_ctx {
   void *scratch = nullptr; size_t scratch_bytes = 0;
   void *scratch2 = nullptr; size_t scratch2_bytes = 0;
   void *scratch3 = nullptr; size_t scratch3_bytes = 0;   // split-K partial accumulators
+  void *small_dev = nullptr;                               // 256 bytes for scalar reductions (mpn_absmax)
   // optional per-category kernel timing (bench.py roofline): CUDA events around every launch group
   int profiling = 0;
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -36,7 +37,7 @@ struct mpn_ctx {
   unsigned long long *tl_min = nullptr, *tl_max = nullptr; int tl_cap = 0, tl_n = 0, tl_on = 0;
   // the end-of-run all-gather (dist.cu): an ncclComm_t bound at run time, this ctx's rank / world, collectives issued
   // run-time knobs (mpn_ctx_set_option); -1 = take the environment default
-  int opt_roi_norm_split = -1, opt_roi_impl = -1;
+  int opt_roi_norm_split = -1, opt_roi_impl = -1, opt_fc_w16 = -1;
   void *dist_comm = nullptr; int dist_rank = 0, dist_world = 1; int64_t collectives = 0;
 };
 

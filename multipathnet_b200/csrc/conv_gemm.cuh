@@ -26,6 +26,10 @@ struct ConvProblem {
   // accumulator grouping, split-K count, no stream-K — so a row's result does not change with the number of rows in
   // the call (chunked forward == full forward, bit for bit: modules/test.lua:85-98, ImageDetect.lua:126-133)
   int m_invariant = 0;
+  // "w16" numerics for the big per-ROI Linears (fc6 / fc7): the weight as ONE fp16 plane scaled by a power of two
+  // (w16[co][k] = rn_fp16(w * scale), w16_inv_scale = 1 / scale), the activation still hi + lo bf16: two tensor-core
+  // products per MAC (A_hi x W + A_lo x W) instead of three; the epilogue multiplies the accumulator by w16_inv_scale.
+  const void *w16 = nullptr; float w16_inv_scale = 1.f;
   OutScatter scatter;              // n > 0: split-K plans only (conv_tc_launch rejects it otherwise)
   void *dbg = nullptr;             // diagnostics: device buffer of 16 x u64 pipeline-wait counters (tools/engine_sweep.py)
 };
@@ -43,6 +47,7 @@ struct ConvPlan {
   int streamk = 0;                 // 3x3 kernel: contiguous (tile, step) ranges per CTA pair instead of whole tiles (no wave quantisation)
   int mode = 0;                    // 0 generic implicit GEMM, 1 = 3x3/s1/p1 A-reuse kernel (conv3x3_tc_kernel)
   int flat = 0;                    // 1: 1x1/s1/p0 => pixels treated as one flat axis
+  int w16 = 0;                     // 1: B operand = one fp16 plane (ConvProblem::w16), 2 MMAs per k16
   int valid = 0;
 };
 

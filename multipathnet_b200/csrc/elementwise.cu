@@ -3,6 +3,8 @@
 // (+ integral-head mean), per-class scored-box gather, max/avg pooling on split-bf16
 // NHWC planes and layout converters. Each kernel cites the reference lines it restates.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <algorithm>
 #include <float.h>
 
 namespace {
@@ -302,6 +304,25 @@ __global__ void weight_permute_split_kernel(const float *__restrict__ w, int64_t
   oh[idx] = h; ol[idx] = l;
 }
 
+// max |w| of an fp32 array (bit pattern of a non-negative float orders like an unsigned integer); *out must start at 0
+__global__ void absmax_kernel(const float *__restrict__ w, int64_t n, unsigned *__restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
+}
+// Torch conv weight [Cout][Cin][kh][kw] fp32 -> [Cout][kh][kw][Cin] ONE fp16 plane of w * scale (scale = a power of two)
+__global__ void weight_permute_half_kernel(const float *__restrict__ w, int64_t Cout, int Cin, int kh, int kw, float scale,
+                                           __half *__restrict__ o) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t K = (int64_t)Cin * kh * kw;
+  if (idx >= Cout * K) return;
+  int64_t co = idx / K; int64_t k = idx % K;            // output order (r, q, ci)
+  int ci = (int)(k % Cin); int q = (int)((k / Cin) % kw); int r = (int)(k / ((int64_t)Cin * kw));
+  o[idx] = __float2half_rn(w[((co * Cin + ci) * kh + r) * kw + q] * scale);
+}
+
 }  // namespace
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -364,6 +385,30 @@ int mpn_gather_scored_launch(mpn_ctx *ctx, const float *scores_dev, const float 
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
+// per-class gather for the foreground classes [c_begin, c_begin + nseg) only (1-based class index): segment s = class
+// c_begin + s, capacity R each (class-sharded post-processing: BASELINE configs[4])
+int mpn_gather_scored_range_launch(mpn_ctx *ctx, const float *scores_dev, const float *bboxes_dev, int R, int C, int c_begin, int nseg,
+                                   float thresh, float *sb_dev, int32_t *src_idx_dev, int32_t *counts_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
+  if (nseg <= 0 || R <= 0) return MPN_OK;
+  // the kernel addresses class j = seg + 1 of row r as scores[r*C + j] / float4 bboxes[r*C + j]: shift both bases
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, gather_scored_kernel, dim3(nseg), dim3(256), 0, scores_dev + (c_begin - 1), bboxes_dev + 4 * (size_t)(c_begin - 1),
+                               R, C, thresh, sb_dev, src_idx_dev, counts_dev));
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+int mpn_bbox_norm_decode_launch(mpn_ctx *ctx, const float *deltas_dev, const float *boxes_dev, int64_t R, int C, int do_clamp, float W0,
+                                float H0, float *out_dev, const float *mean4, const float *std4) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_ELTWISE);
+  if (R <= 0) return MPN_OK;
+  const int has = (mean4 && std4) ? 1 : 0;
+  MPN_CUDA(ctx, mpn_launch_pdl(ctx, detect_tail_kernel, dim3(nblk(R * C, 256)), dim3(256), 0, (const float *)nullptr, R, C, 1, 0, (float *)nullptr, 0,
+      deltas_dev, boxes_dev, do_clamp, W0, H0, out_dev, has,
+      has ? make_float4(mean4[0], mean4[1], mean4[2], mean4[3]) : make_float4(0, 0, 0, 0),
+      has ? make_float4(std4[0], std4[1], std4[2], std4[3]) : make_float4(1, 1, 1, 1)));
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
 int mpn_maxpool_launch(mpn_ctx *ctx, const DTensor &in, int k, int s, int p, DTensor &out) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_POOL);
   int64_t total = out.N * out.H * out.W * (out.C / 8);
@@ -386,6 +431,25 @@ int mpn_split_rows_launch(mpn_ctx *ctx, const float *in_dev, int64_t rows, int64
                           __nv_bfloat16 *oh, __nv_bfloat16 *ol, int64_t ld_out) {
   if (rows * cols <= 0) return MPN_OK;
   split_rows_kernel<<<nblk(rows * cols, 256), 256, 0, ctx->stream>>>(in_dev, rows, cols, ld_in, oh, ol, ld_out);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+// max |w| (device array) -> host; synchronises the ctx stream (model-planning time only)
+int mpn_absmax(mpn_ctx *ctx, const float *w_dev, int64_t n, float *out_host) {
+  if (!ctx->small_dev) MPN_CUDA(ctx, cudaMalloc(&ctx->small_dev, 256));
+  unsigned *d = (unsigned *)ctx->small_dev;
+  MPN_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned), ctx->stream));
+  if (n > 0) { absmax_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(w_dev, n, d); MPN_LAUNCHED(ctx); }
+  unsigned bits = 0;
+  MPN_CUDA(ctx, cudaMemcpyAsync(&bits, d, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out_host, &bits, sizeof(float));
+  return MPN_OK;
+}
+int mpn_weight_permute_half_launch(mpn_ctx *ctx, const float *w_dev, int64_t Cout, int Cin, int kh, int kw, float scale, void *out) {
+  int64_t total = Cout * Cin * kh * kw;
+  if (total <= 0) return MPN_OK;
+  weight_permute_half_kernel<<<nblk(total, 256), 256, 0, ctx->stream>>>(w_dev, Cout, Cin, kh, kw, scale, (__half *)out);
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }

@@ -39,9 +39,10 @@ constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB per plane
 
 // CG = CTAs per MMA (tcgen05 cta_group): with CG=2 a CTA pair shares one B tile (each CTA stages BN/2 rows),
 // which cuts the operand bytes landing in each SM per MMA cycle from (128+BN) to (128+BN/2) rows x 128 B.
-__host__ __device__ constexpr int stage_bytes(int BN, int CG = 1) { return 2 * A_TILE_BYTES + 2 * (BN / CG) * BK * 2; }
-__host__ __device__ constexpr int num_stages(int BN, int CG = 1) {
-  return (196608 / stage_bytes(BN, CG)) > 4 ? 4 : (196608 / stage_bytes(BN, CG));
+// W16: the B operand is one fp16 plane instead of the bf16 hi/lo pair
+__host__ __device__ constexpr int stage_bytes(int BN, int CG = 1, bool W16 = false) { return 2 * A_TILE_BYTES + (W16 ? 1 : 2) * (BN / CG) * BK * 2; }
+__host__ __device__ constexpr int num_stages(int BN, int CG = 1, bool W16 = false) {
+  return (196608 / stage_bytes(BN, CG, W16)) > 4 ? 4 : (196608 / stage_bytes(BN, CG, W16));
 }
 // Accumulator rotation: back-to-back tcgen05.mma into the SAME TMEM accumulator serialise on its read-modify-write
 // latency (~117 cycles measured, independent of N), so for N <= 128 (32/64 cycles of tensor work per instruction) the
@@ -72,6 +73,7 @@ struct TcParams {
   unsigned long long *tl_min, *tl_max;   // diagnostics: %globaltimer stamps of this launch (4 + 4 u64) or null
   int b_prefetch;                // 3x3 kernel: fill the B ring with weight tiles before the programmatic-dependency wait
   int tma_store;                 // 3x3 kernel: the epilogue stages 64-channel slabs in shared memory and ships them with TMA tensor stores
+  float acc_scale;               // W16 kernels: accumulator * acc_scale (= 1 / the weight plane's power-of-two scale) before the bias; 1 otherwise
 };
 
 // Work walk of one scheduling unit (CTA or CTA pair). Plain: tiles unit, unit + num_units, ... each with all S steps.
@@ -269,10 +271,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with b_format F16 = 0: A bf16 (hi / lo plane) x B fp16 (kind::f16 takes the two 16-bit formats independently)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ---------------------------------------------------------------- epilogue of one accumulator tile (shared by both kernels)
 // warp q reads its 32 TMEM lanes 32 columns at a time; + bias (+ residual) (ReLU); re-split to bf16 hi/lo and/or fp32
-template <int BN, int CG>
+template <int BN, int CG, bool W16 = false>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tmem_base, int q, int a, int nt, bool row_ok,
                                                  long long pix, float *out_f32, int ch_first, long long ppix = -1,
                                                  const EpiSk sk = EpiSk(), int ch_lo = 0) {
@@ -315,6 +321,10 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
       }
     } else {
       tc_wait_ld();
+    }
+    if (W16) {                             // undo the weight plane's power-of-two scale (exact)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.acc_scale);
     }
     if (sk.role != SK_FULL) {
       // partial tiles live as [chunk][float4 j][128 rows] so that a warp's 32 rows are 512 contiguous bytes
@@ -431,7 +441,7 @@ constexpr int STG_POOL_BYTES = 2 * STG_POOL_PLANE;
 
 // full != 0: store the tile itself; pooled != 0: store its 2x2/2 max pool (8 x 4 pooled pixels per 16 x 8 patch; window =
 // lanes {l, l^1, l^8} of a warp, rows outside the image count as -inf: ceil-mode borders). Both may be set.
-template <int BN, int CG>
+template <int BN, int CG, bool W16 = false>
 __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CUtensorMap *tmYh, const CUtensorMap *tmYl,
                                                      const CUtensorMap *tmPh, const CUtensorMap *tmPl, uint8_t *stg, uint8_t *stg_pool,
                                                      uint32_t tmem_base, int q, int a, int nt, int ch_first, int ew, int w0,
@@ -463,6 +473,10 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
       }
     } else {
       tc_wait_ld();
+    }
+    if (W16) {                             // undo the weight plane's power-of-two scale (exact)
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * p.acc_scale);
     }
     if (sk.role == SK_FINISHER) {
       for (int t = 0; t < sk.ncont; ++t) {            // fixed order: pair u+1, u+2, ...
@@ -557,16 +571,17 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int BN, int CG>
+template <int BN, int CG, bool W16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
                     const TcParams p) {
-  constexpr int S = num_stages(BN, CG);
-  constexpr int STAGE = stage_bytes(BN, CG);
+  static_assert(!W16 || num_acc(BN) == 1, "W16 kernels accumulate both products into one TMEM accumulator");
+  constexpr int S = num_stages(BN, CG, W16);
+  constexpr int STAGE = stage_bytes(BN, CG, W16);
   constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;            // this CTA's share of the B tile
-  constexpr uint32_t IDESC = make_idesc(BM * CG, BN);         // cta_group::2: one 256 x BN MMA over the pair
+  constexpr uint32_t IDESC = W16 ? make_idesc_bf16_f16(BM * CG, BN) : make_idesc(BM * CG, BN);   // cta_group::2: one 256 x BN MMA over the pair
   constexpr uint32_t IDESC2 = make_idesc(BM * CG, 2 * BN <= 256 ? 2 * BN : BN);   // A_hi x [B_hi ; B_lo] (BN = 64 only)
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for SWIZZLE_128B tiles
@@ -648,13 +663,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               tma_load_4d_2sm(sa, &tmA_hi, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
               tma_load_4d_2sm(sa + A_TILE_BYTES, &tmA_lo, lbar, cb * BK, w_in0 + kwi, h_in0 + khi, n0);
               tma_load_2d_2sm(sa + 2 * A_TILE_BYTES, &tmB_hi, lbar, kb * BK, b_row0);
-              tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, lbar, kb * BK, b_row0);
+              if (!W16) tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, lbar, kb * BK, b_row0);
             } else {
               mbar_expect_tx(full_bar(s), (uint32_t)STAGE);
               tma_load_4d(sa, &tmA_hi, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
               tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), cb * BK, w_in0 + kwi, h_in0 + khi, n0);
               tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), kb * BK, b_row0);
-              tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, b_row0);
+              if (!W16) tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), kb * BK, b_row0);
             }
           }
           __syncwarp();
@@ -690,7 +705,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32B per k16 inside the swizzle atom
             const uint32_t later = ((kb - kb0) | k) != 0 ? 1u : 0u;     // 0 on the first k16 of the tile: zero-init
             const uint32_t f_lh = later, f_hh = (NACC >= 2) ? later : 1u, f_hl = (NACC == 3) ? later : 1u;
-            if (NACC == 3) {
+            if (W16) {
+              // two products per MAC: A_lo x W16 then A_hi x W16 (b_hi holds the single fp16 weight plane)
+              if (CG == 2) {
+                tc_mma_bf16_2sm(d_base, a_lo + adv, b_hi + adv, IDESC, later);
+                tc_mma_bf16_2sm(d_base, a_hi + adv, b_hi + adv, IDESC, 1u);
+              } else {
+                tc_mma_bf16(d_base, a_lo + adv, b_hi + adv, IDESC, later);
+                tc_mma_bf16(d_base, a_hi + adv, b_hi + adv, IDESC, 1u);
+              }
+            } else if (NACC == 3) {
               // narrow tiles are bound by the shared-memory read of A (4 KB per MMA): B_lo sits right behind B_hi, so
               // ONE 2*BN-wide MMA computes A_hi x [B_hi ; B_lo] and A is read twice per k16 instead of three times
               if (CG == 2) {
@@ -740,13 +764,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       mbar_wait(tfull_bar(a), aph);
       tc_fence_after();
       if (p.tma_store)       // plain split output: 64-channel slabs through shared memory + TMA tensor stores (box = the tile's patch)
-        tc_epilogue_tile_tma<BN, CG>(p, &tmY_hi, &tmY_lo, &tmY_hi, &tmY_lo, stg, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
+        tc_epilogue_tile_tma<BN, CG, W16>(p, &tmY_hi, &tmY_lo, &tmY_hi, &tmY_lo, stg, stg, tmem_base, q, a, nt, (warp - 2) >> 2, warp - 2,
                                      twi * p.tw, thi * p.th, tni * p.tn, row_ok, pix, EpiSk());
       if (p.tma_store && (BN % 64) != 0)       // BN = 240: the last 48 channels are not a whole slab: register-store path
-        tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2, -1, EpiSk(), (BN / 64) * 2);
+        tc_epilogue_tile<BN, CG, W16>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2, -1, EpiSk(), (BN / 64) * 2);
       else if (p.tma_store) {}
       else
-        tc_epilogue_tile<BN, CG>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
+        tc_epilogue_tile<BN, CG, W16>(p, tmem_base, q, a, nt, row_ok, pix, out_f32, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {                             // 4*CG arrivals (one per epilogue warp of the pair) free the buffer
@@ -1383,12 +1407,12 @@ inline bool tc_use_pdl() {
   return on != 0;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool W16 = false>
 int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
-  const int smem = num_stages(BN, CG) * stage_bytes(BN, CG) + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  constexpr int slot = (BN == 240 ? 6 : (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1));
+  const int smem = num_stages(BN, CG, W16) * stage_bytes(BN, CG, W16) + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int slot = W16 ? (18 + (BN == 240 ? 0 : 1) + 2 * (CG - 1)) : ((BN == 240 ? 6 : (BN == 256 ? 2 : (BN == 128 ? 1 : 0)) + 3 * (CG - 1)));
   if (!ctx->tc_attr_set[slot]) {     // per ctx (= per device): the attribute is per device function
-    MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MPN_CUDA(ctx, cudaFuncSetAttribute(conv_gemm_tc_kernel<BN, CG, W16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ctx->tc_attr_set[slot] = 1;
   }
   const int tiles_m = pl.tiles_img * pl.tiles_h * pl.tiles_w;
@@ -1409,7 +1433,7 @@ int launch_bn(mpn_ctx *ctx, const ConvPlan &pl, const TcParams &tp) {
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tp));
+  MPN_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_gemm_tc_kernel<BN, CG, W16>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, pl.tmY_hi, pl.tmY_lo, tp));
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
@@ -1485,7 +1509,8 @@ double conv_flops(const ConvProblem &p) {
 // (mpn_debug_plan: CPU tests pin the planner's choices for the BASELINE layers).
 static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, ConvPlan &pl, bool choose_only) {
   pl.valid = 0;
-  MPN_CHECK_ARG(ctx, choose_only || (p.x.hi && p.x.lo && p.w_hi && p.w_lo), "conv_tc: operands must be split-bf16");
+  MPN_CHECK_ARG(ctx, choose_only || (p.x.hi && p.x.lo && ((p.w_hi && p.w_lo) || p.w16)), "conv_tc: operands must be split-bf16 (or an fp16 weight plane)");
+  pl.w16 = p.w16 ? 1 : 0;
   MPN_CHECK_ARG(ctx, p.x.C % BK == 0, "conv_tc: Cin must be a multiple of 64");
   MPN_CHECK_ARG(ctx, p.x.ld % 8 == 0, "conv_tc: input pixel stride must be a multiple of 8 elements");
   MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
@@ -1538,6 +1563,7 @@ static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, C
           // (of 74 pairs) at 256 but 4 x 18 = 72 units at 240, each 6% shorter, and whole-tile K loops keep chunk invariance
           const int bn = bi == 0 ? 256 : (bi == 1 ? 240 : (bi == 2 ? 128 : 64));
           if (bn == 240 && !(pl.flat && cg == 2 && mode == 0 && p.Cout >= 1024)) continue;
+          if (pl.w16 && (bn < 240 || mode != 0)) continue;          // W16 kernels exist for the wide flat tiles only
           if (!p.m_invariant && bn > 64 && bn > ((p.Cout + 63) / 64) * 64) continue;   // do not pad N by more than one 64-block
           if (p.m_invariant && num_acc(bn) != (p.Cout > 128 ? 1 : (p.Cout > 64 ? 2 : 3))) continue;   // rounding must not depend on M
           if (mode == 1 && cg == 1 && bn == 256) continue;           // B ring would not fit beside the A ring
@@ -1546,7 +1572,8 @@ static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, C
           const long long slots = sm_count / cg;
           const long long rounds = (units + slots - 1) / slots;
           const double rows = mode ? (3.0 * 144 + 9.0 * bn / cg) : (double)taps * (128 + bn / cg);
-          const double cyc = std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
+          const double cyc = pl.w16 ? std::max((double)taps * 4.0 * bn, (double)taps * (256.0 + bn / cg) * 128.0 / 35.0)
+                                    : std::max((double)taps * 6.0 * bn, rows * 256.0 / 35.0);
           double cost = (double)rounds * cyc * cblocks;
           int sk = 0;
           if (mode == 1 && allow_sk && !p.m_invariant) {
@@ -1625,8 +1652,14 @@ static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, C
   const long long Ktot = (long long)p.kh * p.kw * p.x.C;
   cuuint64_t bd[2] = {(cuuint64_t)Ktot, (cuuint64_t)p.Cout}, bs[1] = {(cuuint64_t)Ktot * 2};
   cuuint32_t bb[2] = {BK, (cuuint32_t)(pl.BN / pl.CG)}, be[2] = {1, 1};   // each CTA of a pair stages BN/CG weight rows
-  MPN_TRY(encode_map(ctx, &pl.tmB_hi, p.w_hi, 2, bd, bs, bb, be));
-  MPN_TRY(encode_map(ctx, &pl.tmB_lo, p.w_lo, 2, bd, bs, bb, be));
+  if (pl.w16) {
+    MPN_CHECK_ARG(ctx, pl.mode == 0 && pl.flat && pl.splitk == 1 && pl.BN >= 240, "conv_tc: the fp16-weight path is for wide flat GEMMs without split-K");
+    MPN_TRY(encode_map(ctx, &pl.tmB_hi, p.w16, 2, bd, bs, bb, be));      // 16-bit elements: the TMA only moves bytes
+    pl.tmB_lo = pl.tmB_hi;
+  } else {
+    MPN_TRY(encode_map(ctx, &pl.tmB_hi, p.w_hi, 2, bd, bs, bb, be));
+    MPN_TRY(encode_map(ctx, &pl.tmB_lo, p.w_lo, 2, bd, bs, bb, be));
+  }
   pl.valid = 1;
   return MPN_OK;
 }
@@ -1653,6 +1686,7 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.pool_hi = tp.pool_lo = nullptr; tp.pool_ld = 0; tp.Hp = tp.Wp = 0;
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
   tp.tma_store = 0;      // decided below, once the pooled output (if any) is known
+  tp.acc_scale = pl.w16 ? p.w16_inv_scale : 1.f;
   tp.tl_min = tp.tl_max = nullptr;
   if (ctx->tl_on && ctx->tl_n < ctx->tl_cap) { tp.tl_min = ctx->tl_min + 4 * ctx->tl_n; tp.tl_max = ctx->tl_max + 4 * ctx->tl_n; ++ctx->tl_n; }
   { static const int bp = [] { const char *e = getenv("MPN_TC_BPREFETCH"); return (e && e[0] == '0') ? 0 : 1; }(); tp.b_prefetch = bp; }
@@ -1716,6 +1750,11 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
     }
     if (pl.CG == 2) return pl.BN == 256 ? launch_r3<256, 2>(ctx, pl, tp, tmP_hi, tmP_lo) : (pl.BN == 128 ? launch_r3<128, 2>(ctx, pl, tp, tmP_hi, tmP_lo) : launch_r3<64, 2>(ctx, pl, tp, tmP_hi, tmP_lo));
     return pl.BN == 128 ? launch_r3<128, 1>(ctx, pl, tp, tmP_hi, tmP_lo) : launch_r3<64, 1>(ctx, pl, tp, tmP_hi, tmP_lo);
+  }
+  if (pl.w16) {
+    if (pl.CG == 2) return pl.BN == 240 ? launch_bn<240, 2, true>(ctx, pl, tp) : launch_bn<256, 2, true>(ctx, pl, tp);
+    MPN_CHECK_ARG(ctx, pl.BN == 256, "conv_tc: single-CTA fp16-weight kernel exists for BN = 256 only");
+    return launch_bn<256, 1, true>(ctx, pl, tp);
   }
   if (pl.CG == 2) {
     switch (pl.BN) {

@@ -118,3 +118,46 @@ def test_streamk_schedule(ctx, Cin, H, W, Cout, monkeypatch):
     assert rel_err(a1, a0) < 2e-5      # another BN => another accumulator grouping
     ref = F.relu(F.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), torch.from_numpy(b).double(), padding=1)).float().numpy()
     assert rel_err(a1, ref) < TOL
+
+
+# ---- "w16" numerics of fc6 / fc7 (round 2): weight = ONE fp16 plane scaled by a power of two, two products per MAC ------
+def _w16_emulation(A, B, bias, relu):
+    """what the w16 kernels compute, in fp64: (A_hi + A_lo) @ fp16(B * 2^e)^T / 2^e (+ bias)(ReLU); the only difference
+    left to the GPU is its fp32 accumulation"""
+    a = torch.from_numpy(A)
+    hi = a.to(torch.bfloat16).float()
+    a2 = (hi + (a - hi).to(torch.bfloat16).float()).double()
+    amax = float(np.abs(B).max())
+    e = 14 - int(np.frexp(amax)[1])
+    b16 = (torch.from_numpy(B) * float(2.0 ** e)).to(torch.float16).double() / float(2.0 ** e)
+    y = a2 @ b16.t()
+    if bias is not None:
+        y = y + torch.from_numpy(bias).double()
+    return (F.relu(y) if relu else y).float().numpy()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1024, 2048), (100, 1024, 2048), (1000, 4096, 4096), (257, 2000, 2112), (500, 4096, 25088)])
+def test_gemm_w16(ctx, M, N, K):
+    """the mixed-format MMA (A bf16 hi / lo planes x B fp16) does what the numerics note says: equal to the fp64 emulation
+    of that arithmetic to fp32-accumulation accuracy, and within the weight plane's 2^-12 of the exact product"""
+    rng = np.random.default_rng(M + N + K)
+    A = np.maximum(rng.standard_normal((M, K)), 0).astype(np.float32)              # post-ReLU activations, like fc6 / fc7 inputs
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    B[0, :8] = [3.0, -2.5, 1e-9, -1e-9, 0.0, 1e-4, -7e-5, 2.0]                      # a wide dynamic range inside one tensor
+    bias = rng.standard_normal(N).astype(np.float32)
+    got = ctx.gemm_check(A, B, bias, relu=True, impl=2)
+    assert rel_err(got, _w16_emulation(A, B, bias, True)) < 3e-6
+    assert rel_err(got, _ref_gemm(A, B, bias, True)) < 3e-4
+
+
+def test_gemm_w16_row_chunk_invariance(ctx):
+    """chunked rows == unchunked, bit for bit, also across the CTA-pair / single-CTA plans (ImageDetect.lua:126-133)"""
+    rng = np.random.default_rng(5)
+    M, N, K = 1000, 4096, 2048
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    full = ctx.gemm_check(A, B, b, impl=2)
+    edges = [0, 100, 228, 229, 700, M]
+    parts = np.concatenate([ctx.gemm_check(A[a:z], B, b, impl=2) for a, z in zip(edges[:-1], edges[1:])])
+    assert np.array_equal(full, parts)
