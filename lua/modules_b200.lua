@@ -89,10 +89,23 @@ function ROIPooling:updateOutput(input)
    local data, rois = input[1], input[2]
    assert(data:nDimension() == 4 and rois:nDimension() == 2 and rois:size(2) == 5)
    local R, nC = rois:size(1), data:size(2)
-   local out = torch.FloatTensor(R, nC, self.H, self.W)
-   self.indices:resize(R, nC, self.H, self.W)
-   local d, r = data:float():contiguous(), rois:float():contiguous()
    local ctx = mpn.ctx()
+   if torch.type(data) == 'torch.CudaTensor' then
+      -- CudaTensors (the reference's inference path): device pointers straight into mpn_roi_pool_dev, stream-ordered on the
+      -- ctx's (= cutorch's default) stream: no host round trip (the reference's Foveal.lua:21-22,42 pattern is NOT reproduced)
+      local d, r = data:contiguous(), rois:contiguous()
+      self.output = self.output:typeAs(data):resize(R, nC, self.H, self.W)
+      self._indices_cuda = self._indices_cuda or torch.CudaIntTensor()
+      self._indices_cuda:resize(R, nC, self.H, self.W)
+      mpn.check(ctx, C.mpn_roi_pool_dev(ctx, mpn.fptr(d), d:size(1), nC, d:size(3), d:size(4), mpn.fptr(r), R, self.W, self.H,
+                                        self.spatial_scale, self.v2 and 2 or 1, mpn.fptr(self.output),
+                                        ffi.cast('int32_t*', self._indices_cuda:data())), 'mpn_roi_pool_dev')
+      self.indices = self._indices_cuda
+      return self.output
+   end
+   local out = torch.FloatTensor(R, nC, self.H, self.W)
+   self.indices = torch.IntTensor(R, nC, self.H, self.W)
+   local d, r = data:float():contiguous(), rois:float():contiguous()
    mpn.check(ctx, C.mpn_roi_pool(ctx, mpn.fptr(d), d:size(1), nC, d:size(3), d:size(4), mpn.fptr(r), R, self.W, self.H,
                                  self.spatial_scale, self.v2 and 2 or 1, mpn.fptr(out), ffi.cast('int32_t*', self.indices:data())),
              'mpn_roi_pool')
@@ -103,6 +116,7 @@ function ROIPooling:updateGradInput()
    error('inn.ROIPooling (B200 shim) is inference-only: train with the reference modules')
 end
 function ROIPooling:clearState()
-   self.indices:set()
+   self.indices = torch.IntTensor()
+   self._indices_cuda = nil
    return rparent.clearState(self)
 end

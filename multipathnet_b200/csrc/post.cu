@@ -71,10 +71,24 @@ pack_detections_kernel(const float *__restrict__ scores, const float *__restrict
         if (key != 0 && (key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255], 1);
       }
       __syncthreads();
-      if (tid == 0) {
-        int want = s_want, b = 255;
-        for (; b > 0; --b) { if (s_hist[b] >= want) break; want -= s_hist[b]; }
-        s_want = want; s_prefix = prefix | ((uint32_t)b << shift);
+      if (tid < 32) {
+        // bin holding the `want`-th largest key: suffix sums over the 256 bins, 8 bins per lane (bins 8*lane .. 8*lane+7),
+        // one warp scan instead of a serial walk (a single thread walking shared memory cost ~4 us per pass)
+        int c[8], own = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { c[e] = s_hist[tid * 8 + e]; own += c[e]; }
+        int suf = own;                                     // inclusive suffix sum over the lanes: keys in this lane's bins and above
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, suf, o); if (tid + o < 32) suf += v; }
+        const int above = suf - own;
+        const int want = s_want;
+        __syncwarp();
+        if (above < want && want <= suf) {                 // exactly one lane: the wanted key is in one of its 8 bins
+          int acc = above, b = tid * 8 + 7;
+#pragma unroll
+          for (int e = 7; e >= 0; --e) { if (acc + c[e] >= want) { b = tid * 8 + e; break; } acc += c[e]; }
+          s_want = want - acc; s_prefix = prefix | ((uint32_t)b << shift);
+        }
       }
       __syncthreads();
     }
@@ -86,10 +100,18 @@ pack_detections_kernel(const float *__restrict__ scores, const float *__restrict
     if (key != 0 && key >= thr_key) atomicAdd(&s_cnt[i / cand], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int j = 0; j < nseg; ++j) { const int c = s_cnt[j]; s_cnt[j] = acc; acc += c; }
-    s_total = acc;
+  if (tid < 32) {                                          // exclusive offsets over the classes: warp scan, 32 classes per round
+    int carry = 0;
+    for (int j0 = 0; j0 < nseg; j0 += 32) {
+      const int j = j0 + tid;
+      const int c = j < nseg ? s_cnt[j] : 0;
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += v; }
+      if (j < nseg) s_cnt[j] = carry + inc - c;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (tid == 0) s_total = carry;
   }
   __syncthreads();
   const int total = s_total;

@@ -102,3 +102,45 @@ def test_lua_blocks_balance():
             assert depth >= 0, f
         assert depth == 0, f"{os.path.basename(f)}: unbalanced blocks"
         assert src.count("(") == src.count(")") and src.count("{") == src.count("}") and src.count("[") == src.count("]"), f
+
+
+# ---- the fbcoco.ImageDetect contract: same class, same methods, same argument lists --------------------
+IMAGE_DETECT_API = {           # method -> argument names, as ImageDetect.lua:12,91,137,156 declares them
+    "__init": ["model", "transformer", "scale", "max_size"],
+    "memoryEfficientForward": ["model", "input", "bs", "recompute_features"],
+    "computeRawOutputs": ["im", "boxes", "min_images", "recompute_features"],
+    "detect": ["im", "boxes", "min_images", "recompute_features"],
+}
+
+
+def _methods(src, cls="ImageDetect"):
+    return {m.group(1): [a.strip() for a in m.group(2).split(",") if a.strip()]
+            for m in re.finditer(r"function\s+%s:([A-Za-z_]+)\s*\(([^)]*)\)" % cls, src)}
+
+
+def test_image_detect_keeps_the_reference_contract():
+    shim = _strip_lua(open(os.path.join(ROOT, "lua", "ImageDetect_b200.lua")).read())
+    assert "torch.class(''" in shim                                      # the class name string was blanked by _strip_lua
+    raw = open(os.path.join(ROOT, "lua", "ImageDetect_b200.lua")).read()
+    assert "torch.class('fbcoco.ImageDetect')" in raw
+    got = _methods(shim)
+    assert got == IMAGE_DETECT_API, got
+    ref_path = "/root/reference/ImageDetect.lua"
+    if os.path.exists(ref_path):                                         # the table above IS the reference's (checked where it is present)
+        assert _methods(_strip_lua(open(ref_path).read())) == IMAGE_DETECT_API
+    # the constructor keeps the nn module (Tester_FRCNN.lua:37-49 calls module:apply / module:forward / module.output on it)
+    assert re.search(r"self\.model\s*=\s*model\b", shim) and "model_desc.create(" in shim
+    # no C handle in a serialisable field: the cache is a weak-keyed table, dropped by clearState
+    assert re.search(r"handles\s*=\s*setmetatable\(\{\},\s*\{__mode\s*=\s*''\}\)", shim) and "handles[self] = nil" in shim
+    assert not re.search(r"self\.[A-Za-z_]*handle\s*=", shim)
+    # the CudaTensor path goes through the _dev entry points (no host round trip), the host path through mpn_model_detect
+    for fn in ("mpn_model_trunk_dev", "mpn_model_heads_dev", "mpn_model_detect", "mpn_model_trunk_image"):
+        assert "C." + fn in shim
+
+
+def test_tester_fast_path_wraps_without_editing_the_reference_file():
+    src = _strip_lua(open(os.path.join(ROOT, "lua", "Tester_b200.lua")).read())
+    assert "testOne_reference = Tester.testOne" in src and "function Tester:testOne(i)" in src
+    assert "C.mpn_model_detect_nms(" in src and "return testOne_reference(self, i)" in src
+    mods = _strip_lua(open(os.path.join(ROOT, "lua", "modules_b200.lua")).read())
+    assert "C.mpn_roi_pool_dev(" in mods and "C.mpn_roi_pool(" in mods   # CudaTensors stay on the device
