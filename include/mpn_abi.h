@@ -242,6 +242,28 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
                                 float score_thresh, float nms_thr, float *scores, float *bboxes,
                                 int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket);
 int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket);
+/* Tester_FRCNN:testOne with its test-time options (Tester_FRCNN.lua:54-139) in one stream-ordered pass, nothing but the
+ * inputs and the final results crossing the bus: pass 1 = detect on the proposals, clamped to the image (:72-78); passes
+ * 2..num_iter = detect on nn.SelectBoxes of the previous pass (:82-89; cached trunk features, not clamped, as the
+ * reference); use_rbox_scores: the scores of pass i + 1 with the boxes of pass i (:91-97); the joined rows (:99-100,
+ * n_out = R * (num_iter - use_rbox_scores)) are gathered per class with score > score_thresh and NMS'ed (:106-117);
+ * bbox_voting: utils.bbox_vote of every kept box over its class's gathered rows, scores raised to vote_score_pow
+ * (:118-124; 1 = untouched; other powers use the device powf, not libm's).
+ * Outputs (host, synchronous; any may be NULL): scores n_out x C, bboxes n_out x 4C (the joined raw outputs :138),
+ * keep_idx (C-1) x n_out rows into them in emission order, keep_counts C-1, voted (C-1) x n_out x 5 (row i of class j =
+ * the voted box of keep_idx[j][i]; required when bbox_voting).                                                      */
+typedef struct mpn_test_opts {
+  int32_t num_iter;          /* opt.test_num_iterative_loc (>= 1) */
+  int32_t use_rbox_scores;   /* opt.test_use_rbox_scores */
+  int32_t bbox_voting;       /* opt.test_bbox_voting */
+  float score_thresh;        /* Tester.thresh (-1.5, Tester_FRCNN.lua:50) */
+  float nms_thr;             /* opt.test_nms_threshold (0.3) */
+  float vote_thr;            /* opt.test_bbox_voting_nms_threshold (0.5) */
+  float vote_score_pow;      /* opt.test_bbox_voting_score_pow (1) */
+} mpn_test_opts;
+int mpn_model_test_one(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
+                       float im_scale, float W0, float H0, const mpn_test_opts *opts, float *scores, float *bboxes,
+                       int32_t *keep_idx, int32_t *keep_counts, float *voted);
 /* Same with every buffer resident on the device, fully asynchronous (the
  * throughput path: bench.py `value`). */
 int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W,

@@ -61,6 +61,12 @@ class CImageTransform(C.Structure):
         return t
 
 
+class CTestOpts(C.Structure):
+    """mpn_test_opts: the test-time options of Tester_FRCNN:testOne"""
+    _fields_ = [("num_iter", C.c_int32), ("use_rbox_scores", C.c_int32), ("bbox_voting", C.c_int32), ("score_thresh", C.c_float),
+                ("nms_thr", C.c_float), ("vote_thr", C.c_float), ("vote_score_pow", C.c_float)]
+
+
 class CModelDesc(C.Structure):
     _fields_ = [("n_trunk_layers", C.c_int32), ("trunk_layers", C.POINTER(CLayer)),
                 ("n_towers", C.c_int32), ("towers", C.POINTER(CTower)),
@@ -119,6 +125,8 @@ SIGNATURES = {
     "mpn_model_detect_nms_submit": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                               C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _i32p]),
     "mpn_model_detect_nms_wait": (C.c_int, [_vp, C.c_int32]),
+    "mpn_model_test_one": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.POINTER(CTestOpts),
+                                     _vp, _vp, _vp, _vp, _vp]),
     "mpn_model_detect_nms_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int64, C.c_float, C.c_float,
                                            C.c_float, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     "mpn_post_detect_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64, C.c_int32, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -616,6 +624,23 @@ class Model:
             self.h, _ptr(im), im.shape[1], im.shape[2], _ptr(b), n, float(im_scale), float(W0), float(H0),
             float(score_thresh), float(nms_thr), _ptr(scores), _ptr(bboxes), _ptr(keep), _ptr(counts)), "mpn_model_detect_nms")
         return scores, bboxes, [keep[j, : counts[j]].copy() for j in range(self.C - 1)]
+
+    def test_one(self, image_chw, boxes, im_scale: float, W0: float, H0: float, num_iter: int = 1, use_rbox_scores: bool = False,
+                 bbox_voting: bool = False, score_thresh: float = -1.5, nms_thr: float = 0.3, vote_thr: float = 0.5, vote_score_pow: float = 1.0):
+        """Tester_FRCNN:testOne on the device (mpn_model_test_one): -> (scores n_out x C, bboxes n_out x 4C,
+        [keep rows per class], [voted K_j x 5 per class] or None)"""
+        im, b = _f32(image_chw), _f32(boxes)
+        n = b.shape[0]
+        n_out = n * (num_iter - (1 if use_rbox_scores else 0))
+        o = CTestOpts(int(num_iter), int(bool(use_rbox_scores)), int(bool(bbox_voting)), float(score_thresh), float(nms_thr), float(vote_thr),
+                      float(vote_score_pow))
+        scores = np.empty((n_out, self.C), np.float32); bboxes = np.empty((n_out, 4 * self.C), np.float32)
+        keep = np.empty((self.C - 1, n_out), np.int32); counts = np.empty(self.C - 1, np.int32)
+        voted = np.empty((self.C - 1, n_out, 5), np.float32) if bbox_voting else None
+        self.ctx.check(self.ctx.lib.mpn_model_test_one(self.h, _ptr(im), im.shape[1], im.shape[2], _ptr(b), n, float(im_scale), float(W0), float(H0),
+                                                       C.byref(o), _ptr(scores), _ptr(bboxes), _ptr(keep), _ptr(counts), _ptr(voted)), "mpn_model_test_one")
+        keeps = [keep[j, :counts[j]].copy() for j in range(self.C - 1)]
+        return scores, bboxes, keeps, ([voted[j, :counts[j]].copy() for j in range(self.C - 1)] if bbox_voting else None)
 
     def detect_nms_submit(self, image_chw, boxes, im_scale: float, W0: float, H0: float, score_thresh: float = -1.5,
                           nms_thr: float = 0.3):

@@ -25,6 +25,7 @@ int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
 int mpn_weight_permute_split_launch(mpn_ctx *, const float *, int64_t, int, int, int, __nv_bfloat16 *, __nv_bfloat16 *);
 int mpn_absmax(mpn_ctx *, const float *, int64_t, float *);
 int mpn_weight_permute_half_launch(mpn_ctx *, const float *, int64_t, int, int, int, float, void *);
+int mpn_split_rows_f16_launch(mpn_ctx *, const float *, int64_t, int64_t, int64_t, __nv_bfloat16 *, __nv_bfloat16 *, int64_t);
 
 static std::string g_create_err;
 static std::mutex g_create_mu;
@@ -38,6 +39,28 @@ static int grow(mpn_ctx *ctx, void **p, size_t *have, size_t bytes, void **out) 
   }
   *out = *p;
   return MPN_OK;
+}
+int mpn_ovf_flag(mpn_ctx *ctx, unsigned **flag_dev) {
+  if (!ctx->ovf_dev) {
+    MPN_CUDA(ctx, cudaMalloc((void **)&ctx->ovf_dev, 256));
+    MPN_CUDA(ctx, cudaMemsetAsync(ctx->ovf_dev, 0, 256, ctx->stream));
+    MPN_CUDA(ctx, cudaHostAlloc((void **)&ctx->ovf_host, 64, cudaHostAllocDefault));
+    *ctx->ovf_host = 0;
+  }
+  *flag_dev = ctx->ovf_dev;
+  return MPN_OK;
+}
+int mpn_ovf_copy_async(mpn_ctx *ctx, cudaStream_t stream) {
+  if (!ctx->ovf_dev) return MPN_OK;
+  MPN_CUDA(ctx, cudaMemcpyAsync(ctx->ovf_host, ctx->ovf_dev, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+  return MPN_OK;
+}
+int mpn_ovf_test(mpn_ctx *ctx) {
+  if (!ctx->ovf_dev || !*ctx->ovf_host) return MPN_OK;
+  *ctx->ovf_host = 0;
+  MPN_CUDA(ctx, cudaMemsetAsync(ctx->ovf_dev, 0, sizeof(unsigned), ctx->stream));
+  return mpn_fail(ctx, MPN_ERR_STATE, "an activation left fp16's range (|x| > 65504 or NaN) in the fp16-plane path of fc6 / fc7: results of this call are "
+                                      "saturated; rerun with mpn_ctx_set_option(ctx, \"fc_w16\", 0) (or MPN_FC_W16=0) for the three-product bf16 path");
 }
 int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes, out); }
 int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out) { return grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, bytes, out); }
@@ -97,6 +120,8 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->scratch2) cudaFree(ctx->scratch2);
   if (ctx->scratch3) cudaFree(ctx->scratch3);
   if (ctx->small_dev) cudaFree(ctx->small_dev);
+  if (ctx->ovf_dev) cudaFree(ctx->ovf_dev);
+  if (ctx->ovf_host) cudaFreeHost(ctx->ovf_host);
   if (ctx->sk_ws) cudaFree(ctx->sk_ws);
   if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   if (ctx->tl_min) cudaFree(ctx->tl_min);
@@ -114,8 +139,9 @@ const char *mpn_last_error(const mpn_ctx *ctx) {
 int mpn_ctx_synchronize(mpn_ctx *ctx) {
   if (!ctx) return MPN_ERR_ARG;
   MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
 }
 
 int64_t mpn_ctx_launch_count(const mpn_ctx *ctx) { return ctx ? ctx->launches : -1; }
@@ -645,6 +671,8 @@ int mpn_gemm_check(mpn_ctx *ctx, const float *A, const float *B, const float *bi
       const float sc = ldexpf(1.0f, e);
       MPN_TRY(mpn_weight_permute_half_launch(ctx, a.at<float>(o_b), N, (int)K, 1, 1, sc, a.at<void>(o_bh)));
       p.w16 = a.at<void>(o_bh); p.w16_inv_scale = 1.0f / sc; p.w_hi = p.w_lo = nullptr;
+      MPN_TRY(mpn_split_rows_f16_launch(ctx, a.at<float>(o_a), M, K, K, a.at<__nv_bfloat16>(o_ah), a.at<__nv_bfloat16>(o_al), K));   // A as fp16 hi / lo planes
+      p.x.fmt = 1;
     }
     ConvPlan pl; MPN_TRY(conv_tc_plan(ctx, p, pl)); MPN_TRY(conv_tc_launch(ctx, p, pl));
   }

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -38,6 +39,9 @@ struct mpn_ctx {
   // the end-of-run all-gather (dist.cu): an ncclComm_t bound at run time, this ctx's rank / world, collectives issued
   // run-time knobs (mpn_ctx_set_option); -1 = take the environment default
   int opt_roi_norm_split = -1, opt_roi_impl = -1, opt_fc_w16 = -1;
+  // fp16 activation planes (fc6 / fc7 "w16" numerics): a value beyond fp16's range saturates AND raises this device flag;
+  // host-synchronous entry points copy it to the pinned word with their results and fail loudly (mpn_check_overflow)
+  unsigned *ovf_dev = nullptr; unsigned *ovf_host = nullptr;
   void *dist_comm = nullptr; int dist_rank = 0, dist_world = 1; int64_t collectives = 0;
 };
 
@@ -119,6 +123,11 @@ inline cudaError_t mpn_launch_pdl(mpn_ctx *ctx, void (*kern)(KArgs...), dim3 gri
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
+int mpn_ovf_flag(mpn_ctx *ctx, unsigned **flag_dev);          // the ctx's fp16-overflow flag (allocated on first use)
+// enqueue the copy of the flag to its pinned host word on `stream` (no-op without a flag) / after that stream was
+// synchronised: fail loudly if an fp16 activation plane saturated since the last test, and re-arm the flag
+int mpn_ovf_copy_async(mpn_ctx *ctx, cudaStream_t stream);
+int mpn_ovf_test(mpn_ctx *ctx);
 int mpn_scratch(mpn_ctx *ctx, size_t bytes, void **out);    // slot 1
 int mpn_scratch2(mpn_ctx *ctx, size_t bytes, void **out);   // slot 2
 int mpn_scratch3(mpn_ctx *ctx, size_t bytes, void **out);   // slot 3
@@ -141,6 +150,26 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t &hi2, 
   const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
   lo2 = *reinterpret_cast<const uint32_t *>(&l);
 }
+// ---- fp16 split planes (DTensor::fmt == 1): hi = rn_f16(x), lo = rn_f16(x - hi): 22 significant bits for |x| >= 2^-3,
+// an absolute 2^-24 below (fp16 subnormals), |x| <= 65504. Out-of-range (or NaN) inputs saturate and raise *ovf.
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t &hi2, uint32_t &lo2, unsigned *ovf) {
+  const float c0 = fminf(fmaxf(x0, -65504.f), 65504.f), c1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+  if (ovf && (c0 != x0 || c1 != x1)) atomicOr(ovf, 1u);
+  const __half2 h = __floats2half2_rn(c0, c1);
+  hi2 = *reinterpret_cast<const uint32_t *>(&h);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(c0 - hf.x, c1 - hf.y);
+  lo2 = *reinterpret_cast<const uint32_t *>(&l);
+}
+// one output pair in the tensor's plane format (fmt: 0 = bf16 hi/lo, 1 = fp16 hi/lo)
+__device__ __forceinline__ void split_x2(int fmt, float x0, float x1, uint32_t &hi2, uint32_t &lo2, unsigned *ovf) {
+  if (fmt) split_f16x2(x0, x1, hi2, lo2, ovf);
+  else split_bf16x2(x0, x1, hi2, lo2);
+}
+__device__ __forceinline__ float join_planes(int fmt, uint16_t hi, uint16_t lo) {
+  if (fmt) return __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
+  return __uint_as_float((uint32_t)hi << 16) + __uint_as_float((uint32_t)lo << 16);
+}
 __device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
   return __bfloat162float(hi) + __bfloat162float(lo);
 }
@@ -156,7 +185,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
 // A device tensor in the library's internal layout: NHWC, either split-bf16 planes
 // (hi, lo) or fp32, with a pixel stride `ld` (elements) so channel slices alias.
 struct DTensor {
-  __nv_bfloat16 *hi = nullptr, *lo = nullptr;
+  __nv_bfloat16 *hi = nullptr, *lo = nullptr;   // 16-bit planes: bf16 (fmt 0) or fp16 (fmt 1) bit patterns
+  int fmt = 0;
   float *f32 = nullptr;
   int64_t N = 0, H = 0, W = 0, C = 0, ld = 0;
   int64_t pixels() const { return N * H * W; }

@@ -188,6 +188,8 @@ conv_direct_3x3c3_o64_kernel(const float *__restrict__ x, int N, int H, int W, c
 struct RefParams {
   const __nv_bfloat16 *xh, *xl; long long xld; int N, H, W, Cin;
   const __nv_bfloat16 *wh, *wl;
+  const __half *w16; float w16_inv;        // "w16" layers: one scaled fp16 weight plane instead of wh / wl
+  int xfmt, ofmt; unsigned *ovf;           // plane formats of the input / output (0 = bf16 split, 1 = fp16 split)
   const float *bias; int Cout, kh, kw, stride, pad, relu, Ho, Wo;
   const __nv_bfloat16 *rh, *rl; long long rld;
   __nv_bfloat16 *oh, *ol; long long old_;
@@ -211,16 +213,21 @@ __global__ void __launch_bounds__(256) conv_ref_kernel(const RefParams p) {
       const long long xo = (((long long)n * p.H + hi) * p.W + wi) * p.xld;
       const long long wo_ = (long long)co * Ktot + (long long)(r * p.kw + q) * p.Cin;
       for (int ci = 0; ci < p.Cin; ++ci) {
-        const float a = join_bf16(p.xh[xo + ci], p.xl[xo + ci]);
-        const float b = join_bf16(p.wh[wo_ + ci], p.wl[wo_ + ci]);
+        const float a = join_planes(p.xfmt, __bfloat16_as_ushort(p.xh[xo + ci]), __bfloat16_as_ushort(p.xl[xo + ci]));
+        const float b = p.w16 ? __half2float(p.w16[wo_ + ci]) : join_bf16(p.wh[wo_ + ci], p.wl[wo_ + ci]);
         acc = fmaf(a, b, acc);
       }
     }
   }
+  if (p.w16) acc *= p.w16_inv;
   if (p.bias) acc += p.bias[co];
   if (p.rh) acc += join_bf16(p.rh[pix * p.rld + co], p.rl[pix * p.rld + co]);
   if (p.relu) acc = fmaxf(acc, 0.f);
-  if (p.oh) { __nv_bfloat16 h, l; split_bf16(acc, h, l); p.oh[pix * p.old_ + co] = h; p.ol[pix * p.old_ + co] = l; }
+  if (p.oh) {
+    uint32_t h2, l2;
+    split_x2(p.ofmt, acc, 0.f, h2, l2, p.ovf);
+    p.oh[pix * p.old_ + co] = __ushort_as_bfloat16((unsigned short)(h2 & 0xffffu)); p.ol[pix * p.old_ + co] = __ushort_as_bfloat16((unsigned short)(l2 & 0xffffu));
+  }
   if (p.of) p.of[pix * p.ofld + co] = acc;
 }
 
@@ -263,7 +270,10 @@ int conv_ref_launch(mpn_ctx *ctx, const ConvProblem &p) {
   MpnProfScope prof_scope__(ctx, MPN_CAT_CONV_TC);
   RefParams r;
   r.xh = p.x.hi; r.xl = p.x.lo; r.xld = p.x.ld; r.N = (int)p.x.N; r.H = (int)p.x.H; r.W = (int)p.x.W; r.Cin = (int)p.x.C;
-  r.wh = p.w_hi; r.wl = p.w_lo; r.bias = p.bias; r.Cout = p.Cout; r.kh = p.kh; r.kw = p.kw; r.stride = p.stride;
+  r.wh = p.w_hi; r.wl = p.w_lo; r.w16 = (const __half *)p.w16; r.w16_inv = p.w16_inv_scale;
+  r.xfmt = p.x.fmt; r.ofmt = p.y.fmt; r.ovf = nullptr;
+  if (p.y.fmt) MPN_TRY(mpn_ovf_flag(ctx, &r.ovf));
+  r.bias = p.bias; r.Cout = p.Cout; r.kh = p.kh; r.kw = p.kw; r.stride = p.stride;
   r.pad = p.pad; r.relu = p.relu; r.Ho = (int)p.y.H; r.Wo = (int)p.y.W;
   r.rh = p.res.hi; r.rl = p.res.lo; r.rld = p.res.ld;
   r.oh = p.y.hi; r.ol = p.y.lo; r.old_ = p.y.ld; r.of = p.y.f32; r.ofld = p.y_f32_ld;

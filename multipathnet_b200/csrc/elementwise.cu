@@ -244,13 +244,23 @@ __global__ void split_rows_kernel(const float *__restrict__ in, int64_t rows, in
   __nv_bfloat16 h, l; split_bf16(in[r * ld_in + c], h, l);
   oh[r * ld_out + c] = h; ol[r * ld_out + c] = l;
 }
-// split planes [rows][ld_in] -> fp32 [rows][cols] (hi + lo: exact in fp32)
+// split planes [rows][ld_in] (fmt 0 = bf16, 1 = fp16) -> fp32 [rows][cols] (hi + lo: exact in fp32)
 __global__ void join_rows_kernel(const __nv_bfloat16 *__restrict__ ih, const __nv_bfloat16 *__restrict__ il, int64_t rows,
-                                 int64_t cols, int64_t ld_in, float *__restrict__ out) {
+                                 int64_t cols, int64_t ld_in, int fmt, float *__restrict__ out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * cols) return;
   int64_t r = idx / cols, c = idx % cols;
-  out[idx] = join_bf16(ih[r * ld_in + c], il[r * ld_in + c]);
+  out[idx] = join_planes(fmt, __bfloat16_as_ushort(ih[r * ld_in + c]), __bfloat16_as_ushort(il[r * ld_in + c]));
+}
+// fp32 [rows][cols] -> fp16 split planes (tests of the "w16" kernels)
+__global__ void split_rows_f16_kernel(const float *__restrict__ in, int64_t rows, int64_t cols, int64_t ld_in,
+                                      __nv_bfloat16 *__restrict__ oh, __nv_bfloat16 *__restrict__ ol, int64_t ld_out, unsigned *ovf) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int64_t r = idx / cols, c = idx % cols;
+  uint32_t h2, l2;
+  split_f16x2(in[r * ld_in + c], 0.f, h2, l2, ovf);
+  oh[r * ld_out + c] = __ushort_as_bfloat16((unsigned short)(h2 & 0xffffu)); ol[r * ld_out + c] = __ushort_as_bfloat16((unsigned short)(l2 & 0xffffu));
 }
 // NCHW fp32 -> NHWC split planes
 __global__ void nchw_to_nhwc_split_kernel(const float *__restrict__ in, int N, int C, int H, int W,
@@ -453,10 +463,19 @@ int mpn_weight_permute_half_launch(mpn_ctx *ctx, const float *w_dev, int64_t Cou
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }
-int mpn_join_rows_launch(mpn_ctx *ctx, const __nv_bfloat16 *ih, const __nv_bfloat16 *il, int64_t rows, int64_t cols, int64_t ld_in,
-                         float *out_dev) {
+int mpn_split_rows_f16_launch(mpn_ctx *ctx, const float *in_dev, int64_t rows, int64_t cols, int64_t ld_in, __nv_bfloat16 *oh,
+                              __nv_bfloat16 *ol, int64_t ld_out) {
   if (rows * cols <= 0) return MPN_OK;
-  join_rows_kernel<<<nblk(rows * cols, 256), 256, 0, ctx->stream>>>(ih, il, rows, cols, ld_in, out_dev);
+  unsigned *ovf = nullptr;
+  MPN_TRY(mpn_ovf_flag(ctx, &ovf));
+  split_rows_f16_kernel<<<nblk(rows * cols, 256), 256, 0, ctx->stream>>>(in_dev, rows, cols, ld_in, oh, ol, ld_out, ovf);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+int mpn_join_rows_launch(mpn_ctx *ctx, const __nv_bfloat16 *ih, const __nv_bfloat16 *il, int64_t rows, int64_t cols, int64_t ld_in,
+                         int fmt, float *out_dev) {
+  if (rows * cols <= 0) return MPN_OK;
+  join_rows_kernel<<<nblk(rows * cols, 256), 256, 0, ctx->stream>>>(ih, il, rows, cols, ld_in, fmt, out_dev);
   MPN_LAUNCHED(ctx);
   return MPN_OK;
 }

@@ -74,6 +74,8 @@ struct TcParams {
   int b_prefetch;                // 3x3 kernel: fill the B ring with weight tiles before the programmatic-dependency wait
   int tma_store;                 // 3x3 kernel: the epilogue stages 64-channel slabs in shared memory and ships them with TMA tensor stores
   float acc_scale;               // W16 kernels: accumulator * acc_scale (= 1 / the weight plane's power-of-two scale) before the bias; 1 otherwise
+  int out_fmt;                   // plane format of out_hi / out_lo (and the pooled output): 0 = bf16 split, 1 = fp16 split
+  unsigned *ovf;                 // fp16-overflow flag of the ctx (out_fmt == 1)
 };
 
 // Work walk of one scheduling unit (CTA or CTA pair). Plain: tiles unit, unit + num_units, ... each with all S steps.
@@ -271,9 +273,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// same with b_format F16 = 0: A bf16 (hi / lo plane) x B fp16 (kind::f16 takes the two 16-bit formats independently)
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// same with a_format = b_format = F16 (0): fp16 x fp16 -> fp32. (kind::f16 wants A and B in the SAME 16-bit format: a
+// bf16 A with an fp16 B is an illegal instruction on sm_100a — measured, round 2 — so the W16 layers read fp16 planes.)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- epilogue of one accumulator tile (shared by both kernels)
@@ -388,7 +391,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
         if (p.out_hi && full8 && row_ok) {
           uint32_t oh[4], ol[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) split_bf16x2(f[2 * t], f[2 * t + 1], oh[t], ol[t]);      // packed cvt.rn.bf16x2.f32
+          for (int t = 0; t < 4; ++t) split_x2(p.out_fmt, f[2 * t], f[2 * t + 1], oh[t], ol[t], p.ovf);      // packed cvt.rn.{bf16x2,f16x2}.f32
           *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
         }
@@ -404,7 +407,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams &p, uint32_t tme
           if (ppix >= 0 && full8) {
             uint32_t oh[4], ol[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) split_bf16x2(f[2 * t], f[2 * t + 1], oh[t], ol[t]);
+            for (int t = 0; t < 4; ++t) split_x2(p.out_fmt, f[2 * t], f[2 * t + 1], oh[t], ol[t], p.ovf);
             *reinterpret_cast<uint4 *>(p.pool_hi + ppix * p.pool_ld + c) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
             *reinterpret_cast<uint4 *>(p.pool_lo + ppix * p.pool_ld + c) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
           }
@@ -524,7 +527,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
       for (int j = 0; j < 4; ++j) {
         uint32_t oh[4], ol[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) split_bf16x2(__uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t]);
+        for (int t = 0; t < 4; ++t) split_x2(p.out_fmt, __uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t], p.ovf);
         const int phys = (((ch & 1) * 4 + j) ^ (row & 7)) * 16;      // 128B swizzle: 16-byte chunk index XOR (row mod 8)
         *reinterpret_cast<uint4 *>(pr + phys) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
         *reinterpret_cast<uint4 *>(pr + STG_PLANE + phys) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
@@ -545,7 +548,7 @@ __device__ __forceinline__ void tc_epilogue_tile_tma(const TcParams &p, const CU
         for (int j = 0; j < 4; ++j) {
           uint32_t oh[4], ol[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) split_bf16x2(__uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t]);
+          for (int t = 0; t < 4; ++t) split_x2(p.out_fmt, __uint_as_float(v[8 * j + 2 * t]), __uint_as_float(v[8 * j + 2 * t + 1]), oh[t], ol[t], p.ovf);
           const int phys = (((ch & 1) * 4 + j) ^ (prow & 7)) * 16;
           *reinterpret_cast<uint4 *>(pp + phys) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4 *>(pp + STG_POOL_PLANE + phys) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
@@ -581,7 +584,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   constexpr int S = num_stages(BN, CG, W16);
   constexpr int STAGE = stage_bytes(BN, CG, W16);
   constexpr int B_TILE_BYTES = (BN / CG) * BK * 2;            // this CTA's share of the B tile
-  constexpr uint32_t IDESC = W16 ? make_idesc_bf16_f16(BM * CG, BN) : make_idesc(BM * CG, BN);   // cta_group::2: one 256 x BN MMA over the pair
+  constexpr uint32_t IDESC = W16 ? make_idesc_f16(BM * CG, BN) : make_idesc(BM * CG, BN);   // cta_group::2: one 256 x BN MMA over the pair
   constexpr uint32_t IDESC2 = make_idesc(BM * CG, 2 * BN <= 256 ? 2 * BN : BN);   // A_hi x [B_hi ; B_lo] (BN = 64 only)
   extern __shared__ uint8_t smem_raw[];
   // 1024B alignment for SWIZZLE_128B tiles
@@ -1511,6 +1514,7 @@ static int conv_tc_plan_impl(mpn_ctx *ctx, int sm_count, const ConvProblem &p, C
   pl.valid = 0;
   MPN_CHECK_ARG(ctx, choose_only || (p.x.hi && p.x.lo && ((p.w_hi && p.w_lo) || p.w16)), "conv_tc: operands must be split-bf16 (or an fp16 weight plane)");
   pl.w16 = p.w16 ? 1 : 0;
+  MPN_CHECK_ARG(ctx, choose_only || (p.x.fmt == 1) == (pl.w16 == 1), "conv_tc: fp16 activation planes go with the fp16 weight plane (and only with it)");
   MPN_CHECK_ARG(ctx, p.x.C % BK == 0, "conv_tc: Cin must be a multiple of 64");
   MPN_CHECK_ARG(ctx, p.x.ld % 8 == 0, "conv_tc: input pixel stride must be a multiple of 8 elements");
   MPN_CHECK_ARG(ctx, p.stride >= 1 && p.stride <= 2, "conv_tc: stride must be 1 or 2");
@@ -1687,6 +1691,11 @@ int conv_tc_launch(mpn_ctx *ctx, const ConvProblem &p, const ConvPlan &pl) {
   tp.streamk = 0; tp.sk_epoch = 0; tp.sk_ws = nullptr; tp.sk_flags = nullptr;
   tp.tma_store = 0;      // decided below, once the pooled output (if any) is known
   tp.acc_scale = pl.w16 ? p.w16_inv_scale : 1.f;
+  tp.out_fmt = p.y.fmt; tp.ovf = nullptr;
+  if (p.y.fmt) MPN_TRY(mpn_ovf_flag(ctx, &tp.ovf));
+  MPN_CHECK_ARG(ctx, !p.pool.hi || p.pool.fmt == p.y.fmt, "conv_tc: pooled output must share the output's plane format");
+  MPN_CHECK_ARG(ctx, !(p.y.fmt && pl.splitk > 1), "conv_tc: fp16 output planes are not written by the split-K reduce");
+  MPN_CHECK_ARG(ctx, !p.res.hi || p.res.fmt == 0, "conv_tc: residual inputs are bf16 split planes");
   tp.tl_min = tp.tl_max = nullptr;
   if (ctx->tl_on && ctx->tl_n < ctx->tl_cap) { tp.tl_min = ctx->tl_min + 4 * ctx->tl_n; tp.tl_max = ctx->tl_max + 4 * ctx->tl_n; ++ctx->tl_n; }
   { static const int bp = [] { const char *e = getenv("MPN_TC_BPREFETCH"); return (e && e[0] == '0') ? 0 : 1; }(); tp.b_prefetch = bp; }

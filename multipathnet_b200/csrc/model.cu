@@ -31,7 +31,10 @@ int mpn_detect_tail_launch(mpn_ctx *, const float *, int64_t, int, int, int, flo
 int mpn_gather_scored_launch(mpn_ctx *, const float *, const float *, int, int, float, float *, int32_t *, int32_t *);
 int mpn_nms_launch(mpn_ctx *, const float *, int, int, const int32_t *, const int32_t *, float, int32_t *, int32_t *);
 int mpn_pack_detections_launch(mpn_ctx *, const float *, const float *, int, const int32_t *, const int32_t *, int, int, float *);
-int mpn_join_rows_launch(mpn_ctx *, const __nv_bfloat16 *, const __nv_bfloat16 *, int64_t, int64_t, int64_t, float *);
+int mpn_select_boxes_launch(mpn_ctx *, const float *, const float *, int64_t, int, const float *, const float *, float *);
+int mpn_bbox_vote_batched_launch(mpn_ctx *, const float *, const int32_t *, const int32_t *, const int32_t *, const float *, const float *, int, int,
+                                 float, float, float *);
+int mpn_join_rows_launch(mpn_ctx *, const __nv_bfloat16 *, const __nv_bfloat16 *, int64_t, int64_t, int64_t, int, float *);
 int mpn_absmax(mpn_ctx *, const float *, int64_t, float *);
 int mpn_weight_permute_half_launch(mpn_ctx *, const float *, int64_t, int, int, int, float, void *);
 
@@ -114,6 +117,7 @@ struct mpn_model {
     std::unique_ptr<SplitBuf> pooled_buf; DTensor pooled; int ctot = 0;
     std::vector<LayerExec> layers; std::map<int, DTensor> slots; std::map<int, std::unique_ptr<SplitBuf>> bufs;
     int out_features = 0, col_off = 0;
+    std::map<int, int> slot_fmt;           // tower slot -> 1 when it is stored as fp16 hi / lo planes (input of a "w16" Linear)
   };
   std::vector<TowerExec> tex;
   SplitBuf concat_buf; int concat_width = 0;
@@ -130,6 +134,8 @@ struct mpn_model {
   PipeSlot pipe[2];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   int next_ticket = 0;
+  // ---- mpn_model_test_one: per-pass outputs, joined rows, per-class workspaces of capacity n_rows
+  DevBuf to_pass_scores, to_pass_bboxes, to_new_boxes, to_scores, to_bboxes, to_sb, to_src, to_counts, to_keep, to_keep_counts, to_voted;
   // ---- detection sink (mpn_model_set_detection_sink): every detect+NMS pass also packs the image's record
   float *sink = nullptr; int64_t sink_cap = 0, sink_n = 0; int sink_top_k = 100;
   ~mpn_model() {
@@ -210,15 +216,11 @@ int build_conv(mpn_model *m, LayerExec &e, const DTensor &in, DTensor out, int f
   p.y = out; p.y_f32_ld = out.ld;
   p.m_invariant = per_roi ? 1 : 0;
   MPN_CHECK_ARG(ctx, L.weight >= 0 && L.weight < (int)m->weights.size(), "conv layer without weight");
-  // the big per-ROI Linears (fc6 / fc7: K >= 2048, >= 1024 outputs) take the "w16" numerics: weight = one scaled fp16
-  // plane, two tensor-core products per MAC instead of three (profiles/r01i_split_emulation.md: 4.2e-4 / 5.7e-4 on the
-  // scores against the 1e-3 contract). mpn_ctx_set_option("fc_w16", 0) / MPN_FC_W16=0 keeps the three-product path.
-  static const int w16_env = [] { const char *e = getenv("MPN_FC_W16"); return (e && e[0] == '0') ? 0 : 1; }();
-  const int w16_on = ctx->opt_fc_w16 >= 0 ? ctx->opt_fc_w16 : w16_env;
-  const bool linear = per_roi && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.pad == 0 && in.H == 1 && in.W == 1;
-  bool w16 = w16_on && linear && in.C >= 2048 && L.cout >= 1024 && m->w_prepared[L.weight] != 1;
-  if (m->w_prepared[L.weight] == 2) w16 = true;                    // the fp32 copy is gone: the plane is what there is
-  MPN_CHECK_ARG(ctx, !(m->w_prepared[L.weight] == 2 && !linear), "weight was prepared as an fp16 plane for another layer shape");
+  // the big per-ROI Linears (fc6 / fc7) take the "w16" numerics — weight = one scaled fp16 plane, activation = fp16 hi / lo
+  // planes, two tensor-core products per MAC instead of three — exactly when plan_heads gave their input fp16 planes
+  const bool w16 = (in.fmt == 1);
+  MPN_CHECK_ARG(ctx, !w16 || (per_roi && L.kh == 1 && L.kw == 1 && L.stride == 1 && L.pad == 0 && in.H == 1 && in.W == 1),
+                "fp16 activation planes reached a layer that is not a per-ROI Linear");
   WeightDev &w = *m->weights[L.weight];
   if (w16) {
     MPN_TRY(prepare_conv_weight_w16(m, L.weight, L.cout, fc > 0 ? fc : L.cin, fc > 0 ? fh : L.kh, fc > 0 ? fw : L.kw));
@@ -420,7 +422,7 @@ int plan_heads(mpn_model *m, int64_t R) {
       RoiJob &j = m->jobs.j[m->jobs.n++];
       j.H = (int)f.H; j.W = (int)f.W; j.C = (int)f.C; j.scale = T.level_scale[l];
       j.region = T.region; j.out_hi = X.pooled.hi; j.out_lo = X.pooled.lo; j.out_ld = X.ctot; j.out_ch_off = ch_off;
-      j.normalize = T.normalize;
+      j.normalize = T.normalize; j.out_fmt = 0; j.ovf = nullptr; j.tower = (int)t;
       const mpn_model::Pyramid &P = m->pyramids[T.level_slot[l]];
       j.nlev = P.nlev;
       for (int k = 0; k < ROI_MAX_LEVELS; ++k) j.lv[k] = (const float *)P.lv[std::min(k, P.nlev - 1)]->p;
@@ -443,10 +445,54 @@ int plan_heads(mpn_model *m, int64_t R) {
       } else return mpn_fail(ctx, MPN_ERR_ARG, "unsupported tower layer kind");
       shp[L.out_slot] = out;
     }
+    // ---- plane formats of the tower's slots: the input of a "w16" Linear (fc6 / fc7: K >= 2048, >= 1024 outputs,
+    // profiles/r01i_split_emulation.md) is stored as fp16 hi / lo planes by whoever produces it (the ROI kernel for slot 0,
+    // the previous layer's epilogue otherwise); every reader of such a slot must be a w16 Linear (or the FLATTEN in front
+    // of one), else the slot stays bf16. mpn_ctx_set_option("fc_w16", 0) / MPN_FC_W16=0 switches the scheme off.
+    {
+      static const int w16_env = [] { const char *e = getenv("MPN_FC_W16"); return (e && e[0] == '0') ? 0 : 1; }();
+      const int w16_on = ctx->opt_fc_w16 >= 0 ? ctx->opt_fc_w16 : w16_env;
+      std::map<int, int> &fmt = X.slot_fmt;
+      fmt.clear();
+      auto wants = [&](const mpn_layer &L) {
+        if (!w16_on || L.kind != MPN_LAYER_CONV || L.residual_slot >= 0) return false;
+        const DTensor &in = shp[L.in_slot];
+        if (L.weight >= 0 && L.weight < (int)m->w_prepared.size() && m->w_prepared[L.weight] == 2) return true;   // the fp16 plane is what there is
+        return L.kh == 1 && L.kw == 1 && L.stride == 1 && L.pad == 0 && in.H == 1 && in.W == 1 && in.C >= 2048 && L.cout >= 1024 &&
+               L.weight >= 0 && L.weight < (int)m->w_prepared.size() && m->w_prepared[L.weight] != 1;
+      };
+      for (int i = 0; i < T.n_layers; ++i) { const mpn_layer &L = m->tower_layers[T.first_layer + i]; if (wants(L)) fmt[L.in_slot] = 1; }
+      for (int pass = 0; pass < 4; ++pass) {
+        for (int i = T.n_layers - 1; i >= 0; --i) {                 // a FLATTEN's output aliases its input
+          const mpn_layer &L = m->tower_layers[T.first_layer + i];
+          if (L.kind == MPN_LAYER_FLATTEN && fmt.count(L.out_slot) && fmt[L.out_slot]) fmt[L.in_slot] = 1;
+        }
+        for (int i = 0; i < T.n_layers; ++i) {                      // any other reader vetoes
+          const mpn_layer &L = m->tower_layers[T.first_layer + i];
+          auto veto = [&](int slot) {
+            if (!fmt.count(slot) || !fmt[slot]) return;
+            fmt[slot] = 0;
+            for (int j = 0; j < T.n_layers; ++j) {                  // and so does the alias on the other side of a FLATTEN
+              const mpn_layer &F = m->tower_layers[T.first_layer + j];
+              if (F.kind == MPN_LAYER_FLATTEN && (F.in_slot == slot || F.out_slot == slot)) { fmt[F.in_slot] = 0; fmt[F.out_slot] = 0; }
+            }
+          };
+          if (L.kind == MPN_LAYER_CONV) { if (!wants(L)) veto(L.in_slot); if (L.residual_slot >= 0) veto(L.residual_slot); }
+          else if (L.kind == MPN_LAYER_FLATTEN) { if (fmt.count(L.in_slot) && fmt[L.in_slot] && !(fmt.count(L.out_slot) && fmt[L.out_slot])) veto(L.in_slot); }
+          else veto(L.in_slot);
+        }
+        if (fmt.count(T.out_slot) && fmt[T.out_slot]) fmt[T.out_slot] = 0;      // the concat feeds the (three-product) heads
+      }
+    }
     MPN_CHECK_ARG(ctx, shp.count(T.out_slot), "tower out_slot undefined");
     const DTensor o = shp[T.out_slot];
     MPN_CHECK_ARG(ctx, o.H == 1 && o.W == 1, "tower output must be R x 1 x 1 x F");
     X.out_features = (int)o.C; X.col_off = width; width += (int)o.C;
+  }
+  for (int ji = 0; ji < m->jobs.n; ++ji) {                          // pooled tensors that feed a w16 Linear: fp16 planes
+    RoiJob &j = m->jobs.j[ji];
+    mpn_model::TowerExec &X = m->tex[j.tower];
+    if (X.slot_fmt.count(0) && X.slot_fmt[0]) { j.out_fmt = 1; MPN_TRY(mpn_ovf_flag(ctx, &j.ovf)); X.pooled.fmt = 1; }
   }
   m->concat_width = width;
   MPN_CHECK_ARG(ctx, width % 8 == 0, "concat width must be a multiple of 8");
@@ -482,6 +528,7 @@ int plan_heads(mpn_model *m, int64_t R) {
         MPN_TRY(buf->ensure(ctx, (size_t)(out.N * out.H * out.W * out.C)));
         DTensor v = make_split_view(*buf, out.N, out.H, out.W, out.C); out = v;
       }
+      out.fmt = (X.slot_fmt.count(L.out_slot) && X.slot_fmt[L.out_slot]) ? 1 : 0;
       if (L.kind == MPN_LAYER_CONV) {
         const bool from_flat = (L.in_slot == flat_slot) && L.kh == 1 && L.kw == 1;
         MPN_TRY(build_conv(m, e, in, out, from_flat ? flat_h : 0, from_flat ? flat_w : 0, from_flat ? flat_c : 0, /*per_roi=*/true));
@@ -753,13 +800,15 @@ int mpn_model_heads(mpn_model *m, const float *rois, int64_t R, float *cls_out, 
   MPN_TRY(mpn_model_heads_dev(m, (const float *)m->rois_dev.p, R, (float *)m->scores_dev.p, nullptr));
   if (cls_out) MPN_CUDA(ctx, cudaMemcpyAsync(cls_out, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, ctx->stream));
   if (bbox_out) MPN_CUDA(ctx, cudaMemcpyAsync(bbox_out, m->bbox_raw.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
 }
 
-// shared tail: heads -> scores (softmax / integral mean) -> decode (+clamp) [-> gather -> NMS]
-static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, float im_scale, int do_nms, float W0,
-                           float H0, float score_thresh, float nms_thr) {
+// one detect pass on the cached trunk features: project_im_rois -> heads -> scores (softmax / integral mean) | BBoxNorm +
+// decode (+ clamp) into caller-chosen buffers (ImageDetect.lua:161-192 after getImages; Tester_FRCNN.lua:75-78 clamp)
+static int run_detect_pass(mpn_model *m, const float *boxes_dev, int64_t R, float im_scale, int do_clamp, float W0, float H0,
+                           float *scores_dst, float *bboxes_dst) {
   mpn_ctx *ctx = m->ctx;
   const int C = m->d.num_classes, K = (int)m->cls_heads.size();
   MPN_TRY(ensure_heads(m, R));
@@ -769,9 +818,17 @@ static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, floa
   // class_values: softmax unless model.noSoftMax; an integral head IS its mean of softmaxes (noSoftMax=true).
   // One launch: softmax (+mean) | BBoxNorm + decode (+ clamp to the image for the NMS path, Tester_FRCNN.lua:75-78)
   const int do_softmax = (K > 1) ? 1 : (m->d.no_softmax ? 0 : 1);
-  MPN_TRY(mpn_detect_tail_launch(ctx, (const float *)m->cls_logits.p, R, C, K, do_softmax, (float *)m->scores_dev.p,
-                                 (const float *)m->bbox_raw.p, boxes_dev, do_nms, W0, H0, (float *)m->bboxes_dev.p,
-                                 m->d.has_bbox_norm ? 1 : 0, m->d.bbox_mean, m->d.bbox_std));
+  return mpn_detect_tail_launch(ctx, (const float *)m->cls_logits.p, R, C, K, do_softmax, scores_dst, (const float *)m->bbox_raw.p, boxes_dev,
+                                do_clamp, W0, H0, bboxes_dst, m->d.has_bbox_norm ? 1 : 0, m->d.bbox_mean, m->d.bbox_std);
+}
+
+// shared tail: heads -> scores (softmax / integral mean) -> decode (+clamp) [-> gather -> NMS]
+static int detect_tail_dev(mpn_model *m, const float *boxes_dev, int64_t R, float im_scale, int do_nms, float W0,
+                           float H0, float score_thresh, float nms_thr) {
+  mpn_ctx *ctx = m->ctx;
+  const int C = m->d.num_classes;
+  MPN_TRY(ensure_heads(m, R));
+  MPN_TRY(run_detect_pass(m, boxes_dev, R, im_scale, do_nms, W0, H0, (float *)m->scores_dev.p, (float *)m->bboxes_dev.p));
   if (do_nms) {
     MPN_TRY(mpn_gather_scored_launch(ctx, (const float *)m->scores_dev.p, (const float *)m->bboxes_dev.p, (int)R, C,
                                      score_thresh, (float *)m->sb_dev.p, (int32_t *)m->src_idx_dev.p, (int32_t *)m->counts_dev.p));
@@ -810,8 +867,9 @@ int mpn_model_detect(mpn_model *m, const float *image, int32_t H, int32_t W, con
   MPN_TRY(detect_tail_dev(m, (const float *)m->boxes_dev.p, R, im_scale, 0, 0.f, 0.f, 0.f, 0.f));
   if (scores) MPN_CUDA(ctx, cudaMemcpyAsync(scores, m->scores_dev.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToHost, ctx->stream));
   if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, m->bboxes_dev.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
 }
 
 int mpn_model_detect_nms_dev(mpn_model *m, const float *image_dev, int32_t H, int32_t W, const float *boxes_dev,
@@ -850,8 +908,9 @@ int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W,
   if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, m->bboxes_dev.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
   if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, m->keep_idx_dev.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToHost, ctx->stream));
   if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, m->keep_counts_dev.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
 }
 
 int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
@@ -894,6 +953,7 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
   if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, q.bboxes.p, sizeof(float) * (size_t)R * 4 * C, cudaMemcpyDeviceToHost, m->s_d2h));
   if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, q.keep_idx.p, sizeof(int32_t) * (size_t)(C - 1) * R, cudaMemcpyDeviceToHost, m->s_d2h));
   if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, q.keep_counts.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, m->s_d2h));
+  MPN_TRY(mpn_ovf_copy_async(ctx, m->s_d2h));
   MPN_CUDA(ctx, cudaEventRecord(q.done, m->s_d2h));
   q.busy = true; q.ticket = m->next_ticket;
   *ticket = m->next_ticket++;
@@ -908,7 +968,63 @@ int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket) {
   MPN_CHECK_ARG(ctx, ticket >= 0 && q.busy && q.ticket == ticket, "unknown or already completed ticket");
   MPN_CUDA(ctx, cudaEventSynchronize(q.done));
   q.busy = false;
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
+}
+
+// Tester_FRCNN:testOne (Tester_FRCNN.lua:54-139) entirely on the device: see include/mpn_abi.h
+int mpn_model_test_one(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R, float im_scale, float W0,
+                       float H0, const mpn_test_opts *o, float *scores, float *bboxes, int32_t *keep_idx, int32_t *keep_counts, float *voted) {
+  if (!m || !o) return MPN_ERR_ARG;
+  mpn_ctx *ctx = m->ctx;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, image && boxes && R > 0, "image/boxes missing");
+  MPN_CHECK_ARG(ctx, o->num_iter >= 1 && o->num_iter <= 8, "num_iter must be in 1..8");
+  MPN_CHECK_ARG(ctx, !o->use_rbox_scores || o->num_iter > 1, "test_use_rbox_scores needs test_num_iterative_loc > 1 (Tester_FRCNN.lua:92)");
+  MPN_CHECK_ARG(ctx, !o->bbox_voting || voted, "bbox voting needs the `voted` output");
+  const int C = m->d.num_classes, n_it = o->num_iter;
+  const int64_t n_out = R * (n_it - (o->use_rbox_scores ? 1 : 0));        // rows of the joined outputs
+  MPN_CHECK_ARG(ctx, n_out < (1ll << 30), "too many rows");
+  const size_t bs = sizeof(float) * (size_t)R * C, bb = sizeof(float) * (size_t)R * 4 * C;
+  MPN_TRY(m->image_dev.ensure(ctx, sizeof(float) * 3 * (size_t)H * W));
+  MPN_TRY(m->boxes_dev.ensure(ctx, sizeof(float) * 4 * (size_t)R));
+  MPN_TRY(m->to_pass_scores.ensure(ctx, bs * n_it)); MPN_TRY(m->to_pass_bboxes.ensure(ctx, bb * n_it));
+  MPN_TRY(m->to_new_boxes.ensure(ctx, sizeof(float) * 4 * (size_t)R));
+  MPN_TRY(m->to_scores.ensure(ctx, sizeof(float) * (size_t)n_out * C)); MPN_TRY(m->to_bboxes.ensure(ctx, sizeof(float) * (size_t)n_out * 4 * C));
+  MPN_TRY(m->to_sb.ensure(ctx, sizeof(float) * 5 * (size_t)(C - 1) * n_out)); MPN_TRY(m->to_src.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * n_out));
+  MPN_TRY(m->to_counts.ensure(ctx, sizeof(int32_t) * (size_t)C)); MPN_TRY(m->to_keep.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * n_out));
+  MPN_TRY(m->to_keep_counts.ensure(ctx, sizeof(int32_t) * (size_t)C));
+  if (o->bbox_voting) MPN_TRY(m->to_voted.ensure(ctx, sizeof(float) * 5 * (size_t)(C - 1) * n_out));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->image_dev.p, image, sizeof(float) * 3 * (size_t)H * W, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->boxes_dev.p, boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, ctx->stream));
+  MPN_TRY(mpn_model_trunk_dev(m, (const float *)m->image_dev.p, H, W));
+  auto ps = [&](int it) { return (float *)((char *)m->to_pass_scores.p + bs * it); };
+  auto pb = [&](int it) { return (float *)((char *)m->to_pass_bboxes.p + bb * it); };
+  // pass 1 on the proposals, clamped (:72-78); passes 2..n on nn.SelectBoxes of the previous pass, cached features, NOT clamped (:82-89)
+  MPN_TRY(run_detect_pass(m, (const float *)m->boxes_dev.p, R, im_scale, 1, W0, H0, ps(0), pb(0)));
+  for (int it = 1; it < n_it; ++it) {
+    MPN_TRY(mpn_select_boxes_launch(ctx, ps(it - 1), pb(it - 1), R, C, nullptr, nullptr, (float *)m->to_new_boxes.p));
+    MPN_TRY(run_detect_pass(m, (const float *)m->to_new_boxes.p, R, im_scale, 0, 0.f, 0.f, ps(it), pb(it)));
+  }
+  // joinTable (:99-100); with rbox scores the scores of pass i + 1 go with the boxes of pass i (:91-97)
+  const int s0 = o->use_rbox_scores ? 1 : 0, n_blocks = n_it - s0;
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->to_scores.p, ps(s0), bs * n_blocks, cudaMemcpyDeviceToDevice, ctx->stream));
+  MPN_CUDA(ctx, cudaMemcpyAsync(m->to_bboxes.p, pb(0), bb * n_blocks, cudaMemcpyDeviceToDevice, ctx->stream));
+  MPN_TRY(mpn_gather_scored_launch(ctx, (const float *)m->to_scores.p, (const float *)m->to_bboxes.p, (int)n_out, C, o->score_thresh,
+                                   (float *)m->to_sb.p, (int32_t *)m->to_src.p, (int32_t *)m->to_counts.p));
+  MPN_TRY(mpn_nms_launch(ctx, (const float *)m->to_sb.p, (int)n_out, C - 1, (const int32_t *)m->to_counts.p, (const int32_t *)m->to_src.p,
+                         o->nms_thr, (int32_t *)m->to_keep.p, (int32_t *)m->to_keep_counts.p));
+  if (o->bbox_voting)
+    MPN_TRY(mpn_bbox_vote_batched_launch(ctx, (const float *)m->to_sb.p, (const int32_t *)m->to_counts.p, (const int32_t *)m->to_keep.p,
+                                         (const int32_t *)m->to_keep_counts.p, (const float *)m->to_scores.p, (const float *)m->to_bboxes.p, C,
+                                         (int)n_out, o->vote_thr, o->vote_score_pow, (float *)m->to_voted.p));
+  if (scores) MPN_CUDA(ctx, cudaMemcpyAsync(scores, m->to_scores.p, sizeof(float) * (size_t)n_out * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (bboxes) MPN_CUDA(ctx, cudaMemcpyAsync(bboxes, m->to_bboxes.p, sizeof(float) * (size_t)n_out * 4 * C, cudaMemcpyDeviceToHost, ctx->stream));
+  if (keep_idx) MPN_CUDA(ctx, cudaMemcpyAsync(keep_idx, m->to_keep.p, sizeof(int32_t) * (size_t)(C - 1) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  if (keep_counts) MPN_CUDA(ctx, cudaMemcpyAsync(keep_counts, m->to_keep_counts.p, sizeof(int32_t) * (size_t)(C - 1), cudaMemcpyDeviceToHost, ctx->stream));
+  if (voted && o->bbox_voting) MPN_CUDA(ctx, cudaMemcpyAsync(voted, m->to_voted.p, sizeof(float) * 5 * (size_t)(C - 1) * n_out, cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
+  MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return mpn_ovf_test(ctx);
 }
 
 int mpn_model_set_detection_sink(mpn_model *m, float *records_dev, int64_t capacity, int32_t top_k) {
@@ -940,10 +1056,11 @@ int mpn_model_get_pooled(mpn_model *m, int32_t tower, int64_t r0, int64_t n, flo
   MPN_CHECK_ARG(ctx, r0 >= 0 && n > 0 && r0 + n <= t.N && capacity >= n * row, "row range outside the pooled tensor, or buffer too small");
   void *tmp = nullptr;
   MPN_TRY(mpn_scratch(ctx, sizeof(float) * (size_t)(n * row), &tmp));
-  MPN_TRY(mpn_join_rows_launch(ctx, t.hi + r0 * row, t.lo + r0 * row, n, row, row, (float *)tmp));
+  MPN_TRY(mpn_join_rows_launch(ctx, t.hi + r0 * row, t.lo + r0 * row, n, row, row, t.fmt, (float *)tmp));
   MPN_CUDA(ctx, cudaMemcpyAsync(out, tmp, sizeof(float) * (size_t)(n * row), cudaMemcpyDeviceToHost, ctx->stream));
+  MPN_TRY(mpn_ovf_copy_async(ctx, ctx->stream));
   MPN_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return MPN_OK;
+  return mpn_ovf_test(ctx);
 }
 
 int mpn_model_get_trunk_slot(mpn_model *m, int32_t slot, float *out_nchw, int64_t capacity, int32_t *C, int32_t *H,

@@ -777,6 +777,68 @@ bbox_vote_kernel(const float *__restrict__ nms_boxes, int K, const float *__rest
 }
 }  // namespace
 
+// Batched form for Tester_FRCNN:testOne on the device (Tester_FRCNN.lua:118-124): block (i, seg) votes the i-th NMS box of
+// class seg + 1 — row keep_idx[seg][i] of the detect outputs — over the class's gathered rows sb[seg][0 .. counts[seg])
+// with their scores raised to score_pow (opt.test_bbox_voting_score_pow; 1 = untouched, the only bit-exact setting:
+// powf is not libm's). Same sequential accumulation as bbox_vote_kernel. res: nseg x cap x 5.
+namespace {
+__global__ void __launch_bounds__(256)
+bbox_vote_batched_kernel(const float *__restrict__ sb, const int32_t *__restrict__ counts, const int32_t *__restrict__ keep_idx,
+                         const int32_t *__restrict__ keep_counts, const float *__restrict__ scores, const float *__restrict__ bboxes,
+                         int C, int cap, float thr, float score_pow, float *__restrict__ res) {
+  const int seg = blockIdx.y, i = blockIdx.x;
+  if (i >= keep_counts[seg]) return;
+  __shared__ unsigned char s_sel[256];
+  const int row = keep_idx[(size_t)seg * cap + i], N = counts[seg];
+  const float4 nbx = reinterpret_cast<const float4 *>(bboxes)[(size_t)row * C + seg + 1];
+  const float nscore = scores[(size_t)row * C + seg + 1];
+  const float *seg_sb = sb + (size_t)seg * cap * 5;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f, acc4 = 0.f;
+  for (int base = 0; base < N; base += 256) {
+    const int j = base + threadIdx.x;
+    unsigned char sel = 0;
+    if (j < N) {
+      const float *o = seg_sb + (size_t)j * 5;
+      sel = (iou_ref(o[0], o[1], o[2], o[3], nbx.x, nbx.y, nbx.z, nbx.w) > thr) ? 1 : 0;
+    }
+    s_sel[threadIdx.x] = sel;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int lim = min(256, N - base);
+      for (int t = 0; t < lim; ++t) {
+        if (s_sel[t]) {
+          const float *o = seg_sb + (size_t)(base + t) * 5;
+          const float s = score_pow == 1.f ? o[4] : powf(o[4], score_pow);
+          acc0 = __fadd_rn(acc0, __fmul_rn(o[0], s));
+          acc1 = __fadd_rn(acc1, __fmul_rn(o[1], s));
+          acc2 = __fadd_rn(acc2, __fmul_rn(o[2], s));
+          acc3 = __fadd_rn(acc3, __fmul_rn(o[3], s));
+          acc4 = __fadd_rn(acc4, s);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float *r = res + ((size_t)seg * cap + i) * 5;
+    r[0] = __fdiv_rn(acc0, acc4); r[1] = __fdiv_rn(acc1, acc4);
+    r[2] = __fdiv_rn(acc2, acc4); r[3] = __fdiv_rn(acc3, acc4);
+    r[4] = nscore;
+  }
+}
+}  // namespace
+
+int mpn_bbox_vote_batched_launch(mpn_ctx *ctx, const float *sb_dev, const int32_t *counts_dev, const int32_t *keep_idx_dev,
+                                 const int32_t *keep_counts_dev, const float *scores_dev, const float *bboxes_dev, int C, int cap,
+                                 float thr, float score_pow, float *res_dev) {
+  MpnProfScope prof_scope__(ctx, MPN_CAT_NMS);
+  if (C <= 1 || cap <= 0) return MPN_OK;
+  bbox_vote_batched_kernel<<<dim3((unsigned)cap, (unsigned)(C - 1)), 256, 0, ctx->stream>>>(sb_dev, counts_dev, keep_idx_dev, keep_counts_dev,
+                                                                                         scores_dev, bboxes_dev, C, cap, thr, score_pow, res_dev);
+  MPN_LAUNCHED(ctx);
+  return MPN_OK;
+}
+
 int mpn_bbox_vote_launch(mpn_ctx *ctx, const float *nms_dev, int K, const float *sb_dev, int N,
                          float thr, float *res_dev) {
   if (K <= 0) return MPN_OK;

@@ -13,6 +13,8 @@ struct RoiJob {
   int region;                      // 0: ROI, 1..3: foveal x1.5, x2, x4
   __nv_bfloat16 *out_hi, *out_lo;  // R x bins x out_ld
   long long out_ld; int out_ch_off;
+  int tower;                       // host bookkeeping: index of the tower this job pools for
+  int out_fmt; unsigned *ovf;      // plane format of the pooled tensor (0 = bf16 split, 1 = fp16 split: feeds a "w16" Linear)
   int normalize;
 };
 constexpr int MAX_ROI_JOBS = 16;

@@ -1,10 +1,12 @@
 """fbcoco.Tester_FRCNN mirror (Tester_FRCNN.lua:24-187) over the C ABI.
 
 testOne with the default options is ONE library call (trunk, heads, decode, clamp, per-class gather and batched NMS on the
-GPU). The optional test-time features of the reference stay host-side glue around the same ABI calls, exactly where the
-reference has them in Lua: iterative localisation (`test_num_iterative_loc`, nn.SelectBoxes + detect(...,
-recompute_features=false), :82-89), `test_use_rbox_scores` (:91-97), bbox voting with `test_bbox_voting_score_pow`
-(:118-124), keepTopKPerImage / transposeBoxes (:163-187)."""
+GPU). With the optional test-time features of the reference — iterative localisation (`test_num_iterative_loc`,
+nn.SelectBoxes + detect(..., recompute_features=false), :82-89), `test_use_rbox_scores` (:91-97), bbox voting with
+`test_bbox_voting_score_pow` (:118-124) — it is ONE call as well, mpn_model_test_one: every pass, nn.SelectBoxes, the join,
+the NMS over the joined rows and the voting stay on the device. `device_tail=False` (or a backend without
+`test_one`, e.g. the CPU oracle of the tests) keeps them as host-side glue around the ABI calls, exactly where the
+reference has them in Lua; both paths give the same bits. keepTopKPerImage / transposeBoxes (:163-187) mirror utils.lua."""
 from __future__ import annotations
 
 from typing import List, Optional
@@ -35,12 +37,15 @@ class _AbiBackend:
     def bbox_vote(self, nms_boxes, scored_boxes, thr):
         return U.bbox_vote(self.ctx, nms_boxes, scored_boxes, thr)
 
+    def test_one(self, img, boxes, im_scale, W0, H0, **kw):
+        return self.model.test_one(img, boxes, im_scale, W0, H0, **kw)
+
 
 class Tester:
     def __init__(self, model, transformer, scale=None, max_size=None, nms_thresh: float = 0.3,
                  bbox_vote_thresh: float = 0.5, score_thresh: float = -1.5, bbox_voting: bool = False,
                  num_iterative_loc: int = 1, use_rbox_scores: bool = False, bbox_voting_score_pow: float = 1.0,
-                 backend=None):
+                 backend=None, device_tail: bool = True):
         self.detec = ImageDetect(model, transformer, scale, max_size)
         self.model = model
         self.be = backend if backend is not None else _AbiBackend(model)
@@ -55,6 +60,7 @@ class Tester:
             raise ValueError("test_use_rbox_scores needs test_num_iterative_loc > 1")     # assert(#all_output > 1), :92
         self.boxselect: Optional[SelectBoxes] = None
         self.raw = None
+        self.device_tail = bool(device_tail) and hasattr(self.be, "test_one")
 
     # ---- Tester_FRCNN.lua:54-139
     def testOne(self, im, boxes) -> List[np.ndarray]:
@@ -62,7 +68,7 @@ class Tester:
         boxes = np.ascontiguousarray(boxes, np.float32)
         img, im_scale = self.detec.getImages(im)
         H0, W0 = im.shape[1], im.shape[2]
-        if self.num_iter == 1:
+        if self.num_iter == 1 and not (self.device_tail and self.bbox_voting and self.bbox_voting_score_pow == 1.0):
             scores, bboxes, keeps = self.be.detect_nms(img, boxes, im_scale, W0, H0, self.thresh, self.nms_thresh)
             self.raw = (scores, bboxes)
             out = []
@@ -70,6 +76,15 @@ class Tester:
                 sb = np.concatenate([bboxes[k, 4 * j:4 * j + 4], scores[k, j:j + 1]], axis=1).astype(np.float32)
                 out.append(self._vote(sb, scores, bboxes, j))
             return out
+        if self.device_tail and (self.bbox_voting_score_pow == 1.0 or not self.bbox_voting):
+            # all passes, nn.SelectBoxes, join, per-class gather, NMS and voting in one library call (mpn_model_test_one)
+            output, bbox_pred, keeps, voted = self.be.test_one(
+                img, boxes, im_scale, W0, H0, num_iter=self.num_iter, use_rbox_scores=self.use_rbox_scores, bbox_voting=self.bbox_voting,
+                score_thresh=self.thresh, nms_thr=self.nms_thresh, vote_thr=self.bbox_vote_thresh, vote_score_pow=self.bbox_voting_score_pow)
+            self.raw = (output, bbox_pred)
+            if voted is not None:
+                return voted
+            return [np.concatenate([bbox_pred[k, 4 * j:4 * j + 4], output[k, j:j + 1]], axis=1).astype(np.float32) for j, k in enumerate(keeps, start=1)]
         # ---- iterative localisation: every pass re-uses the cached trunk features (recompute_features = false)
         all_output, all_bbox = [], []
         output, bbox_pred = self.be.detect(img, boxes, im_scale, True)

@@ -122,11 +122,11 @@ def test_streamk_schedule(ctx, Cin, H, W, Cout, monkeypatch):
 
 # ---- "w16" numerics of fc6 / fc7 (round 2): weight = ONE fp16 plane scaled by a power of two, two products per MAC ------
 def _w16_emulation(A, B, bias, relu):
-    """what the w16 kernels compute, in fp64: (A_hi + A_lo) @ fp16(B * 2^e)^T / 2^e (+ bias)(ReLU); the only difference
-    left to the GPU is its fp32 accumulation"""
+    """what the w16 kernels compute, in fp64: (A_hi + A_lo) @ fp16(B * 2^e)^T / 2^e (+ bias)(ReLU) with A_hi / A_lo the fp16
+    planes of A; the only difference left to the GPU is its fp32 accumulation"""
     a = torch.from_numpy(A)
-    hi = a.to(torch.bfloat16).float()
-    a2 = (hi + (a - hi).to(torch.bfloat16).float()).double()
+    hi = a.to(torch.float16).float()
+    a2 = (hi + (a - hi).to(torch.float16).float()).double()
     amax = float(np.abs(B).max())
     e = 14 - int(np.frexp(amax)[1])
     b16 = (torch.from_numpy(B) * float(2.0 ** e)).to(torch.float16).double() / float(2.0 ** e)
@@ -138,8 +138,9 @@ def _w16_emulation(A, B, bias, relu):
 
 @pytest.mark.parametrize("M,N,K", [(300, 1024, 2048), (100, 1024, 2048), (1000, 4096, 4096), (257, 2000, 2112), (500, 4096, 25088)])
 def test_gemm_w16(ctx, M, N, K):
-    """the mixed-format MMA (A bf16 hi / lo planes x B fp16) does what the numerics note says: equal to the fp64 emulation
-    of that arithmetic to fp32-accumulation accuracy, and within the weight plane's 2^-12 of the exact product"""
+    """the fp16 x fp16 kernels (A as fp16 hi / lo planes, B as one scaled fp16 plane) do what the numerics note says: equal to
+    the fp64 emulation of that arithmetic to fp32-accumulation accuracy, and within the weight plane's 2^-12 of the exact
+    product. (A bf16 A with an fp16 B is an illegal instruction on sm_100a: kind::f16 wants one 16-bit format.)"""
     rng = np.random.default_rng(M + N + K)
     A = np.maximum(rng.standard_normal((M, K)), 0).astype(np.float32)              # post-ReLU activations, like fc6 / fc7 inputs
     B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
@@ -161,3 +162,18 @@ def test_gemm_w16_row_chunk_invariance(ctx):
     edges = [0, 100, 228, 229, 700, M]
     parts = np.concatenate([ctx.gemm_check(A[a:z], B, b, impl=2) for a, z in zip(edges[:-1], edges[1:])])
     assert np.array_equal(full, parts)
+
+
+def test_w16_activation_overflow_is_loud(ctx):
+    """an activation beyond fp16's range saturates and the call FAILS (no silent garbage): the flag is raised by the plane
+    conversion, tested at the synchronising entry point, and re-armed"""
+    import multipathnet_b200 as mpn
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((64, 2048)).astype(np.float32); A[3, 7] = 1.0e5
+    B = (rng.standard_normal((1024, 2048)) / 45).astype(np.float32)
+    ctx.gemm_check(A, B, None, impl=2)                 # the check entry itself does not test the flag...
+    with pytest.raises(mpn.MpnError, match="fp16"):
+        ctx.synchronize()                              # ...the next synchronising call does
+    ctx.synchronize()                                  # re-armed
+    A[3, 7] = 1.0
+    ctx.gemm_check(A, B, None, impl=2); ctx.synchronize()

@@ -108,3 +108,59 @@ def test_model_detection_sink_and_world_of_one_gather(ctx):
     m.set_detection_sink(None, 0)
     m.detect_nms(img, boxes, 1.0, W, H, -1.5, 0.3)
     m.close()
+
+
+# ---- Tester_FRCNN:testOne with its test-time options on the device (mpn_model_test_one) -------------------
+class _OracleNmsBackend:
+    """the seam of multipathnet_b200/tester.py with the GPU network behind detect() and the CPU ORACLE (nms.c restatement,
+    pinned by the literal build) behind NMS / voting: what the device tail must reproduce bit for bit"""
+
+    def __init__(self, model):
+        self.model = model
+
+    def detect(self, img, boxes, im_scale, recompute_features):
+        return self.model.detect(img, boxes, im_scale, recompute_features)
+
+    def detect_nms(self, img, boxes, im_scale, W0, H0, thresh, nms_thresh):
+        from oracle import ref as O
+        scores, bboxes = self.model.detect(img, boxes, im_scale, True)
+        bboxes = O.clamp_boxes(bboxes, W0, H0)
+        keeps = []
+        for j in range(1, scores.shape[1]):
+            idx = np.nonzero(scores[:, j] > thresh)[0]
+            sb = np.concatenate([bboxes[idx, 4 * j:4 * j + 4], scores[idx, j:j + 1]], 1).astype(np.float32)
+            keeps.append(idx[O.nms(sb, nms_thresh)] if len(idx) else idx)
+        return scores, bboxes, keeps
+
+    def nms_batched(self, sb, offsets, thr):
+        from oracle import ref as O
+        return [O.nms(sb[offsets[s]:offsets[s + 1]], thr) for s in range(len(offsets) - 1)]
+
+    def bbox_vote(self, nms_boxes, scored_boxes, thr):
+        from oracle import ref as O
+        return O.bbox_vote(nms_boxes, scored_boxes, thr)
+
+
+@pytest.mark.parametrize("num_iter,rbox,voting", [(2, False, True), (1, False, True), (3, True, False), (2, True, True), (2, False, False)])
+def test_tester_test_one_on_the_device(ctx, num_iter, rbox, voting):
+    """Tester(num_iterative_loc, use_rbox_scores, bbox_voting) at R = 1000: ONE mpn_model_test_one call == the host-side glue
+    of the reference's control flow around detect() with the oracle's nms.c / bbox_vote — same boxes, same order, same bits"""
+    spec = models.vgg16_fast_rcnn(21, seed=7, width_div=4, fc_dim=256)
+    m = mpn.Model(ctx, spec, max_rois=4096, max_h=256, max_w=320)
+    raw = wl.raw_image(150, 203, 31)
+    boxes = wl.random_boxes(1000, 150, 203, 31)
+    tf = mpn.modules.ImageTransformer(spec.transformer)
+    kw = dict(scale=[150], max_size=400, num_iterative_loc=num_iter, use_rbox_scores=rbox, bbox_voting=voting, score_thresh=0.02)
+    dev = mpn.Tester(m, tf, **kw)
+    host = mpn.Tester(m, tf, backend=_OracleNmsBackend(m), device_tail=False, **kw)
+    assert dev.device_tail and not host.device_tail
+    n0 = ctx.launch_count
+    got = dev.testOne(raw, boxes)
+    assert ctx.launch_count > n0
+    want = host.testOne(raw, boxes)
+    assert len(got) == len(want) == spec.num_classes - 1
+    for j, (a, b) in enumerate(zip(got, want), start=1):
+        assert a.shape == b.shape and np.array_equal(a, b), f"class {j}"
+    assert np.array_equal(dev.raw[0], host.raw[0]) and np.array_equal(dev.raw[1], host.raw[1])
+    assert sum(len(a) for a in got) > 50
+    m.close()

@@ -51,11 +51,19 @@ def oracle_pooled(spec, m, rois, tower, rows):
     return np.ascontiguousarray(x.reshape(n, x.shape[1], -1).transpose(0, 2, 1))
 
 
-def check_tower(spec, m, rois, tower, rows, ref=None):
+def check_tower(spec, m, rois, tower, rows, ref=None, fp16_planes=False):
     t = spec.towers[tower]
     got = m.pooled(tower, rows.start, rows.stop - rows.start)
     ref = oracle_pooled(spec, m, rois, tower, rows) if ref is None else ref
     assert got.shape == ref.shape
+    if fp16_planes:
+        # the pooled tensor feeds a "w16" Linear and is stored as fp16 hi / lo planes: 22 significant bits, but an absolute
+        # 2^-24 grid (fp16 subnormals) — exact wherever the value's own last bit (17 significant bits) is on that grid
+        assert not t.normalize
+        big = np.abs(ref) >= 2.0 ** -7
+        assert np.array_equal(got[big], ref[big]), f"tower {tower}: {np.count_nonzero(got[big] != ref[big])} values >= 2^-7 differ"
+        assert np.abs(got - ref).max() <= 2.0 ** -24
+        return 1.0
     if not t.normalize:
         assert np.array_equal(got, ref), f"tower {tower}: {np.count_nonzero(got != ref)} of {got.size} pooled values differ"
         return 1.0
@@ -105,17 +113,18 @@ def test_fused_roi_multipathnet_small_all_towers(ctx, roi_impl):
         m.close()
 
 
-@pytest.mark.parametrize("roi_impl", [0, 1])
-def test_fused_roi_full_size_cfg2(ctx, roi_impl):
-    """BASELINE configs[1]: VGG-16 600x800, R=1000, 7x7 bins on conv5 — every pooled value of the timed kernel, bit-exact"""
+@pytest.mark.parametrize("roi_impl,fc_w16", [(0, 1), (0, 0), (1, 0), (1, 1)])
+def test_fused_roi_full_size_cfg2(ctx, roi_impl, fc_w16):
+    """BASELINE configs[1]: VGG-16 600x800, R=1000, 7x7 bins on conv5 — every pooled value of the timed kernel: bit-exact as
+    bf16 planes (fc_w16 = 0), exact down to the fp16 subnormal grid as fp16 planes (the default: fc6 takes the w16 numerics)"""
     spec = models.vgg16_fast_rcnn(21, seed=1234)
+    ctx.set_option("roi_impl", roi_impl); ctx.set_option("fc_w16", fc_w16)
     m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
-    ctx.set_option("roi_impl", roi_impl)
     try:
         rois = run_detect(m, spec, 600, 800, 1000, 2, sharp=False)
-        check_tower(spec, m, rois, 0, slice(0, 1000))
+        check_tower(spec, m, rois, 0, slice(0, 1000), fp16_planes=bool(fc_w16))
     finally:
-        ctx.set_option("roi_impl", -1)
+        ctx.set_option("roi_impl", -1); ctx.set_option("fc_w16", -1)
         m.close()
 
 
