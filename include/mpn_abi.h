@@ -200,6 +200,12 @@ int mpn_get_images(mpn_ctx *ctx, const float *im, int32_t H0, int32_t W0, const 
                    int32_t h, int32_t w, float *out);
 int mpn_get_images_dev(mpn_ctx *ctx, const float *im_dev, int32_t H0, int32_t W0, const mpn_image_transform *tf,
                        int32_t h, int32_t w, float *out_dev);
+/* Same from the decoder's bytes: im_hwc H0 x W0 x 3 uint8, interleaved RGB; the sample value is byte / 255 in fp32 (what
+ * image.load(path, 3, 'float') hands to the transformer): a quarter of the bytes to move over the bus. */
+int mpn_get_images_u8(mpn_ctx *ctx, const uint8_t *im_hwc, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                      int32_t h, int32_t w, float *out);
+int mpn_get_images_u8_dev(mpn_ctx *ctx, const uint8_t *im_hwc_dev, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                          int32_t h, int32_t w, float *out_dev);
 /* getImages + model:get(1):forward: uploads the RAW image (host), transforms and scales it on the device into the
  * model's image buffer and runs the trunk; *im_scale, *h, *w as mpn_get_images_size. Follow with mpn_model_detect(...,
  * image = NULL, recompute_features = 0) on the cached features. */
@@ -241,6 +247,14 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
                                 const float *boxes, int64_t R, float im_scale, float W0, float H0,
                                 float score_thresh, float nms_thr, float *scores, float *bboxes,
                                 int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket);
+/* The same pipeline fed with the RAW image as the decoder leaves it (H0 x W0 x 3 uint8, interleaved RGB): getImages
+ * (ImageDetect.lua:22-52: transformer, im_scale rule for `scale` / `max_size`, image.scale) runs on the device in front
+ * of the trunk, boxes are original-image coordinates, the clamp is to the original W0 x H0. 0.9 MB cross the bus for a
+ * 480 x 640 image instead of the 5.8 MB of its scaled fp32 form. Same ticket protocol as mpn_model_detect_nms_submit. */
+int mpn_model_detect_nms_submit_u8(mpn_model *m, const uint8_t *im_hwc, int32_t H0, int32_t W0,
+                                   const mpn_image_transform *tf, double scale, double max_size, const float *boxes,
+                                   int64_t R, float score_thresh, float nms_thr, float *scores, float *bboxes,
+                                   int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket);
 int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket);
 /* Tester_FRCNN:testOne with its test-time options (Tester_FRCNN.lua:54-139) in one stream-ordered pass, nothing but the
  * inputs and the final results crossing the bus: pass 1 = detect on the proposals, clamped to the image (:72-78); passes

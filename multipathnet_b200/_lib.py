@@ -112,6 +112,10 @@ SIGNATURES = {
     "mpn_get_images_size": (C.c_int, [C.c_int32, C.c_int32, C.c_double, C.c_double, _i32p, _i32p, C.POINTER(C.c_double)]),
     "mpn_get_images": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
     "mpn_get_images_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
+    "mpn_get_images_u8": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
+    "mpn_get_images_u8_dev": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, _vp]),
+    "mpn_model_detect_nms_submit_u8": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, _vp, C.c_int64, C.c_float, C.c_float,
+                                                 _vp, _vp, _vp, _vp, _i32p]),
     "mpn_model_trunk_image": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, C.POINTER(C.c_double), _i32p, _i32p]),
     "mpn_model_create": (C.c_int, [_vp, C.POINTER(CModelDesc), C.POINTER(_vp), _i64p, C.c_int32, C.POINTER(_vp)]),
     "mpn_model_destroy": (None, [_vp]),
@@ -361,6 +365,20 @@ class Context:
         tf = CImageTransform.of(kind)
         self.check(self.lib.mpn_get_images(self.h, _ptr(im), im.shape[1], im.shape[2], C.addressof(tf), h.value, w.value, _ptr(out)),
                    "mpn_get_images")
+        return out, float(s.value)
+
+    def get_images_u8(self, im_hwc_u8, kind: str, scale: float = 600, max_size: float = 1000):
+        """getImages on the device from the decoder's bytes (H0 x W0 x 3 uint8 RGB) -> (transformed + scaled image, im_scale)"""
+        im = np.ascontiguousarray(im_hwc_u8, dtype=np.uint8)
+        if im.ndim != 3 or im.shape[2] != 3:
+            raise ValueError("expected an H x W x 3 uint8 image")
+        h, w, s = C.c_int32(), C.c_int32(), C.c_double()
+        self.check(self.lib.mpn_get_images_size(im.shape[0], im.shape[1], float(scale), float(max_size), C.byref(h), C.byref(w), C.byref(s)),
+                   "mpn_get_images_size")
+        out = np.empty((3, h.value, w.value), np.float32)
+        tf = CImageTransform.of(kind)
+        self.check(self.lib.mpn_get_images_u8(self.h, _ptr(im), im.shape[0], im.shape[1], C.addressof(tf), h.value, w.value, _ptr(out)),
+                   "mpn_get_images_u8")
         return out, float(s.value)
 
     def bbox_norm(self, deltas, mean, std) -> np.ndarray:
@@ -657,6 +675,22 @@ class Model:
             "mpn_model_detect_nms_submit")
         self._inflight = getattr(self, "_inflight", {})
         self._inflight[t.value] = out              # keeps the host buffers alive until wait()
+        return t.value
+
+    def detect_nms_submit_u8(self, im_hwc_u8, boxes, kind: str, scale: float = 600, max_size: float = 1000, score_thresh: float = -1.5,
+                             nms_thr: float = 0.3):
+        """pipelined detect_nms from the RAW uint8 H0 x W0 x 3 image: getImages runs on the device (mpn_model_detect_nms_submit_u8)"""
+        im, b = np.ascontiguousarray(im_hwc_u8, dtype=np.uint8), _f32(boxes)
+        n = b.shape[0]
+        out = dict(im=im, b=b, scores=np.empty((n, self.C), dtype=np.float32), bboxes=np.empty((n, 4 * self.C), dtype=np.float32),
+                   keep=np.empty((self.C - 1, n), dtype=np.int32), counts=np.empty(self.C - 1, dtype=np.int32), tf=CImageTransform.of(kind))
+        t = C.c_int32(-1)
+        self.ctx.check(self.ctx.lib.mpn_model_detect_nms_submit_u8(
+            self.h, _ptr(im), im.shape[0], im.shape[1], C.addressof(out["tf"]), float(scale), float(max_size), _ptr(b), n, float(score_thresh),
+            float(nms_thr), _ptr(out["scores"]), _ptr(out["bboxes"]), _ptr(out["keep"]), _ptr(out["counts"]), C.byref(t)),
+            "mpn_model_detect_nms_submit_u8")
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[t.value] = out
         return t.value
 
     def detect_nms_wait(self, ticket: int):

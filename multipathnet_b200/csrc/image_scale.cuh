@@ -71,12 +71,14 @@ struct Transform {
 
 // one sample of the transformed image (before resizing)
 struct TransformedImage {
-  const float *im;       // 3 x H0 x W0 fp32, RGB in [0,1] (loaders/loader.lua:79)
+  const float *im;       // 3 x H0 x W0 fp32, RGB in [0,1] (loaders/loader.lua:79), or null with:
+  const uint8_t *im_u8;  // H0 x W0 x 3 bytes, interleaved RGB as a decoder hands them over; the value is byte / 255 in fp32
+                         // (what image.load(path, 3, 'float') returns), one IEEE division per sample
   int32_t H0, W0;
   Transform t;
   MPN_HD float at(int c, int y, int x) const {      // selects, not indexing: the struct stays in kernel-parameter space
     const int sc = c == 0 ? t.src_chan[0] : (c == 1 ? t.src_chan[1] : t.src_chan[2]);
-    float v = im[((int64_t)sc * H0 + y) * W0 + x];
+    float v = im ? im[((int64_t)sc * H0 + y) * W0 + x] : fdiv((float)im_u8[((int64_t)y * W0 + x) * 3 + sc], 255.0f);
     if (t.has_scale) v = fmul(v, t.scale);
     v = fadd(v, c == 0 ? t.neg_mean[0] : (c == 1 ? t.neg_mean[1] : t.neg_mean[2]));
     if (t.has_std) v = fdiv(v, c == 0 ? t.std[0] : (c == 1 ? t.std[1] : t.std[2]));
@@ -84,12 +86,18 @@ struct TransformedImage {
   }
 };
 
-// one output sample di of a 1-D resample src_len -> dst_len; get(i) reads source sample i
+// the step of a 1-D resample src_len -> dst_len (one IEEE division; the kernel gets it precomputed on the host, same bits)
+MPN_HD float axis_scale(int src_len, int dst_len) {
+  if (dst_len > src_len) return (src_len == 1) ? 0.0f : fdiv((float)(src_len - 1), (float)(dst_len - 1));
+  if (dst_len < src_len) return fdiv((float)src_len, (float)dst_len);
+  return 1.0f;
+}
+
+// one output sample di of a 1-D resample src_len -> dst_len; get(i) reads source sample i; scale = axis_scale(src_len, dst_len)
 template <class Get>
-MPN_HD float scale1d(int src_len, int dst_len, int di, const Get &get) {
+MPN_HD float scale1d(int src_len, int dst_len, int di, const Get &get, const float scale) {
   if (dst_len > src_len) {
     if (src_len == 1 || di == dst_len - 1) return get(src_len - 1);
-    const float scale = fdiv((float)(src_len - 1), (float)(dst_len - 1));
     float sf = fmul((float)di, scale);
     int si = (int)sf;
     sf = fsub(sf, (float)si);
@@ -97,7 +105,6 @@ MPN_HD float scale1d(int src_len, int dst_len, int di, const Get &get) {
     return fadd(fmul(fsub(1.0f, sf), get(si)), fmul(sf, get(si + 1)));
   }
   if (dst_len < src_len) {
-    const float scale = fdiv((float)src_len, (float)dst_len);
     float s0f = fmul((float)di, scale);
     int s0 = (int)s0f;
     s0f = fsub(s0f, (float)s0);
@@ -119,6 +126,8 @@ MPN_HD float scale1d(int src_len, int dst_len, int di, const Get &get) {
   }
   return get(di);
 }
+template <class Get>
+MPN_HD float scale1d(int src_len, int dst_len, int di, const Get &get) { return scale1d(src_len, dst_len, di, get, axis_scale(src_len, dst_len)); }
 
 struct RowGet {               // source row y of channel c, sampled along x
   const TransformedImage *I;
@@ -128,16 +137,20 @@ struct RowGet {               // source row y of channel c, sampled along x
 struct TmpColGet {            // column x of the width-resampled temporary (H0 x w), sampled along y
   const TransformedImage *I;
   int c, x, w;
+  float sx;                   // axis_scale(W0, w)
   MPN_HD float operator()(int y) const {
     RowGet r{I, c, y};
-    return scale1d(I->W0, w, x, r);
+    return scale1d(I->W0, w, x, r, sx);
   }
 };
 
-// pixel (c, y, x) of image.scale(transformer(im), w, h)
+// pixel (c, y, x) of image.scale(transformer(im), w, h); sx / sy = axis_scale(W0, w) / axis_scale(H0, h)
+MPN_HD float scaled_pixel(const TransformedImage &I, int h, int w, int c, int y, int x, float sx, float sy) {
+  TmpColGet col{&I, c, x, w, sx};
+  return scale1d(I.H0, h, y, col, sy);
+}
 MPN_HD float scaled_pixel(const TransformedImage &I, int h, int w, int c, int y, int x) {
-  TmpColGet col{&I, c, x, w};
-  return scale1d(I.H0, h, y, col);
+  return scaled_pixel(I, h, w, c, y, x, axis_scale(I.W0, w), axis_scale(I.H0, h));
 }
 
 }  // namespace mpn_img

@@ -23,6 +23,7 @@ int mpn_nhwc_split_to_nchw_launch(mpn_ctx *, const DTensor &, float *);
 int mpn_project_rois_launch(mpn_ctx *, const float *, int64_t, float, float *);
 int mpn_get_images_launch(mpn_ctx *, const float *, int32_t, int32_t, const mpn_image_transform *, int32_t, int32_t, float *);
 int mpn_get_images_size_impl(int32_t, int32_t, double, double, int32_t *, int32_t *, double *);
+int mpn_get_images_u8_launch(mpn_ctx *, const uint8_t *, int32_t, int32_t, const mpn_image_transform *, int32_t, int32_t, float *);
 int mpn_bbox_norm_launch(mpn_ctx *, float *, int64_t, int64_t, const float *, const float *);
 int mpn_bbox_decode_launch(mpn_ctx *, const float *, const float *, int64_t, int, int, float, float, float *);
 int mpn_softmax_mean_launch(mpn_ctx *, const float *, int64_t, int, int, int, float *);
@@ -127,7 +128,7 @@ struct mpn_model {
   RoiJobs jobs;
   // ---- pipelined submit/wait (two slots): per-slot input staging + a private copy of the outputs, copy streams, events
   struct PipeSlot {
-    DevBuf image, boxes, scores, bboxes, keep_idx, keep_counts;
+    DevBuf image, raw_u8, boxes, scores, bboxes, keep_idx, keep_counts;
     cudaEvent_t h2d = nullptr, compute = nullptr, done = nullptr;
     bool busy = false; int ticket = -1;
   };
@@ -913,13 +914,15 @@ int mpn_model_detect_nms(mpn_model *m, const float *image, int32_t H, int32_t W,
   return mpn_ovf_test(ctx);
 }
 
-int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
-                                float im_scale, float W0, float H0, float score_thresh, float nms_thr, float *scores,
-                                float *bboxes, int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket) {
-  if (!m) return MPN_ERR_ARG;
+// image != null: the transformed + scaled fp32 image (H x W); else raw_u8: the RAW H0 x W0 x 3 byte image, transformed and
+// scaled on the device (get_images_kernel) to the size getImages prescribes
+static int submit_common(mpn_model *m, const float *image, int32_t H, int32_t W, const uint8_t *raw_u8, int32_t H0r, int32_t W0r,
+                         const mpn_image_transform *tf, double scale, double max_size, const float *boxes, int64_t R, float im_scale,
+                         float W0, float H0, float score_thresh, float nms_thr, float *scores, float *bboxes, int32_t *keep_idx,
+                         int32_t *keep_counts, int32_t *ticket) {
   mpn_ctx *ctx = m->ctx;
   MPN_CUDA(ctx, cudaSetDevice(ctx->device));
-  MPN_CHECK_ARG(ctx, image && boxes && R > 0 && ticket, "image/boxes/ticket missing");
+  MPN_CHECK_ARG(ctx, (image || raw_u8) && boxes && R > 0 && ticket, "image/boxes/ticket missing");
   const int C = m->d.num_classes;
   mpn_model::PipeSlot &q = m->pipe[m->next_ticket & 1];
   if (q.busy) return mpn_fail(ctx, MPN_ERR_STATE, "two submissions are already in flight: call mpn_model_detect_nms_wait first");
@@ -932,6 +935,13 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
     MPN_CUDA(ctx, cudaEventCreateWithFlags(&q.compute, cudaEventDisableTiming));
     MPN_CUDA(ctx, cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming));
   }
+  if (raw_u8) {
+    MPN_CHECK_ARG(ctx, tf && H0r > 0 && W0r > 0, "raw image: transformer / size missing");
+    double s = 0;
+    MPN_CHECK_ARG(ctx, mpn_get_images_size_impl(H0r, W0r, scale, max_size, &H, &W, &s) == MPN_OK && H > 0 && W > 0, "bad scale / max_size");
+    MPN_CHECK_ARG(ctx, H <= m->d.max_h && W <= m->d.max_w, "scaled image larger than max_h x max_w");
+    im_scale = (float)s; W0 = (float)W0r; H0 = (float)H0r;          // clamp to the ORIGINAL image (Tester_FRCNN.lua:75-78)
+  }
   const size_t img_bytes = sizeof(float) * 3 * (size_t)H * W;
   MPN_TRY(q.image.ensure(ctx, img_bytes));
   MPN_TRY(q.boxes.ensure(ctx, sizeof(float) * 4 * (size_t)R));
@@ -940,10 +950,16 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
   MPN_TRY(q.keep_idx.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1) * R));
   MPN_TRY(q.keep_counts.ensure(ctx, sizeof(int32_t) * (size_t)(C - 1)));
   // inputs: the slot's previous occupant was waited for (busy == false), so its staging buffers are free
-  MPN_CUDA(ctx, cudaMemcpyAsync(q.image.p, image, img_bytes, cudaMemcpyHostToDevice, m->s_h2d));
+  if (raw_u8) {
+    MPN_TRY(q.raw_u8.ensure(ctx, (size_t)H0r * W0r * 3));
+    MPN_CUDA(ctx, cudaMemcpyAsync(q.raw_u8.p, raw_u8, (size_t)H0r * W0r * 3, cudaMemcpyHostToDevice, m->s_h2d));
+  } else {
+    MPN_CUDA(ctx, cudaMemcpyAsync(q.image.p, image, img_bytes, cudaMemcpyHostToDevice, m->s_h2d));
+  }
   MPN_CUDA(ctx, cudaMemcpyAsync(q.boxes.p, boxes, sizeof(float) * 4 * (size_t)R, cudaMemcpyHostToDevice, m->s_h2d));
   MPN_CUDA(ctx, cudaEventRecord(q.h2d, m->s_h2d));
   MPN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, q.h2d, 0));
+  if (raw_u8) MPN_TRY(mpn_get_images_u8_launch(ctx, (const uint8_t *)q.raw_u8.p, H0r, W0r, tf, H, W, (float *)q.image.p));
   MPN_TRY(mpn_model_detect_nms_dev(m, (const float *)q.image.p, H, W, (const float *)q.boxes.p, R, im_scale, W0, H0, score_thresh,
                                    nms_thr, scores ? (float *)q.scores.p : nullptr, bboxes ? (float *)q.bboxes.p : nullptr,
                                    keep_idx ? (int32_t *)q.keep_idx.p : nullptr, keep_counts ? (int32_t *)q.keep_counts.p : nullptr));
@@ -958,6 +974,24 @@ int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int
   q.busy = true; q.ticket = m->next_ticket;
   *ticket = m->next_ticket++;
   return MPN_OK;
+}
+
+int mpn_model_detect_nms_submit(mpn_model *m, const float *image, int32_t H, int32_t W, const float *boxes, int64_t R,
+                                float im_scale, float W0, float H0, float score_thresh, float nms_thr, float *scores,
+                                float *bboxes, int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket) {
+  if (!m) return MPN_ERR_ARG;
+  MPN_CHECK_ARG(m->ctx, image, "image missing");
+  return submit_common(m, image, H, W, nullptr, 0, 0, nullptr, 0, 0, boxes, R, im_scale, W0, H0, score_thresh, nms_thr, scores, bboxes,
+                       keep_idx, keep_counts, ticket);
+}
+
+int mpn_model_detect_nms_submit_u8(mpn_model *m, const uint8_t *im_hwc, int32_t H0, int32_t W0, const mpn_image_transform *tf,
+                                   double scale, double max_size, const float *boxes, int64_t R, float score_thresh, float nms_thr,
+                                   float *scores, float *bboxes, int32_t *keep_idx, int32_t *keep_counts, int32_t *ticket) {
+  if (!m) return MPN_ERR_ARG;
+  MPN_CHECK_ARG(m->ctx, im_hwc, "image missing");
+  return submit_common(m, nullptr, 0, 0, im_hwc, H0, W0, tf, scale, max_size, boxes, R, 0.f, 0.f, 0.f, score_thresh, nms_thr, scores, bboxes,
+                       keep_idx, keep_counts, ticket);
 }
 
 int mpn_model_detect_nms_wait(mpn_model *m, int32_t ticket) {

@@ -7,7 +7,7 @@
 extern "C" void hd_get_images(const float *im, int H0, int W0, const int *swap /* 1-based */, float scale, const float *mean,
                               const float *std /* or NULL */, int h, int w, float *out) {
   mpn_img::TransformedImage I;
-  I.im = im; I.H0 = H0; I.W0 = W0;
+  I.im = im; I.im_u8 = nullptr; I.H0 = H0; I.W0 = W0;
   for (int c = 0; c < 3; ++c) {
     I.t.src_chan[c] = swap[c] - 1;
     I.t.neg_mean[c] = (float)(-(double)mean[c]);
