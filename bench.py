@@ -504,6 +504,44 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * R * args.steps / float(t[0].item())
     e2e_sync_value = world * R * args.steps / float(t[1].item())
+    # ---- same pipeline fed with the RAW decoder bytes: a 480 x 640 x 3 uint8 image per step, getImages (transformer +
+    # im_scale rule + image.scale to 600 x 800) on the device in front of the trunk; boxes in original-image coordinates
+    e2e_raw = None
+    if args.config == "vgg16_frcnn":
+        H0r, W0r = (H * 4) // 5, (W * 4) // 5                      # 480 x 640 -> scale 600 / max 1000 gives exactly H x W
+        rng = np.random.default_rng(77 + rank)
+        raw_pin = [torch.from_numpy(rng.integers(0, 256, (H0r, W0r, 3), dtype=np.uint8)).pin_memory() for _ in range(NIMG)]
+        rbox_pin = [torch.from_numpy(wl.random_boxes(R, H0r, W0r, 2000 * rank + i)).pin_memory() for i in range(NIMG)]
+        from multipathnet_b200._lib import CImageTransform
+        tfm = CImageTransform.of(spec.transformer)
+
+        def submit_raw(i):
+            k = i % NIMG
+            o = outs[i & 1]
+            t = _C.c_int32(-1)
+            ctx.check(lib.mpn_model_detect_nms_submit_u8(model.h, raw_pin[k].data_ptr(), H0r, W0r, _C.addressof(tfm), 600.0, 1000.0, rbox_pin[k].data_ptr(), R,
+                                                         -1.5, 0.3, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), _C.byref(t)),
+                      "detect_nms_submit_u8")
+            return t.value
+
+        def run_raw(n):
+            prev = submit_raw(0)
+            for i in range(1, n):
+                cur = submit_raw(i)
+                ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
+                prev = cur
+            ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
+
+        run_raw(3)
+        barrier()
+        t0 = time.perf_counter()
+        run_raw(args.steps)
+        raw_s = time.perf_counter() - t0
+        tr = torch.tensor([raw_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        e2e_raw = {"value": world * R * args.steps / float(tr.item()), "unit": "proposals/s", "h2d_bytes_per_step": H0r * W0r * 3 + R * 4 * 4,
+                   "api": "mpn_model_detect_nms_submit_u8 / _wait: raw 480x640x3 uint8 image in, getImages on the device (get_images_kernel)"}
     h2d = 3 * H * W * 4 + R * 4 * 4
     d2h = R * C * 4 + R * 4 * C * 4 + (C - 1) * R * 4 + (C - 1) * 4 + world * REC * 4      # + this image's share of the gathered records
 
@@ -545,6 +583,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight) + mpn_dist_all_gather (records to host) at the end",
                     "sync_value": e2e_sync_value, "sync_api": "mpn_model_detect_nms (host buffers, one blocking call per image)"},
+            "e2e_raw": e2e_raw,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == "vgg16_frcnn":

@@ -778,7 +778,7 @@ int mpn_model_heads_dev(mpn_model *m, const float *rois_dev, int64_t R, float *c
   MPN_TRY(run_heads(m, rois_dev, R));
   const int C = m->d.num_classes, K = (int)m->cls_heads.size();
   if (cls_out_dev) {
-    if (K == 1 && !m->d.no_softmax) {
+    if (K == 1) {   // a single head's own output: what the Linear produced (the same rule as detect: any softmax is applied there)
       MPN_CUDA(ctx, cudaMemcpyAsync(cls_out_dev, m->cls_logits.p, sizeof(float) * (size_t)R * C, cudaMemcpyDeviceToDevice, ctx->stream));
     } else {   // integral head: the model's own output is the mean of K softmaxes
       MPN_TRY(mpn_softmax_mean_launch(ctx, (const float *)m->cls_logits.p, R, C, K, 1, cls_out_dev));

@@ -236,9 +236,9 @@ class _Writer:
     def _index(self, o) -> bool:
         """writes the memo index; True if the object was written before (nothing more to emit)"""
         if id(o) in self.seen:
-            self.i32(self.seen[id(o)])
+            self.i32(self.seen[id(o)][0])
             return True
-        self.seen[id(o)] = self.next_idx
+        self.seen[id(o)] = (self.next_idx, o)      # the entry keeps `o` alive: a freed temporary's id() could be reused within one save
         self.i32(self.next_idx)
         self.next_idx += 1
         return False
@@ -839,6 +839,7 @@ def model_from_t7(model, name: str = "t7", transformer: str = None, num_classes:
     total = sum(widths)
     narrows, cls_heads, bbox_head = None, None, None
     no_softmax = 1 if model.get("noSoftMax") else 0
+    graph_softmax = False
     bbox_mean, bbox_std, has_norm = (0.0, 0.0, 0.0, 0.0), (0.1, 0.1, 0.2, 0.2), 0
 
     def norm_of(k):
@@ -863,14 +864,25 @@ def model_from_t7(model, name: str = "t7", transformer: str = None, num_classes:
             for k in kids:
                 if _base(k.typename) == "BBoxNorm":
                     has_norm, bbox_mean, bbox_std = norm_of(k)
+                elif _base(k.typename) == "SoftMax":
+                    graph_softmax = True
         elif b == "BBoxNorm":
             has_norm, bbox_mean, bbox_std = norm_of(m)
-        elif b in ("SoftMax",) + _PASS:
+        elif b == "SoftMax":
+            graph_softmax = True
+        elif b in _PASS:
             continue
         else:
             raise NotImplementedError(f"head module {m.typename}")
     if cls_heads is None:
         raise ValueError("no {class, bbox} head found")
+    if graph_softmax and len(cls_heads) == 1:
+        # a SoftMax inside the graph (test_add_nosoftmax, test_runner.lua:38-41): with model.noSoftMax the reference returns the
+        # model's own softmax and ImageDetect adds none (ImageDetect.lua:189) = ONE softmax, which is what detect() applies
+        # when no_softmax = 0; without noSoftMax the reference would apply it twice
+        if not model.get("noSoftMax"):
+            raise NotImplementedError("nn.SoftMax inside the graph without model.noSoftMax: the reference applies the softmax twice")
+        no_softmax = 0
     C = cls_heads[0].cout
     if any(h.cout != C for h in cls_heads) or bbox_head.cout != 4 * C:
         raise ValueError("class / bbox head sizes disagree")

@@ -81,3 +81,42 @@ def test_roi_two_pass_normalisation_knob():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         return int(r.stdout.strip().splitlines()[-1].split()[-1])
     assert run({"MPN_ROI_NORM_SPLIT": "1"}) == run({"MPN_ROI_NORM_SPLIT": "0"}) + 1
+
+
+@pytest.mark.parametrize("H0,W0,scale,max_size", [(60, 80, 60, 100), (120, 90, 60, 1000), (333, 500, 600, 1000), (480, 640, 600, 1000)])
+@pytest.mark.parametrize("kind", ["ross", "imagenet"])
+def test_get_images_from_the_decoder_bytes(ctx, oracle_built, H0, W0, scale, max_size, kind):
+    """uint8 H x W x 3 in (what a JPEG decoder leaves): value = byte / 255 in fp32, then exactly the fp32 path — bit for bit
+    against the oracle fed with that float image"""
+    rng = np.random.default_rng(H0 * W0)
+    im_u8 = rng.integers(0, 256, (H0, W0, 3), dtype=np.uint8)
+    im_f = np.ascontiguousarray((im_u8.astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1))
+    ref, s_ref = oracle_built.get_images(im_f, kind, scale, max_size)
+    out, s = ctx.get_images_u8(im_u8, kind, scale, max_size)
+    assert s == s_ref and out.shape == ref.shape and np.array_equal(out, ref)
+    out_f, _ = ctx.get_images(im_f, kind, scale, max_size)
+    assert np.array_equal(out, out_f)
+
+
+def test_raw_u8_submit_equals_the_host_getimages_path(ctx):
+    """mpn_model_detect_nms_submit_u8 (raw bytes up, getImages + trunk + heads + NMS on the device) == getImages on the host +
+    mpn_model_detect_nms, bit for bit, two images in flight"""
+    spec = models.vgg16_fast_rcnn(21, seed=3, width_div=4, fc_dim=256)
+    m = mpn.Model(ctx, spec, max_rois=128, max_h=192, max_w=256)
+    rng = np.random.default_rng(5)
+    ims = [rng.integers(0, 256, (96, 128, 3), dtype=np.uint8) for _ in range(3)]
+    boxes = [wl.random_boxes(64, 96, 128, 40 + i) for i in range(3)]
+    want = []
+    for im, bx in zip(ims, boxes):
+        im_f = np.ascontiguousarray((im.astype(np.float32) / np.float32(255.0)).transpose(2, 0, 1))
+        img, s = ctx.get_images(im_f, "ross", 120, 200)
+        want.append(m.detect_nms(img, bx, s, 128, 96, 0.0, 0.3))
+    tickets = [m.detect_nms_submit_u8(ims[0], boxes[0], "ross", 120, 200, 0.0, 0.3)]
+    got = []
+    for i in (1, 2):
+        tickets.append(m.detect_nms_submit_u8(ims[i], boxes[i], "ross", 120, 200, 0.0, 0.3))
+        got.append(m.detect_nms_wait(tickets[i - 1]))
+    got.append(m.detect_nms_wait(tickets[2]))
+    for (s0, b0, k0), (s1, b1, k1) in zip(want, got):
+        assert np.array_equal(s0, s1) and np.array_equal(b0, b1) and all(np.array_equal(a, b) for a, b in zip(k0, k1))
+    m.close()

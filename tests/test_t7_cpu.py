@@ -229,3 +229,22 @@ def test_nobackprop_legacy_inner_field():
     inner = _pack_obj(3, "V 1", "nn.Identity", _pack_table(4, []))
     o = t7.load(io.BytesIO(_pack_obj(1, "V 1", "nn.NoBackprop", _pack_table(2, [("inner", inner)]))))
     assert [m.typename for m in o.modules] == ["nn.Identity"] and "inner" not in o.fields
+
+
+def test_writer_memo_keeps_temporaries_alive(tmp_path):
+    """the writer memoised by id(o) without holding o, so a freed temporary's id could be reused inside one save
+    and a later, different table came back as an alias of an earlier one"""
+    from multipathnet_b200 import t7
+    import io
+    w = t7._Writer(io.BytesIO())
+    w.obj([1, 2]); w.obj([3, 4])                       # two temporaries that may share an id() once the first is freed
+    w.f.seek(0)
+    r = t7._Reader(w.f)
+    a, b = r.obj(), r.obj()
+    assert list(a.values() if isinstance(a, dict) else a) != list(b.values() if isinstance(b, dict) else b)
+    tables = [t7.T7Object("nn.ModelParallelTable", {"gpuAssignments": [float(i), float(i + 1)], "modules": [], "dimension": 2.0}) for i in range(20)]
+    p = tmp_path / "mpt.t7"
+    t7.save(str(p), {"tables": tables})
+    back = t7.load(str(p))["tables"]
+    got = [list(x.gpuAssignments.values()) if isinstance(x.gpuAssignments, dict) else list(x.gpuAssignments) for x in (back.values() if isinstance(back, dict) else back)]
+    assert got == [[float(i), float(i + 1)] for i in range(20)]
