@@ -37,11 +37,13 @@ for (k, lines), d in zip(kernels.items(), dem):
             cnt.append(len(re.findall(r"\b" + re.escape(w) + r"\b", text)))
     print(f"| `{short[:70]}` | {len(lines)} | " + " | ".join(str(c) for c in cnt) + " |")
 print()
-for pat, title in (("conv_gemm_tc_kernel<240, 2, true>", "fc6 / fc7 (fp16 x fp16 two-product kernel, CTA pairs)"), ("conv3x3_tc_kernel<256, 2>", "3x3 trunk convolution (A-reuse kernel, CTA pairs)"),
-                   ("roi_pool_cluster_kernel", "fused Foveal + ROI pooling (4-CTA clusters)")):
+for pat, title, mn in (("conv_gemm_tc_kernel<240, 2, true>", "fc6 / fc7 (fp16 x fp16 two-product kernel, CTA pairs)", "UTCHMMA"),
+                       ("conv3x3_tc_kernel<256, 2>", "3x3 trunk convolution (A-reuse kernel, CTA pairs)", "UTCHMMA"),
+                       ("conv3x3_tc_kernel<256, 2>", "3x3 trunk convolution: first TMEM read of the epilogue", "LDTM"),
+                       ("roi_pool_cluster_kernel", "fused Foveal + ROI pooling (4-CTA clusters)", "UCGABAR")):
     for (k, lines), d in zip(kernels.items(), dem):
         if pat in d:
-            idx = next((i for i, l in enumerate(lines) if "UTCHMMA" in l or "UCGABAR" in l), 0)
+            idx = next((i for i, l in enumerate(lines) if mn in l), 0)
             print(f"## {title}: `{pat}`, instructions {max(0, idx - 6)}..{idx + 10}\n\n```")
             for l in lines[max(0, idx - 6): idx + 10]:
                 print(re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", l).rstrip())
