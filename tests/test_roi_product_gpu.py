@@ -97,10 +97,11 @@ def test_fused_roi_small_unnormalised_and_regions_leaving_the_image(ctx):
     m.close()
 
 
-@pytest.mark.parametrize("roi_impl", [0, 1, 2])
+@pytest.mark.parametrize("roi_impl", [0, 1, 2, 3])
 def test_fused_roi_multipathnet_small_all_towers(ctx, roi_impl):
     """cfg 3 structure at reduced width: towers 0..3 = Foveal regions x1, x1.5, x2, x4 on conv5|conv4|conv3 with per-level
-    L2 normalise; every implementation of the stage (0 = roi_pool_cluster_kernel, the default; 1 / 2 = the round-1 kernels)"""
+    L2 normalise; every implementation of the stage (0 = roi_pool_cluster_kernel, the default; 3 = the same with the
+    barrier.cluster exchange; 1 / 2 = the round-1 kernels)"""
     spec = models.vgg16_multipathnet(21, seed=11, width_div=4, fc_dim=256)
     m = mpn.Model(ctx, spec, max_rois=256, max_h=256, max_w=320)
     ctx.set_option("roi_impl", roi_impl)
@@ -137,7 +138,7 @@ def test_fused_roi_full_size_cfg3_all_towers(ctx):
         rois = run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
         blocks = (slice(0, 200), slice(800, 1000))                  # 400 of the 1000 ROIs per tower: ~30 s of oracle time in all
         refs = {(t, b.start): oracle_pooled(spec, m, rois, t, b) for t in range(len(spec.towers)) for b in blocks}
-        for impl in (0, 1, 2):
+        for impl in (0, 1, 2, 3):
             ctx.set_option("roi_impl", impl)
             run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
             for t in range(len(spec.towers)):
