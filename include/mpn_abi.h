@@ -45,9 +45,10 @@ const char *mpn_version(void);
 /* run-time knobs of the product kernels, so that tests can cover every variant in one process; value < 0 restores the
  * default (the environment variable of the same meaning, else the built-in choice). Names:
  *   "fc_w16"          numerics of the big per-ROI Linears (fc6 / fc7: K >= 2048, >= 1024 outputs), read when a model plans
- *                     its heads: 1 (default) = weight as ONE fp16 plane scaled by a power of two, two tensor-core
- *                     products per MAC (A_hi x W + A_lo x W); 0 = the three-product bf16 split every other layer uses.
- *                     Environment: MPN_FC_W16.
+ *                     its heads: 1 = weight as ONE fp16 plane scaled by a power of two, two tensor-core products per
+ *                     MAC (A_hi x W + A_lo x W); 0 = the three-product bf16 split every other layer uses. Unset: 1 for
+ *                     single-tower graphs (Fast R-CNN: 4-5e-4 on the scores at full size), 0 for multi-tower graphs
+ *                     (MultiPathNet measured 2.3e-3 with it: outside the 1e-3 contract). Environment: MPN_FC_W16.
  *   "roi_impl"        fused Foveal + ROI pooling kernel: 0 = roi_pool_cluster_kernel (default: 4-CTA clusters, the
  *                     L2 norm reduced over distributed shared memory), 1 = the round-1 kernel (one block stages a
  *                     normalised level's whole vector), 2 = the round-1 two-pass variant (sum-of-squares pre-pass +

@@ -451,8 +451,12 @@ int plan_heads(mpn_model *m, int64_t R) {
     // the previous layer's epilogue otherwise); every reader of such a slot must be a w16 Linear (or the FLATTEN in front
     // of one), else the slot stays bf16. mpn_ctx_set_option("fc_w16", 0) / MPN_FC_W16=0 switches the scheme off.
     {
-      static const int w16_env = [] { const char *e = getenv("MPN_FC_W16"); return (e && e[0] == '0') ? 0 : 1; }();
-      const int w16_on = ctx->opt_fc_w16 >= 0 ? ctx->opt_fc_w16 : w16_env;
+      // Default (option / environment unset): ON for single-tower graphs (Fast R-CNN: cfg 2 measures 4-5e-4 on the scores, the
+      // figure the CPU emulation predicted), OFF for multi-tower graphs — the first B200 run of cfg 3 with w16 in all five
+      // towers measured 2.3e-3: the class Linear reads a 4 x 4096 concat of w16 outputs and its logits are large enough that
+      // the weight plane's 2^-12 becomes a visible softmax error (tests/test_model_gpu.py::test_multipathnet_full_size_cfg3).
+      static const int w16_env = [] { const char *e = getenv("MPN_FC_W16"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+      const int w16_on = ctx->opt_fc_w16 >= 0 ? ctx->opt_fc_w16 : (w16_env >= 0 ? w16_env : (m->towers.size() == 1 ? 1 : 0));
       std::map<int, int> &fmt = X.slot_fmt;
       fmt.clear();
       auto wants = [&](const mpn_layer &L) {

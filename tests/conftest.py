@@ -32,3 +32,13 @@ def rel_err(a, b):
     import numpy as np
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def record_parity(name, **values):
+    """append one JSON line of measured parity figures to $MPN_PARITY_LOG (the GPU run scripts set it; the numbers end up
+    under profiles/): the bars are asserted by the tests, the log keeps HOW FAR inside them a run was"""
+    import json, os
+    path = os.environ.get("MPN_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if not isinstance(v, (list, tuple, str)) else v) for k, v in values.items()}}) + "\n")

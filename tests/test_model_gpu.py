@@ -7,7 +7,7 @@ import pytest
 import multipathnet_b200 as mpn
 from multipathnet_b200 import models, workloads as wl
 from oracle import graphs as G, ref as O
-from conftest import rel_err
+from conftest import rel_err, record_parity
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
@@ -184,6 +184,7 @@ def test_vgg16_full_size_cfg2(ctx):
         assert abs(tf / 1e9 - 294.0) < 0.1 and abs(hf / 1e9 - 239.9) < 0.2
         m.close()
     print("cfg2 scores / boxes rel err: fc_w16=1", errs[1], " fc_w16=0", errs[0])
+    record_parity("cfg2_full_size", scores_w16=errs[1][0], boxes_w16=errs[1][1], scores_3prod=errs[0][0], boxes_3prod=errs[0][1])
     assert errs[0][0] < 2e-4            # the three-product path keeps its margin
 
 
@@ -206,17 +207,32 @@ def test_resnet50_integral_small(ctx):
 
 
 def test_multipathnet_full_size_cfg3(ctx):
-    """BASELINE configs[2] at full size: VGG-16 MultiPathNet, 5 towers, 600x800, 1000 SharpMask-shaped ROIs, C=81"""
+    """BASELINE configs[2] at full size: VGG-16 MultiPathNet, 5 towers, 600x800, 1000 SharpMask-shaped ROIs, C=81.
+    The default numerics of a multi-tower graph are the three-product split in every layer; forcing the two-product fp16-weight
+    kernels into the five towers' fc6 / fc7 ("fc_w16" = 1) is measured beside it and must NOT be what the default does
+    (first B200 run: 2.3e-3 on the scores, outside the contract)."""
     spec = models.vgg16_multipathnet(81, seed=1234)
-    m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
     img, boxes = _inputs(spec, 600, 800, 1000, 3, sharp=True)
+    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600, nms_fn=lambda sb, thr: np.zeros(0, np.int64))
+    m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
     scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
-    rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 800, 600)
-    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    es, eb = rel_err(scores, rs), rel_err(bboxes, rb)
+    assert es < TOL and eb < TOL, (es, eb)
     assert_nms_every_class(scores, bboxes, keeps)
     tf, hf = m.last_flops()
     assert abs(hf / 1e12 - 1.458) < 0.01                     # SURVEY 8a12: 1.458 GFLOP/ROI x 1000
     m.close()
+    ctx.set_option("fc_w16", 1)
+    try:
+        m = mpn.Model(ctx, spec, max_rois=1024, max_h=608, max_w=800)
+        s16, b16, _ = m.detect_nms(img, boxes, 1.0, 800, 600, -1.5, 0.3)
+        m.close()
+    finally:
+        ctx.set_option("fc_w16", -1)
+    e16 = (rel_err(s16, rs), rel_err(b16, rb))
+    record_parity("cfg3_full_size", scores_default=es, boxes_default=eb, scores_forced_w16=e16[0], boxes_forced_w16=e16[1])
+    assert not np.array_equal(s16, scores)                   # the default really is the other numerics
+    assert e16[0] < 1e-2 and e16[1] < 1e-2                    # still a sane forward, just not inside the contract
 
 
 def test_resnet50_full_size_cfg4(ctx):
@@ -226,7 +242,9 @@ def test_resnet50_full_size_cfg4(ctx):
     img, boxes = _inputs(spec, 800, 1000, 2000, 4, sharp=True)
     scores, bboxes, keeps = m.detect_nms(img, boxes, 1.0, 1000, 800, -1.5, 0.3)
     rs, rb, _ = G.test_one(spec, img, boxes, 1.0, 1000, 800, nms_fn=lambda sb, thr: np.zeros(0, np.int64))
-    assert rel_err(scores, rs) < TOL and rel_err(bboxes, rb) < TOL
+    es, eb = rel_err(scores, rs), rel_err(bboxes, rb)
+    record_parity("cfg4_full_size", scores=es, boxes=eb)
+    assert es < TOL and eb < TOL, (es, eb)
     assert_nms_every_class(scores, bboxes, keeps)                       # 80 classes x 2000 boxes
     tf, hf = m.last_flops()
     assert abs(tf / 1e9 - 104.9) < 1.5 and abs(hf / 2000 / 1e9 - 1.62) < 0.02

@@ -57,13 +57,15 @@ def check_tower(spec, m, rois, tower, rows, ref=None, fp16_planes=False):
     ref = oracle_pooled(spec, m, rois, tower, rows) if ref is None else ref
     assert got.shape == ref.shape
     if fp16_planes:
-        # the pooled tensor feeds a "w16" Linear and is stored as fp16 hi / lo planes: 22 significant bits, but an absolute
-        # 2^-24 grid (fp16 subnormals) — exact wherever the value's own last bit (17 significant bits) is on that grid
+        # the pooled tensor feeds a "w16" Linear and is stored as fp16 hi / lo planes: 22 significant bits on an absolute
+        # 2^-24 grid (fp16 subnormals). The value itself is hi + lo of two bf16 planes and can carry all 24 fp32 bits (a small
+        # `lo` sits far below `hi`), so: within 2^-22 relative + the grid everywhere, and exact for the bulk of the values
         assert not t.normalize
-        big = np.abs(ref) >= 2.0 ** -7
-        assert np.array_equal(got[big], ref[big]), f"tower {tower}: {np.count_nonzero(got[big] != ref[big])} values >= 2^-7 differ"
-        assert np.abs(got - ref).max() <= 2.0 ** -24
-        return 1.0
+        err = np.abs(got - ref)
+        assert (err <= 2.0 ** -22 * np.abs(ref) + 2.0 ** -24).all(), f"tower {tower}: worst {err.max():.3e}"
+        same = float(np.mean(got == ref))
+        assert same > 0.99, f"tower {tower}: only {same:.4f} of the fp16-plane values are exact"
+        return same
     if not t.normalize:
         assert np.array_equal(got, ref), f"tower {tower}: {np.count_nonzero(got != ref)} of {got.size} pooled values differ"
         return 1.0
