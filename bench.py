@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[1], the config `metric` is quoted on): VGG-16 Fast R-CNN, one
 600x800 image + 1000 random proposals per step, C=21, fp32-faithful (bf16x3 split on tcgen05, fp32
-accumulate). A "step" = ONE image through trunk -> fused ROI pooling -> fc6/fc7/cls/bbox -> BBoxNorm
+accumulate; fc6 / fc7 two fp16 products). A "step" = ONE image through trunk -> fused ROI pooling -> fc6/fc7/cls/bbox -> BBoxNorm
 -> decode + clamp -> softmax -> per-class gather -> batched NMS (20 classes), i.e. everything
 ImageDetect:detect + Tester_FRCNN:testOne do per image.
 
@@ -557,9 +557,15 @@ def main():
     peak_tf, hbm_gbs, peak_src = load_peaks()
     achieved = tflop_step / (tc_ms_step / 1e3) if tc_ms_step > 0 else 0.0
     n_tc = prof["conv_gemm_tc"][1] // args.steps
-    roofline = {"bound": "tensor", "kernel": "conv_gemm_tc_kernel<BN> (tcgen05 bf16x3 implicit-GEMM, %d launches/step)" % n_tc,
+    # issued MMA work: three bf16 products per algorithmic MAC, two fp16 products in the "w16" Linears (fc6 / fc7 of single-tower graphs)
+    w16_on = os.environ.get("MPN_FC_W16", "") != "0"
+    tflop_w16 = (models.w16_flops_per_roi(spec) * R / 1e12) if w16_on else 0.0
+    issued = (3.0 * (tflop_step - tflop_w16) + 2.0 * tflop_w16) / (tc_ms_step / 1e3) if tc_ms_step > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv3x3_tc_kernel / conv_gemm_tc_kernel<BN> (tcgen05 implicit-GEMM, %d launches/step)" % n_tc,
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "issued_frac": 3.0 * achieved / peak_tf if peak_tf else None, "peak_source": peak_src,
+                "issued_frac": issued / peak_tf if peak_tf else None, "issued_tflops": issued,
+                "products_per_mac": {"three_bf16": tflop_step - tflop_w16, "two_fp16_w16": tflop_w16, "unit": "algorithmic TFLOP/step"},
+                "peak_source": peak_src,
                 "traffic": (traffic_from_profiles(args.config) or {}).get("dram_bytes_per_launch"),   # bytes, or None
                 "traffic_detail": traffic_from_profiles(args.config),
                 "algorithmic_tflop_per_step": tflop_step, "kernel_ms_per_step": tc_ms_step,
@@ -578,7 +584,8 @@ def main():
                            "ms": collective_ms, "bytes_per_rank": args.steps * REC * 4, "in_timed_region": True, "in_e2e_region": True,
                            "detections_per_image_mean": float(det_counts.mean())},
             "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (bf16x3 split on tcgen05, fp32 accumulate)", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32 (tcgen05 split emulation, fp32 accumulate: 3 bf16 products per MAC" + (", 2 fp16 products in fc6/fc7)" if tflop_w16 > 0 else ")"), "data": "synthetic",
             "config": bench_config(world),
             "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight) + mpn_dist_all_gather (records to host) at the end",

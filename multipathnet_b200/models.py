@@ -259,3 +259,25 @@ def head_flops_per_roi(spec: ModelSpec) -> float:
     for hd in list(spec.cls_heads) + [spec.bbox_head]:
         fl += 2.0 * hd.col_len * hd.cout
     return fl
+
+
+def w16_flops_per_roi(spec: ModelSpec) -> float:
+    """algorithmic FLOPs per ROI of the Linears that take the two-product "w16" numerics by default (csrc/model.cu, plan_heads:
+    single-tower graphs only; a Linear on a 1 x 1 map — incl. the one that follows a FLATTEN, whose kernel spans the pooled
+    map — with >= 2048 inputs and >= 1024 outputs, no residual): what `issued` MMA work is counted x2 instead of x3 for"""
+    if len(spec.towers) != 1:
+        return 0.0
+    fl = 0.0
+    for t in spec.towers:
+        shp = {0: (t.pooled_h, t.pooled_w)}
+        for L in t.layers:
+            h, w = shp[L.in_slot]
+            if L.kind == MPN_LAYER_CONV:
+                ho, wo = (h + 2 * L.pad - L.kh) // L.stride + 1, (w + 2 * L.pad - L.kw) // L.stride + 1
+                k_in = L.cin * L.kh * L.kw
+                if ho == 1 and wo == 1 and L.kh == h and L.kw == w and L.pad == 0 and L.residual_slot < 0 and k_in >= 2048 and L.cout >= 1024:
+                    fl += 2.0 * k_in * L.cout
+                shp[L.out_slot] = (ho, wo)
+            else:
+                shp[L.out_slot] = (1, 1)
+    return fl
