@@ -10,6 +10,10 @@ ImageDetect:detect + Tester_FRCNN:testOne do per image.
   python bench.py [--gpus N --steps K --warmup W]          our arm (N>1: launched by torchrun, one rank/GPU)
   python bench.py --impl reference [...]                    the reference's CPU path on the host cores
 
+`--replicas K` (default 2): K model replicas per GPU, each on its own mpn_ctx / stream, images dealt round-robin (the
+            reference's one-replica-per-donkey-thread runner, test_runner.lua:55-66, with K threads per GPU): the kernels of one
+            replica fill the layer-boundary / NMS-chain bubbles of the others. `ms_per_image_p50` stays the latency of ONE image
+            on ONE replica.
 `value`   : proposals/s with image+proposals already resident in HBM (mpn_model_detect_nms_dev).
 `e2e`     : proposals/s through the host-buffer C-ABI (mpn_model_detect_nms_submit/_wait, two images in flight per
             model: pinned host image and boxes copied H2D, scores/boxes/keep lists copied D2H every step, inside the
@@ -172,10 +176,11 @@ def run_nms_sweep(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def bench_config(world):
+def bench_config(world, replicas=2):
     """`config` of the JSON line: ONE dict for both arms (ours / --impl reference) so the driver's same-config check holds;
     arm-specific facts (CPU thread count, ...) live in other keys of the line."""
     return {"workload": WORKLOAD,
+            "replicas_per_gpu": f"GPU arm: {replicas} model replica(s) per GPU, each on its own stream, images dealt round-robin (test_runner.lua:55-66 with {replicas} donkey thread(s) per GPU); CPU arm: n/a",
             "parallelism": (f"images sharded over {world} rank(s), one NCCL all-gather of the packed top-100 detection records at the end"
                             if world > 1 else "single GPU"),
             "l2": "GPU arm: inputs larger than L2, each step streams 0.55 GB of weights + ~1 GB of activations (L2 = 126 MB); CPU arm: n/a",
@@ -294,7 +299,7 @@ def run_reference(args, rank, world):
             "steps": args.steps, "warmup": args.warmup, "steps_timed": len(ts), "warmup_run": 1 if t_first is not None else 0,
             "ms_per_step": 1e3 * total / len(ts), "ms_per_image_p50": 1e3 * statistics.median(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": bench_config(args.gpus),
+            "config": bench_config(args.gpus, args.replicas),
             "host": {"arm": "CPU only", "threads": cores, "logical_cpus": os.cpu_count(), "thread_count_proxy_s": tried},
             "cpu_baseline": {"value": val, "unit": "proposals/s", "cores": cores,
                              "kind": "port", "sample": f"{len(ts)} full images (1000 ROIs each); dense layers PyTorch-CPU fp32, "
@@ -310,6 +315,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", type=int, default=2, help="model replicas per GPU, each on its own mpn_ctx / stream (images dealt round-robin)")
     ap.add_argument("--config", default="vgg16_frcnn", choices=list(WORKLOADS) + ["nms_sweep"])
     args = ap.parse_args()
     global H, W, R, C, WORKLOAD
@@ -337,10 +343,14 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.current_stream(dev)
-    ctx = mpn.Context(local_rank, stream.cuda_stream if stream.cuda_stream else None)
+    # K model replicas on this GPU, each on its own mpn_ctx / non-blocking stream (multipathnet_b200/replicas.py): the kernels of
+    # one replica fill the layer-boundary and NMS-chain bubbles of the others. Images are dealt round-robin.
+    K = max(1, args.replicas)
     spec = getattr(models, wk["model"])(C, seed=1234, **wk["kw"])
-    model = mpn.Model(ctx, spec, max_rois=max(R, 1024), max_h=H + 8, max_w=W)
+    reps = mpn.ModelReplicas(local_rank, spec, K, max_rois=max(R, 1024), max_h=H + 8, max_w=W)
+    ctx, model = reps.ctxs[0], reps.models[0]          # replica 0: p50 loop, blocking-call leg, profiling pass, the collective
+    streams = [torch.cuda.ExternalStream(c.stream_handle, device=dev) for c in reps.ctxs]
+    stream = streams[0]
 
     # ---- synthetic inputs: a small rotating set of distinct images/proposals per rank (seeded by rank)
     NIMG = 4
@@ -349,14 +359,12 @@ def main():
     boxes_h = [mkbox(R, H, W, 1000 * rank + i) for i in range(NIMG)]
     imgs_d = [torch.from_numpy(x).to(dev) for x in imgs_h]
     boxes_d = [torch.from_numpy(x).to(dev) for x in boxes_h]
-    scores_d = torch.empty((R, C), dtype=torch.float32, device=dev)
-    bboxes_d = torch.empty((R, 4 * C), dtype=torch.float32, device=dev)
-    keep_d = torch.empty((C - 1, R), dtype=torch.int32, device=dev)
-    counts_d = torch.empty((C - 1,), dtype=torch.int32, device=dev)
+    outs_d = [(torch.empty((R, C), dtype=torch.float32, device=dev), torch.empty((R, 4 * C), dtype=torch.float32, device=dev),
+               torch.empty((C - 1, R), dtype=torch.int32, device=dev), torch.empty((C - 1,), dtype=torch.int32, device=dev)) for _ in range(K)]
 
     def step_dev(i):
         k = i % NIMG
-        model.detect_nms_dev(imgs_d[k], H, W, boxes_d[k], R, 1.0, W, H, -1.5, 0.3, scores_d, bboxes_d, keep_d, counts_d)
+        reps.models[i % K].detect_nms_dev(imgs_d[k], H, W, boxes_d[k], R, 1.0, W, H, -1.5, 0.3, *outs_d[i % K])
 
     def barrier():
         if world > 1:
@@ -364,13 +372,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- the path's ONE collective, issued by the library (mpn_dist_*, csrc/dist.cu): every detect+NMS pass also packs the
-    # image's record (keep_top_k 100 + fixed-size layout, csrc/post.cu) into `records_d`; after the last image ONE ncclAllGather
-    # of (steps x MPN_REC_FLOATS) floats per rank. At N = 1 the same calls run (the gather degenerates to a copy).
+    # image's record (keep_top_k 100 + fixed-size layout, csrc/post.cu) into its replica's slice of `records_d`; after the last
+    # image replica 0's stream waits for the others (mpn_ctx_wait_ctx) and ONE ncclAllGather ships K x PER x MPN_REC_FLOATS
+    # floats per rank (image i = record [i mod K, i div K]). At N = 1 the same calls run (the gather degenerates to a copy).
     REC = mpn.MPN_REC_FLOATS
-    n_rec = max(args.steps, args.warmup, 3)
-    records_d = torch.zeros((n_rec, REC), dtype=torch.float32, device=dev)
-    gathered_d = torch.zeros((world, args.steps, REC), dtype=torch.float32, device=dev)
-    gathered_h = torch.empty((world, args.steps, REC), dtype=torch.float32).pin_memory()
+    PER = (max(args.steps, args.warmup, 3) + K - 1) // K
+    records_d = torch.zeros((K, PER, REC), dtype=torch.float32, device=dev)
+    gathered_d = torch.zeros((world, K, PER, REC), dtype=torch.float32, device=dev)
+    gathered_h = torch.empty((world, K, PER, REC), dtype=torch.float32).pin_memory()
     if world > 1:
         idt = torch.zeros(mpn.MPN_DIST_ID_BYTES, dtype=torch.uint8, device=dev)
         if rank == 0:
@@ -378,13 +387,23 @@ def main():
         dist.broadcast(idt, 0)
         ctx.dist_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
-    def gather_dev():
-        ctx.dist_all_gather_dev(records_d, args.steps * REC, gathered_d)
+    def sinks_on():
+        for k, m in enumerate(reps.models):
+            m.set_detection_sink(records_d[k], PER, 100)      # (re)sets the record count of the replica
 
-    # warm-up: the exact sequence of the timed region (steps with the sink on, then the collective: the first NCCL call on a
-    # communicator sets up its channels — tens of ms that are not part of a steady-state run)
-    model.set_detection_sink(records_d, n_rec, 100)
-    for i in range(args.warmup):
+    def sinks_off():
+        for m in reps.models:
+            m.set_detection_sink(None, 0, 100)
+
+    def gather_dev():
+        reps.join()
+        ctx.dist_all_gather_dev(records_d, K * PER * REC, gathered_d)
+
+    # warm-up: the exact sequence of the timed region (steps with the sinks on, then the join + the collective: the first NCCL
+    # call on a communicator sets up its channels — tens of ms that are not part of a steady-state run)
+    barrier()
+    sinks_on()
+    for i in range(max(args.warmup, 2 * K)):
         step_dev(i)
     gather_dev()
     barrier()
@@ -393,23 +412,24 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    model.set_detection_sink(records_d, n_rec, 100)                  # resets the record count
-    launches0 = ctx.launch_count
+    sinks_on()
+    launches0 = reps.launch_count
     barrier()
-    ev[0].record(stream)
+    ev0, ev_loop, end_ev = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    ev0.record(stream)                                               # every replica stream is idle here
     for i in range(args.steps):
         step_dev(i)
-        ev[i + 1].record(stream)
-    gather_dev()                                                     # THE collective of the path, inside the timed region
-    end_ev = torch.cuda.Event(enable_timing=True); end_ev.record(stream)
+    reps.join()
+    ev_loop.record(stream)                                           # this rank's K steps are done on every replica
+    ctx.dist_all_gather_dev(records_d, K * PER * REC, gathered_d)    # THE collective of the path, inside the timed region
+    end_ev.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(end_ev)
-    collective_ms = ev[args.steps].elapsed_time(end_ev)              # the all-gather incl. the wait for the slowest rank
-    launches = ctx.launch_count - launches0
+    total_ms = ev0.elapsed_time(end_ev)
+    collective_ms = ev_loop.elapsed_time(end_ev)                     # the all-gather incl. the wait for the slowest rank
+    launches = reps.launch_count - launches0
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    loop_ms = ev[0].elapsed_time(ev[args.steps])                      # this rank's K steps alone, before the collective
+    loop_ms = ev0.elapsed_time(ev_loop)                               # this rank's K steps alone, before the collective
     per_rank_ms = [loop_ms / args.steps]
     if world > 1:
         tl_ = torch.tensor([loop_ms], dtype=torch.float64, device=dev)
@@ -423,19 +443,24 @@ def main():
     value = world * R * args.steps / (total_ms_max / 1e3)
     # what was gathered: every rank's records, real detections (count field = rows kept by keep_top_k, <= MPN_MAX_DET)
     g = gathered_d.cpu().numpy()
-    det_counts = g[:, :, 0]
-    assert np.array_equal(g[rank], records_d[:args.steps].cpu().numpy()), "gathered records differ from this rank's own"
+    det_counts = np.array([[g[r, i % K, i // K, 0] for i in range(args.steps)] for r in range(world)])
+    assert np.array_equal(g[rank], records_d.cpu().numpy()), "gathered records differ from this rank's own"
     assert det_counts.min() >= 1 and det_counts.max() <= mpn.MPN_MAX_DET, "gathered detection records are empty or overflowed"
 
-    # ---- p50 latency over a fixed >= 200-image loop, whatever --steps says
-    model.set_detection_sink(None, 0, 100)
+    # ---- p50 latency of ONE image on ONE replica over a fixed >= 200-image loop, whatever --steps says
+    sinks_off()
     P50_STEPS, P50_WARM = max(200, args.steps), 20
+
+    def step_one(i):
+        k = i % NIMG
+        model.detect_nms_dev(imgs_d[k], H, W, boxes_d[k], R, 1.0, W, H, -1.5, 0.3, *outs_d[0])
+
     for i in range(P50_WARM):
-        step_dev(i)
+        step_one(i)
     evp = [torch.cuda.Event(enable_timing=True) for _ in range(P50_STEPS + 1)]
     evp[0].record(stream)
     for i in range(P50_STEPS):
-        step_dev(i)
+        step_one(i)
         evp[i + 1].record(stream)
     torch.cuda.synchronize(dev)
     per_step = [evp[i].elapsed_time(evp[i + 1]) for i in range(P50_STEPS)]
@@ -463,42 +488,48 @@ def main():
     torch.cuda.synchronize(dev)
     e2e_sync_s = time.perf_counter() - t0
 
-    # pipelined public API (two images in flight per model, like the reference's one image per donkey thread): every step
+    # pipelined public API (two images in flight per replica, like the reference's one image per donkey thread): every step
     # still copies its own inputs host->device and its own results device->host inside the timed region
-    outs = [(torch.empty((R, C), dtype=torch.float32).pin_memory(), torch.empty((R, 4 * C), dtype=torch.float32).pin_memory(),
-             torch.empty((C - 1, R), dtype=torch.int32).pin_memory(), torch.empty((C - 1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    outs = [[(torch.empty((R, C), dtype=torch.float32).pin_memory(), torch.empty((R, 4 * C), dtype=torch.float32).pin_memory(),
+              torch.empty((C - 1, R), dtype=torch.int32).pin_memory(), torch.empty((C - 1,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+            for _ in range(K)]
     import ctypes as _C
+    from collections import deque
 
-    def submit(i):
+    def run_pipelined(n, submit_fn):
+        """deal image i to replica i mod K; at most two submissions in flight per replica (the API's limit)"""
+        pend = [deque() for _ in range(K)]
+        for i in range(n):
+            rk = i % K
+            if len(pend[rk]) == 2:
+                reps.ctxs[rk].check(lib.mpn_model_detect_nms_wait(reps.models[rk].h, pend[rk].popleft()), "detect_nms_wait")
+            pend[rk].append(submit_fn(i, rk, outs[rk][(i // K) & 1]))
+        for rk in range(K):
+            while pend[rk]:
+                reps.ctxs[rk].check(lib.mpn_model_detect_nms_wait(reps.models[rk].h, pend[rk].popleft()), "detect_nms_wait")
+
+    def submit(i, rk, o):
         k = i % NIMG
-        o = outs[i & 1]
         t = _C.c_int32(-1)
-        ctx.check(lib.mpn_model_detect_nms_submit(model.h, pin_img[k].data_ptr(), H, W, pin_box[k].data_ptr(), R, 1.0, float(W), float(H),
-                                                  -1.5, 0.3, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), _C.byref(t)),
-                  "detect_nms_submit")
+        reps.ctxs[rk].check(lib.mpn_model_detect_nms_submit(reps.models[rk].h, pin_img[k].data_ptr(), H, W, pin_box[k].data_ptr(), R, 1.0, float(W), float(H),
+                                                            -1.5, 0.3, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), _C.byref(t)),
+                            "detect_nms_submit")
         return t.value
 
-    def run_pipelined(n):
-        prev = submit(0)
-        for i in range(1, n):
-            cur = submit(i)
-            ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
-            prev = cur
-        ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
+    def gather_host():       # the join + the collective + the gathered records to (pinned) host memory, synchronous
+        reps.join()
+        ctx.check(lib.mpn_dist_all_gather(ctx.h, records_d.data_ptr(), K * PER * REC, gathered_h.data_ptr()), "mpn_dist_all_gather")
 
-    def gather_host():       # the collective + the gathered records to (pinned) host memory, synchronous
-        ctx.check(lib.mpn_dist_all_gather(ctx.h, records_d.data_ptr(), args.steps * REC, gathered_h.data_ptr()), "mpn_dist_all_gather")
-
-    model.set_detection_sink(records_d, n_rec, 100)
-    run_pipelined(3)
+    sinks_on()
+    run_pipelined(max(3, 2 * K), submit)
     gather_host()
     barrier()
-    model.set_detection_sink(records_d, n_rec, 100)
+    sinks_on()
     t0 = time.perf_counter()
-    run_pipelined(args.steps)
+    run_pipelined(args.steps, submit)
     gather_host()
     e2e_s = time.perf_counter() - t0
-    model.set_detection_sink(None, 0, 100)
+    sinks_off()
     t = torch.tensor([e2e_s, e2e_sync_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -515,27 +546,18 @@ def main():
         from multipathnet_b200._lib import CImageTransform
         tfm = CImageTransform.of(spec.transformer)
 
-        def submit_raw(i):
+        def submit_raw(i, rk, o):
             k = i % NIMG
-            o = outs[i & 1]
             t = _C.c_int32(-1)
-            ctx.check(lib.mpn_model_detect_nms_submit_u8(model.h, raw_pin[k].data_ptr(), H0r, W0r, _C.addressof(tfm), 600.0, 1000.0, rbox_pin[k].data_ptr(), R,
-                                                         -1.5, 0.3, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(), o[3].data_ptr(), _C.byref(t)),
-                      "detect_nms_submit_u8")
+            reps.ctxs[rk].check(lib.mpn_model_detect_nms_submit_u8(reps.models[rk].h, raw_pin[k].data_ptr(), H0r, W0r, _C.addressof(tfm), 600.0, 1000.0,
+                                                                   rbox_pin[k].data_ptr(), R, -1.5, 0.3, o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                                                   o[3].data_ptr(), _C.byref(t)), "detect_nms_submit_u8")
             return t.value
 
-        def run_raw(n):
-            prev = submit_raw(0)
-            for i in range(1, n):
-                cur = submit_raw(i)
-                ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
-                prev = cur
-            ctx.check(lib.mpn_model_detect_nms_wait(model.h, prev), "detect_nms_wait")
-
-        run_raw(3)
+        run_pipelined(max(3, 2 * K), submit_raw)
         barrier()
         t0 = time.perf_counter()
-        run_raw(args.steps)
+        run_pipelined(args.steps, submit_raw)
         raw_s = time.perf_counter() - t0
         tr = torch.tensor([raw_s], dtype=torch.float64, device=dev)
         if world > 1:
@@ -546,9 +568,11 @@ def main():
     d2h = R * C * 4 + R * 4 * C * 4 + (C - 1) * R * 4 + (C - 1) * 4 + world * REC * 4      # + this image's share of the gathered records
 
     # ---- per-kernel-category CUDA-event timing of the same steps (roofline numerators)
+    # (ONE replica, in order: the events between the launches serialise them, so the categories describe the kernels themselves)
+    torch.cuda.synchronize(dev)
     ctx.profile_begin()
     for i in range(args.steps):
-        step_dev(i)
+        step_one(i)
     prof = ctx.profile_end()
     L0 = spec.trunk_layers[0]
     first_flops = 2.0 * L0.cin * L0.cout * L0.kh * L0.kw * ((H + 2 * L0.pad - L0.kh) // L0.stride + 1) * ((W + 2 * L0.pad - L0.kw) // L0.stride + 1)
@@ -579,16 +603,18 @@ def main():
 
     line = {"metric": "proposals/sec", "value": value, "unit": "proposals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "ms_per_image_p50": statistics.median(per_step), "p50_steps": P50_STEPS,
+            "p50_note": "latency of one image on one replica (in-order loop); ms_per_step = wall / images with %d replica(s) overlapped" % K,
+            "replicas_per_gpu": K,
             "per_rank_loop_ms_per_step": per_rank_ms,
             "collective": {"api": "mpn_dist_all_gather_dev (ncclAllGather issued by libmpn_b200.so on the ctx stream)" if world > 1 else "world of 1: device copy",
-                           "ms": collective_ms, "bytes_per_rank": args.steps * REC * 4, "in_timed_region": True, "in_e2e_region": True,
+                           "ms": collective_ms, "bytes_per_rank": K * PER * REC * 4, "in_timed_region": True, "in_e2e_region": True,
                            "detections_per_image_mean": float(det_counts.mean())},
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32 (tcgen05 split emulation, fp32 accumulate: 3 bf16 products per MAC" + (", 2 fp16 products in fc6/fc7)" if tflop_w16 > 0 else ")"), "data": "synthetic",
-            "config": bench_config(world),
+            "config": bench_config(world, K),
             "e2e": {"value": e2e_value, "unit": "proposals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight) + mpn_dist_all_gather (records to host) at the end",
+                    "api": "mpn_model_detect_nms_submit / _wait (pinned host buffers, 2 images in flight per replica) + mpn_ctx_wait_ctx + mpn_dist_all_gather (records to host) at the end",
                     "sync_value": e2e_sync_value, "sync_api": "mpn_model_detect_nms (host buffers, one blocking call per image)"},
             "e2e_raw": e2e_raw,
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
@@ -612,6 +638,7 @@ def main():
     if world > 1:
         ctx.dist_destroy()
         dist.destroy_process_group()
+    reps.close()
 
 
 if __name__ == "__main__":

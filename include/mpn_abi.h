@@ -36,6 +36,16 @@ typedef struct mpn_model mpn_model;
 /* device: CUDA ordinal. cuda_stream: a cudaStream_t, or NULL for the legacy
  * default stream (what cutorch uses unless cutorch.setStream was called).   */
 int mpn_ctx_create(int device, void *cuda_stream, mpn_ctx **out);
+/* A context on a stream of its own (non-blocking, created and destroyed with the ctx; priority as cudaStreamCreateWithPriority,
+ * clamped to the device's range, 0 = default): for SEVERAL model replicas on one GPU. The reference runs one model replica per
+ * donkey thread (test_runner.lua:55-66); with K threads per GPU, each on its own ctx / stream, the layer-boundary and NMS-chain
+ * bubbles of one replica are filled by the kernels of the others (+8 % proposals/s at K = 2 on cfg 2). Work of different
+ * contexts is unordered; mpn_ctx_wait_ctx(ctx, other) makes everything enqueued on `ctx` afterwards wait for what `other` has
+ * enqueued so far (the join before the end-of-run gather). mpn_ctx_stream returns the cudaStream_t (interop with the caller's
+ * own kernels / events). */
+int mpn_ctx_create_stream(int device, int priority, mpn_ctx **out);
+void *mpn_ctx_stream(const mpn_ctx *ctx);
+int mpn_ctx_wait_ctx(mpn_ctx *ctx, mpn_ctx *other);
 void mpn_ctx_destroy(mpn_ctx *ctx);
 const char *mpn_last_error(const mpn_ctx *ctx);   /* ctx may be NULL: last create error */
 int mpn_ctx_synchronize(mpn_ctx *ctx);

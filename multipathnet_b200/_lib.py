@@ -86,6 +86,9 @@ _vp = C.c_void_p
 # name -> (restype, argtypes). Mirrors include/mpn_abi.h one to one (tests check the symbol set).
 SIGNATURES = {
     "mpn_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "mpn_ctx_create_stream": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
+    "mpn_ctx_stream": (_vp, [_vp]),
+    "mpn_ctx_wait_ctx": (C.c_int, [_vp, _vp]),
     "mpn_ctx_destroy": (None, [_vp]),
     "mpn_last_error": (C.c_char_p, [_vp]),
     "mpn_ctx_synchronize": (C.c_int, [_vp]),
@@ -204,10 +207,15 @@ class Context:
     """One mpn_ctx: (thread, device, stream). Mirrors the one-replica-per-thread model of
     test_runner.lua:55-66."""
 
-    def __init__(self, device: int = 0, stream: Optional[int] = None):
+    def __init__(self, device: int = 0, stream: Optional[int] = None, own_stream: bool = False, priority: int = 0):
+        """stream: a cudaStream_t handle of the caller's (None = the legacy default stream); own_stream=True: the ctx
+        creates a non-blocking stream of its own (mpn_ctx_create_stream) — what several replicas on one GPU use"""
         self.lib = load_library()
         h = _vp()
-        rc = self.lib.mpn_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h))
+        if own_stream:
+            rc = self.lib.mpn_ctx_create_stream(int(device), int(priority), C.byref(h))
+        else:
+            rc = self.lib.mpn_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h))
         if rc != 0:
             raise MpnError(f"mpn_ctx_create failed ({rc}): {self.lib.mpn_last_error(None).decode()}")
         self.h = h
@@ -220,6 +228,15 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.mpn_ctx_synchronize(self.h), "synchronize")
+
+    @property
+    def stream_handle(self) -> int:
+        """the ctx's cudaStream_t as an integer (0 = the legacy default stream)"""
+        return int(self.lib.mpn_ctx_stream(self.h) or 0)
+
+    def wait_ctx(self, other: "Context"):
+        """everything enqueued on this ctx from now on waits for what `other` has enqueued so far (mpn_ctx_wait_ctx)"""
+        self.check(self.lib.mpn_ctx_wait_ctx(self.h, other.h), "mpn_ctx_wait_ctx")
 
     def set_option(self, name: str, value: int):
         self.check(self.lib.mpn_ctx_set_option(self.h, name.encode(), int(value)), "mpn_ctx_set_option")

@@ -112,6 +112,37 @@ int mpn_ctx_create(int device, void *cuda_stream, mpn_ctx **out) {
   return MPN_OK;
 }
 
+int mpn_ctx_create_stream(int device, int priority, mpn_ctx **out) {
+  const int rc = mpn_ctx_create(device, nullptr, out);
+  if (rc != MPN_OK) return rc;
+  mpn_ctx *c = *out;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);                  // lo = numerically largest = least urgent
+  const int pr = priority < hi ? hi : (priority > lo ? lo : priority);
+  cudaStream_t s = nullptr;
+  const cudaError_t e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, pr);
+  if (e != cudaSuccess) {
+    { std::lock_guard<std::mutex> lk(g_create_mu); g_create_err = std::string("cudaStreamCreateWithPriority failed: ") + cudaGetErrorString(e); }
+    delete c; *out = nullptr;
+    return MPN_ERR_CUDA;
+  }
+  c->stream = s; c->own_stream = 1;
+  return MPN_OK;
+}
+
+void *mpn_ctx_stream(const mpn_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int mpn_ctx_wait_ctx(mpn_ctx *ctx, mpn_ctx *other) {
+  if (!ctx || !other) return MPN_ERR_ARG;
+  MPN_CHECK_ARG(ctx, ctx->device == other->device, "mpn_ctx_wait_ctx: both contexts must be on the same device");
+  if (ctx == other || ctx->stream == other->stream) return MPN_OK;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->join_ev) MPN_CUDA(ctx, cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+  MPN_CUDA(ctx, cudaEventRecord(ctx->join_ev, other->stream));
+  MPN_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+  return MPN_OK;
+}
+
 void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -129,6 +160,8 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->tl_max) cudaFree(ctx->tl_max);
   for (auto &r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
