@@ -35,7 +35,12 @@ function M.ctx()
    local dev = cutorch and (cutorch.getDevice() - 1) or 0
    if not ctxs[dev] then
       local out = ffi.new('mpn_ctx*[1]')
-      local rc = C.mpn_ctx_create(dev, nil, out)     -- nil stream = legacy default stream (cutorch's default)
+      -- default: nil stream = the legacy default stream (cutorch's default), so ordering with surrounding Torch ops is kept.
+      -- mpn_replica_streams=1: a stream of its own, for several donkey threads (model replicas) per GPU whose kernels should
+      -- overlap (INTEGRATION.md section 5); CudaTensors handed to _dev entry points must then be synchronised by the caller.
+      local rc
+      if os.getenv('mpn_replica_streams') == '1' then rc = C.mpn_ctx_create_stream(dev, 0, out)
+      else rc = C.mpn_ctx_create(dev, nil, out) end
       if rc ~= 0 then error('mpn_ctx_create: ' .. ffi.string(C.mpn_last_error(nil))) end
       ctxs[dev] = ffi.gc(out[0], C.mpn_ctx_destroy)
    end
