@@ -64,7 +64,9 @@ const char *mpn_version(void);
  *                     normalised level's whole vector), 2 = the round-1 two-pass variant (sum-of-squares pre-pass +
  *                     unstaged writing pass), 3 = the cluster kernel exchanging its partial sums through
  *                     barrier.cluster instead of st.async, 4 = roi_pool_bulk_kernel (the pyramid blocks arrive in
- *                     shared-memory slots by cp.async.bulk). Environment: MPN_ROI_IMPL.
+ *                     shared-memory slots by cp.async.bulk), 5 = roi_pool_ring_kernel (one persistent CTA per SM: a
+ *                     producer warp keeps a ring of bulk-copy stages full, 16 consumer warps drain it).
+ *                     Environment: MPN_ROI_IMPL.
  *   "roi_norm_split"  older spelling: 1 selects roi_impl 2, 0 selects roi_impl 1 (MPN_ROI_NORM_SPLIT).          */
 int mpn_ctx_set_option(mpn_ctx *ctx, const char *name, int64_t value);
 /* per-category kernel timing for roofline reporting: between begin and end every launch group is

@@ -99,7 +99,7 @@ def test_fused_roi_small_unnormalised_and_regions_leaving_the_image(ctx):
     m.close()
 
 
-@pytest.mark.parametrize("roi_impl", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("roi_impl", [0, 1, 2, 3, 4, 5])
 def test_fused_roi_multipathnet_small_all_towers(ctx, roi_impl):
     """cfg 3 structure at reduced width: towers 0..3 = Foveal regions x1, x1.5, x2, x4 on conv5|conv4|conv3 with per-level
     L2 normalise; every implementation of the stage (0 = roi_pool_cluster_kernel, the default; 3 = the same with the
@@ -116,7 +116,7 @@ def test_fused_roi_multipathnet_small_all_towers(ctx, roi_impl):
         m.close()
 
 
-@pytest.mark.parametrize("roi_impl,fc_w16", [(0, 1), (0, 0), (1, 0), (1, 1), (4, 1), (4, 0)])
+@pytest.mark.parametrize("roi_impl,fc_w16", [(0, 1), (0, 0), (1, 0), (1, 1), (4, 1), (4, 0), (5, 1), (5, 0)])
 def test_fused_roi_full_size_cfg2(ctx, roi_impl, fc_w16):
     """BASELINE configs[1]: VGG-16 600x800, R=1000, 7x7 bins on conv5 — every pooled value of the timed kernel: bit-exact as
     bf16 planes (fc_w16 = 0), exact down to the fp16 subnormal grid as fp16 planes (the default: fc6 takes the w16 numerics)"""
@@ -140,7 +140,7 @@ def test_fused_roi_full_size_cfg3_all_towers(ctx):
         rois = run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
         blocks = (slice(0, 200), slice(800, 1000))                  # 400 of the 1000 ROIs per tower: ~30 s of oracle time in all
         refs = {(t, b.start): oracle_pooled(spec, m, rois, t, b) for t in range(len(spec.towers)) for b in blocks}
-        for impl in (0, 1, 2, 3, 4):
+        for impl in (0, 1, 2, 3, 4, 5):
             ctx.set_option("roi_impl", impl)
             run_detect(m, spec, 600, 800, 1000, 3, sharp=True)
             for t in range(len(spec.towers)):
@@ -151,7 +151,7 @@ def test_fused_roi_full_size_cfg3_all_towers(ctx):
         m.close()
 
 
-@pytest.mark.parametrize("roi_impl", [0, 4])
+@pytest.mark.parametrize("roi_impl", [0, 4, 5])
 def test_fused_roi_full_size_cfg4(ctx, roi_impl):
     """BASELINE configs[3]: ResNet-50, 800x1000, R=2000, 14x14 bins on layer3 (1024 channels) — rows from both ends"""
     spec = models.resnet50_fast_rcnn(81, seed=1234, integral_k=6)
