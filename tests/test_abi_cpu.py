@@ -37,7 +37,12 @@ def test_no_gpu_means_loud_failure_not_fallback():
         pytest.skip("GPU present")
     with pytest.raises(mpn.MpnError):
         mpn.Context(0)
+    with pytest.raises(mpn.MpnError):
+        mpn.Context(0, own_stream=True)                       # mpn_ctx_create_stream: the same loud failure
+    with pytest.raises(mpn.MpnError):
+        mpn.ModelReplicas(0, models.vgg16_fast_rcnn(21, seed=1, width_div=16, fc_dim=64), 2)
     lib = mpn.load_library()
+    assert lib.mpn_ctx_stream(None) is None and lib.mpn_ctx_wait_ctx(None, None) < 0
     assert len(lib.mpn_last_error(None)) > 0
     # NULL-handle calls are rejected, not crashes
     assert lib.mpn_ctx_synchronize(None) < 0
