@@ -13,7 +13,6 @@ which the end-of-run gather of the detection records is issued on re
 """
 from __future__ import annotations
 
-from collections import deque
 from typing import List, Optional
 
 from ._lib import Context, Model
@@ -36,7 +35,6 @@ class ModelReplicas:
                 self._owned.append(ctx)
             self.ctxs.append(ctx)
             self.models.append(Model(ctx, spec, max_rois=max_rois, max_h=max_h, max_w=max_w))
-        self._pending = [deque() for _ in range(n_replicas)]      # tickets in flight per replica (submit / wait API)
 
     def __len__(self):
         return len(self.models)
