@@ -242,7 +242,7 @@ def pick_cpu_threads(torch):
     dominant layers (conv3_2, fc6) at a few thread counts and keep the fastest. Returns (threads, {threads: seconds})."""
     import torch.nn.functional as F
     n = os.cpu_count() or 1
-    cands = sorted({max(min(n, 4), n >> s) for s in range(4)}, reverse=True)
+    cands = sorted({max(min(n, 4), n >> s) for s in range(6)}, reverse=True)       # nproc, /2, /4, ... /32 (never below 4)
     x, w = torch.randn(1, 256, 150, 200), torch.randn(256, 256, 3, 3)
     a, b = torch.randn(1000, 25088), torch.randn(4096, 25088)
     tried = {}
