@@ -20,10 +20,12 @@ VGG16_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M",
 
 
 class _W:
-    """weight list builder with a seeded generator"""
+    """weight list builder with a seeded generator; seed=None builds the STRUCTURE only (all-zero weights, allocated lazily:
+    for tests of layer tables / FLOP counts that never look at a weight)"""
 
-    def __init__(self, seed: int):
-        self.rng = np.random.default_rng(seed)
+    def __init__(self, seed):
+        self.skeleton = seed is None
+        self.rng = np.random.default_rng(0 if seed is None else seed)
         self.arrays: List[np.ndarray] = []
 
     def add(self, a: np.ndarray) -> int:
@@ -32,18 +34,23 @@ class _W:
 
     def conv(self, cout, cin, kh, kw, gain=1.0, bias_std=0.05) -> Tuple[int, int]:
         std = gain * np.sqrt(2.0 / (cin * kh * kw))
+        if self.skeleton:
+            return self.add(np.zeros((cout, cin, kh, kw), np.float32)), self.add(np.zeros(cout, np.float32))
         w = self.rng.standard_normal((cout, cin, kh, kw), dtype=np.float32) * np.float32(std)
         b = self.rng.standard_normal(cout, dtype=np.float32) * np.float32(bias_std)
         return self.add(w), self.add(b)
 
     def linear(self, cout, cin, std=None, zero_bias=False, bias_std=0.05) -> Tuple[int, int]:
         std = np.sqrt(2.0 / cin) if std is None else std
+        if self.skeleton:
+            return self.add(np.zeros((cout, cin), np.float32)), self.add(np.zeros(cout, np.float32))
         w = self.rng.standard_normal((cout, cin), dtype=np.float32) * np.float32(std)
         b = np.zeros(cout, np.float32) if zero_bias else self.rng.standard_normal(cout, dtype=np.float32) * np.float32(bias_std)
         return self.add(w), self.add(b)
 
     def clone(self, idx: int) -> int:
-        return self.add(self.arrays[idx].copy())
+        a = self.arrays[idx]
+        return self.add(np.zeros(a.shape, np.float32) if self.skeleton else a.copy())
 
 
 def _vgg_trunk(W: _W, width_div: int = 1, first_gain: float = 1.0 / 64.0):
