@@ -142,5 +142,11 @@ def test_tester_fast_path_wraps_without_editing_the_reference_file():
     src = _strip_lua(open(os.path.join(ROOT, "lua", "Tester_b200.lua")).read())
     assert "testOne_reference = Tester.testOne" in src and "function Tester:testOne(i)" in src
     assert "C.mpn_model_detect_nms(" in src and "return testOne_reference(self, i)" in src
+    # iterative localisation / rbox scores / voting: one device call as well, with the option struct of the header
+    assert "C.mpn_model_test_one(" in src and "ffi.new('mpn_test_opts')" in open(os.path.join(ROOT, "lua", "Tester_b200.lua")).read()
+    for field in ("num_iter", "use_rbox_scores", "bbox_voting", "score_thresh", "nms_thr", "vote_thr", "vote_score_pow"):
+        assert f"o.{field} =" in src, field
+    ffi_src = _strip_lua(open(os.path.join(ROOT, "lua", "mpn_ffi.lua")).read())
+    assert "C.mpn_ctx_create_stream(" in ffi_src and "C.mpn_ctx_create(" in ffi_src          # replica streams are opt-in
     mods = _strip_lua(open(os.path.join(ROOT, "lua", "modules_b200.lua")).read())
     assert "C.mpn_roi_pool_dev(" in mods and "C.mpn_roi_pool(" in mods   # CudaTensors stay on the device
