@@ -12,6 +12,13 @@ function Foveal:__init() parent.__init(self) end
 function Foveal:updateOutput(input)
    assert(input:nDimension() == 2)
    assert(input:size(2) == 5)
+   if torch.type(input) == 'torch.CudaTensor' then            -- stays on the device (the reference copies to the host and back)
+      local cin = input:contiguous()
+      self.output:resize(cin:size(1) * 4, 5)
+      local ctx = mpn.ctx()
+      mpn.check(ctx, C.mpn_foveal_dev(ctx, mpn.fptr(cin), cin:size(1), mpn.fptr(self.output)), 'mpn_foveal_dev')
+      return self.output
+   end
    local cin = input:float():contiguous()
    local cout = torch.FloatTensor(input:size(1) * 4, 5)
    local ctx = mpn.ctx()
@@ -26,6 +33,13 @@ function Context:__init(scale) cparent.__init(self); self.scale = scale end
 function Context:updateOutput(input)
    assert(input:nDimension() == 2)
    assert(input:size(2) == 5)
+   if torch.type(input) == 'torch.CudaTensor' then
+      local cin = input:contiguous()
+      self.output:resize(cin:size())
+      local ctx = mpn.ctx()
+      mpn.check(ctx, C.mpn_context_region_dev(ctx, mpn.fptr(cin), cin:size(1), self.scale, mpn.fptr(self.output)), 'mpn_context_region_dev')
+      return self.output
+   end
    local cin = input:float():contiguous()
    local cout = torch.FloatTensor(cin:size())
    local ctx = mpn.ctx()
@@ -48,7 +62,15 @@ end
 function BBoxNorm:updateOutput(input)
    assert(input:dim() == 2 and input:size(2) % 4 == 0)
    self.output:set(input)
-   if not self.train then
+   if not self.train and torch.type(input) == 'torch.CudaTensor' then
+      -- evaluate mode on the device: out = in .* std + mean per group of 4 (BBoxNorm.lua:24-29), no host round trip
+      self._output = self._output or input.new()
+      self._output:resize(input:size()):copy(input)
+      local m, s = self.mean:float():contiguous(), self.std:float():contiguous()
+      local ctx = mpn.ctx()
+      mpn.check(ctx, C.mpn_bbox_norm_dev(ctx, mpn.fptr(self._output), input:size(1), input:size(2), mpn.fptr(m), mpn.fptr(s)), 'mpn_bbox_norm_dev')
+      self.output = self._output
+   elseif not self.train then
       local x = input:float():contiguous()
       local m, s = self.mean:float():contiguous(), self.std:float():contiguous()
       local ctx = mpn.ctx()

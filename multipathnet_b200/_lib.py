@@ -107,6 +107,9 @@ SIGNATURES = {
     "mpn_foveal": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "mpn_context_region": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp]),
     "mpn_bbox_norm": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
+    "mpn_foveal_dev": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "mpn_context_region_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_float, _vp]),
+    "mpn_bbox_norm_dev": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp]),
     "mpn_bbox_decode": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp]),
     "mpn_roi_pool": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int64,
                                C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp]),
@@ -369,6 +372,17 @@ class Context:
         out = np.empty_like(r)
         self.check(self.lib.mpn_context_region(self.h, _ptr(r), r.shape[0], float(scale), _ptr(out)), "mpn_context_region")
         return out
+
+    # device-resident module ops (torch CUDA tensors or raw addresses in, stream-ordered, nothing copied)
+    def foveal_dev(self, rois_dev, R: int, out_dev):
+        self.check(self.lib.mpn_foveal_dev(self.h, _ptr(rois_dev), int(R), _ptr(out_dev)), "mpn_foveal_dev")
+
+    def context_region_dev(self, rois_dev, R: int, scale: float, out_dev):
+        self.check(self.lib.mpn_context_region_dev(self.h, _ptr(rois_dev), int(R), float(scale), _ptr(out_dev)), "mpn_context_region_dev")
+
+    def bbox_norm_dev(self, deltas_dev, R: int, C4: int, mean, std):
+        m, s = _f32(mean).reshape(4), _f32(std).reshape(4)
+        self.check(self.lib.mpn_bbox_norm_dev(self.h, _ptr(deltas_dev), int(R), int(C4), _ptr(m), _ptr(s)), "mpn_bbox_norm_dev")
 
     def get_images(self, im, kind: str, scale: float = 600, max_size: float = 1000):
         """getImages on the device (ImageDetect.lua:22-52): raw 3 x H0 x W0 image -> (transformed + scaled image, im_scale)"""

@@ -454,6 +454,33 @@ int mpn_context_region(mpn_ctx *ctx, const float *rois, int64_t R, float scale, 
   return unary_rois(ctx, rois, R, 1, out, mpn_context_region_launch, scale);
 }
 
+// device-resident variants (stream-ordered, no copies): what a CudaTensor nn.Module forwards through — the reference's
+// Foveal moves its input to the host and back (Foveal.lua:21-22,42); these do not
+int mpn_foveal_dev(mpn_ctx *ctx, const float *rois_dev, int64_t R, float *out_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0, "bad R");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, rois_dev && out_dev, "buffers missing");
+  return mpn_foveal_launch(ctx, rois_dev, R, out_dev);
+}
+int mpn_context_region_dev(mpn_ctx *ctx, const float *rois_dev, int64_t R, float scale, float *out_dev) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0, "bad R");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, rois_dev && out_dev, "buffers missing");
+  return mpn_context_region_launch(ctx, rois_dev, R, scale, out_dev);
+}
+int mpn_bbox_norm_dev(mpn_ctx *ctx, float *deltas_dev, int64_t R, int64_t C4, const float *mean4, const float *std4) {
+  if (!ctx) return MPN_ERR_ARG;
+  MPN_CUDA(ctx, cudaSetDevice(ctx->device));
+  MPN_CHECK_ARG(ctx, R >= 0 && C4 > 0 && C4 % 4 == 0, "BBoxNorm: input:size(2) % 4 == 0 required (BBoxNorm.lua:19)");
+  if (R == 0) return MPN_OK;
+  MPN_CHECK_ARG(ctx, deltas_dev && mean4 && std4, "buffers missing");
+  return mpn_bbox_norm_launch(ctx, deltas_dev, R, C4, mean4, std4);        // mean4 / std4 are HOST pointers (4 floats each)
+}
+
 // ------------------------------------------------------------------ getImages
 int mpn_get_images_size(int32_t H0, int32_t W0, double scale, double max_size, int32_t *h, int32_t *w, double *im_scale) {
   return mpn_get_images_size_impl(H0, W0, scale, max_size, h, w, im_scale);

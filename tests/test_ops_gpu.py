@@ -89,3 +89,26 @@ def test_roi_pool_rejects_bad_batch_index(ctx):
     fm = np.zeros((1, 8, 10, 10), np.float32)
     with pytest.raises(mpn.MpnError):
         ctx.roi_pool(fm, np.array([[3, 1, 1, 5, 5]], np.float32), 7, 7, 1.0)
+
+
+def test_module_ops_on_device_buffers_equal_the_host_entry_points(ctx):
+    """mpn_foveal_dev / mpn_context_region_dev / mpn_bbox_norm_dev (what the Lua modules call for CudaTensors: no host round
+    trip) == the host-pointer entry points above, bit for bit (same kernels), which are pinned against the oracle"""
+    import torch
+    rng = np.random.default_rng(12)
+    R = 333
+    rois = np.concatenate([np.ones((R, 1), np.float32), wl.random_boxes(R, 600, 800, 12)], 1).astype(np.float32)
+    r_d = torch.from_numpy(rois).cuda()
+    out_f = torch.empty((4 * R, 5), dtype=torch.float32, device="cuda")
+    ctx.foveal_dev(r_d, R, out_f)
+    out_c = torch.empty((R, 5), dtype=torch.float32, device="cuda")
+    ctx.context_region_dev(r_d, R, 1.5, out_c)
+    d = rng.standard_normal((R, 84)).astype(np.float32)
+    d_d = torch.from_numpy(d).cuda()
+    mean, std = np.float32([0.1, -0.2, 0.05, 0.0]), np.float32([0.1, 0.1, 0.2, 0.2])
+    ctx.bbox_norm_dev(d_d, R, 84, mean, std)
+    ctx.synchronize()
+    assert np.array_equal(out_f.cpu().numpy(), ctx.foveal(rois))
+    assert np.array_equal(out_c.cpu().numpy(), ctx.context_region(rois, 1.5))
+    assert np.array_equal(d_d.cpu().numpy(), ctx.bbox_norm(d, mean, std))
+    assert np.array_equal(out_f.cpu().numpy(), O.foveal(rois))
