@@ -154,6 +154,7 @@ void mpn_ctx_destroy(mpn_ctx *ctx) {
   if (ctx->small_dev) cudaFree(ctx->small_dev);
   if (ctx->ovf_dev) cudaFree(ctx->ovf_dev);
   if (ctx->ovf_host) cudaFreeHost(ctx->ovf_host);
+  if (ctx->u8_lut_dev) cudaFree(ctx->u8_lut_dev);
   if (ctx->sk_ws) cudaFree(ctx->sk_ws);
   if (ctx->sk_flags) cudaFree(ctx->sk_flags);
   if (ctx->tl_min) cudaFree(ctx->tl_min);

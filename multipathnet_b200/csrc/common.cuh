@@ -45,6 +45,7 @@ struct mpn_ctx {
   void *dist_comm = nullptr; int dist_rank = 0, dist_world = 1; int64_t collectives = 0;
   int own_stream = 0;              // mpn_ctx_create_stream: the ctx created (and destroys) its stream
   cudaEvent_t join_ev = nullptr;   // mpn_ctx_wait_ctx
+  float *u8_lut_dev = nullptr;     // getImages from uint8: b / 255.0f for b = 0..255 (preproc.cu)
 };
 
 enum { MPN_CAT_CONV_TC = 0, MPN_CAT_CONV_DIRECT = 1, MPN_CAT_ROI = 2, MPN_CAT_NMS = 3, MPN_CAT_ELTWISE = 4, MPN_CAT_POOL = 5, MPN_NCAT = 6 };

@@ -74,11 +74,21 @@ struct TransformedImage {
   const float *im;       // 3 x H0 x W0 fp32, RGB in [0,1] (loaders/loader.lua:79), or null with:
   const uint8_t *im_u8;  // H0 x W0 x 3 bytes, interleaved RGB as a decoder hands them over; the value is byte / 255 in fp32
                          // (what image.load(path, 3, 'float') returns), one IEEE division per sample
+  const float *lut;      // optional: lut[b] = (float)b / 255.0f for b = 0..255, the SAME correctly rounded quotients, computed once
+                         // (the kernel spent a third of its instructions in four IEEE divisions per output pixel, and a zero byte
+                         // sends div.rn down its slow path); null = divide
   int32_t H0, W0;
   Transform t;
+  MPN_HD float byte_value(uint8_t b) const {
+#if defined(__CUDA_ARCH__)
+    return lut ? __ldg(lut + b) : fdiv((float)b, 255.0f);
+#else
+    return lut ? lut[b] : fdiv((float)b, 255.0f);
+#endif
+  }
   MPN_HD float at(int c, int y, int x) const {      // selects, not indexing: the struct stays in kernel-parameter space
     const int sc = c == 0 ? t.src_chan[0] : (c == 1 ? t.src_chan[1] : t.src_chan[2]);
-    float v = im ? im[((int64_t)sc * H0 + y) * W0 + x] : fdiv((float)im_u8[((int64_t)y * W0 + x) * 3 + sc], 255.0f);
+    float v = im ? im[((int64_t)sc * H0 + y) * W0 + x] : byte_value(im_u8[((int64_t)y * W0 + x) * 3 + sc]);
     if (t.has_scale) v = fmul(v, t.scale);
     v = fadd(v, c == 0 ? t.neg_mean[0] : (c == 1 ? t.neg_mean[1] : t.neg_mean[2]));
     if (t.has_std) v = fdiv(v, c == 0 ? t.std[0] : (c == 1 ? t.std[1] : t.std[2]));

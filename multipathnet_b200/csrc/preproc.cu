@@ -35,7 +35,17 @@ static int get_images_launch_any(mpn_ctx *ctx, const float *im_dev, const uint8_
   MPN_CHECK_ARG(ctx, (im_dev || im_u8_dev) && out_dev && tf, "getImages: buffers missing");
   MPN_CHECK_ARG(ctx, H0 > 0 && W0 > 0 && h > 0 && w > 0 && h <= 65535, "getImages: bad sizes");
   mpn_img::TransformedImage I;
-  I.im = im_dev; I.im_u8 = im_u8_dev; I.H0 = H0; I.W0 = W0;
+  I.im = im_dev; I.im_u8 = im_u8_dev; I.lut = nullptr; I.H0 = H0; I.W0 = W0;
+  if (im_u8_dev) {     // byte -> float table: the 256 correctly rounded quotients b / 255.0f, divided once on the host (IEEE: same bits)
+    if (!ctx->u8_lut_dev) {
+      static float tab[256];
+      static const bool init = [] { for (int b = 0; b < 256; ++b) tab[b] = (float)b / 255.0f; return true; }();
+      (void)init;
+      MPN_CUDA(ctx, cudaMalloc((void **)&ctx->u8_lut_dev, sizeof(tab)));
+      MPN_CUDA(ctx, cudaMemcpyAsync(ctx->u8_lut_dev, tab, sizeof(tab), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    I.lut = ctx->u8_lut_dev;
+  }
   for (int c = 0; c < 3; ++c) {
     MPN_CHECK_ARG(ctx, tf->swap[c] >= 1 && tf->swap[c] <= 3, "ImageTransformer: swap entries are 1-based channel numbers");
     I.t.src_chan[c] = tf->swap[c] - 1;

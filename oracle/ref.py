@@ -252,3 +252,17 @@ def hd_get_images(im, kind, h, w):
     _hd.hd_get_images(_p(im), C.c_int(im.shape[1]), C.c_int(im.shape[2]), (C.c_int * 3)(*swap), C.c_float(scale), _p(m),
                       _p(sd) if sd is not None else None, C.c_int(h), C.c_int(w), _p(out))
     return out
+
+
+def hd_get_images_u8(im_hwc_u8, kind, h, w, use_lut=True):
+    """the same per-pixel code fed with the decoder's uint8 H0 x W0 x 3 bytes, with or without the byte -> float table"""
+    global _hd
+    if _hd is None:
+        _hd = _load(_HD)
+    im = np.ascontiguousarray(im_hwc_u8, np.uint8)
+    mean, std, scale, swap = _TRANSFORMERS[kind]
+    m = _f(mean); sd = _f(std) if std is not None else None
+    out = np.empty((3, h, w), np.float32)
+    _hd.hd_get_images_u8(im.ctypes.data_as(C.c_void_p), C.c_int(im.shape[0]), C.c_int(im.shape[1]), (C.c_int * 3)(*swap), C.c_float(scale), _p(m),
+                         _p(sd) if sd is not None else None, C.c_int(h), C.c_int(w), C.c_int(1 if use_lut else 0), _p(out))
+    return out

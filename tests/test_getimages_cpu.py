@@ -111,3 +111,20 @@ def test_getimages_golden_fixture(oracle_built):
         assert sm == s and np.array_equal(img, out)
         assert np.array_equal(oracle_built.hd_get_images(im, kind, out.shape[1], out.shape[2]), out)
     assert g["capped_out"].shape[2] == 90 and g["same_cfg"][2] == 1.0
+
+
+@pytest.mark.parametrize("kind", ["ross", "imagenet"])
+@pytest.mark.parametrize("H0,W0,scale,max_size", [(48, 64, 60, 100), (75, 50, 60, 70), (40, 40, 40, 100)])
+def test_u8_source_table_equals_the_division(oracle_built, H0, W0, scale, max_size, kind):
+    """the uint8 path's byte -> float table (what the kernel reads since round 2) holds the same correctly rounded quotients as the
+    per-sample IEEE division it replaces, and both equal the fp32 path fed with byte / 255: bit for bit, growing and shrinking"""
+    O = oracle_built
+    rng = np.random.default_rng(H0 + W0)
+    im_u8 = rng.integers(0, 256, (H0, W0, 3), dtype=np.uint8)
+    im_u8[:3, :5] = 0; im_u8[-2:, -4:] = 255
+    h, w, _ = O.get_images_size(H0, W0, scale, max_size)
+    a = O.hd_get_images_u8(im_u8, kind, h, w, use_lut=True)
+    b = O.hd_get_images_u8(im_u8, kind, h, w, use_lut=False)
+    assert np.array_equal(a, b)
+    im_f = np.ascontiguousarray(im_u8.transpose(2, 0, 1)).astype(np.float32) / np.float32(255.0)
+    assert np.array_equal(a, O.hd_get_images(im_f, kind, h, w))
